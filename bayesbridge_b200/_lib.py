@@ -1,0 +1,178 @@
+"""ctypes binding of libbbgpu.so (the C-ABI declared in include/bbgpu.h).
+
+There is no CPU fallback: if the shared library is missing or no B200 is visible, every
+compute entry point raises.  Importing this module never touches the GPU.
+"""
+import ctypes
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libbbgpu.so')
+
+c_int, c_i64, c_u64, c_dbl = ctypes.c_int, ctypes.c_int64, ctypes.c_uint64, ctypes.c_double
+c_void_p, c_char_p = ctypes.c_void_p, ctypes.c_char_p
+P_dbl = ctypes.POINTER(c_dbl)
+P_i32 = ctypes.POINTER(ctypes.c_int32)
+P_int = ctypes.POINTER(c_int)
+P_i64 = ctypes.POINTER(c_i64)
+
+# name -> (restype, argtypes); mirrors include/bbgpu.h one to one
+SIGNATURES = {
+    'bb_last_error': (c_char_p, []),
+    'bb_version': (c_int, []),
+    'bb_device_count': (c_int, [P_int]),
+    'bb_init': (c_int, [c_int, ctypes.POINTER(c_void_p)]),
+    'bb_destroy': (c_int, [c_void_p]),
+    'bb_set_option': (c_int, [c_void_p, c_char_p, c_i64]),
+    'bb_get_option': (c_int, [c_void_p, c_char_p, P_i64]),
+    'bb_get_launch_count': (c_int, [c_void_p, P_i64]),
+    'bb_reset_launch_count': (c_int, [c_void_p]),
+    'bb_sync': (c_int, [c_void_p]),
+    'bb_comm_unique_id': (c_int, [c_char_p, ctypes.c_char_p]),
+    'bb_comm_init': (c_int, [c_void_p, c_char_p, c_int, c_int, c_char_p]),
+    'bb_comm_allreduce_host': (c_int, [c_void_p, P_dbl, c_i64]),
+    'bb_csr_upload': (c_int, [c_void_p, c_i64, c_i64, c_i64, P_i32, P_i32, P_dbl, P_dbl, c_int, c_i64, c_i64,
+                              ctypes.POINTER(c_void_p)]),
+    'bb_dense_upload': (c_int, [c_void_p, c_i64, c_i64, P_dbl, P_dbl, c_int, c_i64, c_i64, ctypes.POINTER(c_void_p)]),
+    'bb_mat_free': (c_int, [c_void_p]),
+    'bb_mat_info': (c_int, [c_void_p, P_i64, P_i64, P_i64, P_int, P_int]),
+    'bb_mat_export_csr': (c_int, [c_void_p, P_i32, P_i32, P_dbl]),
+    'bb_mat_export_csc': (c_int, [c_void_p, P_i32, P_i32, P_dbl]),
+    'bb_dot': (c_int, [c_void_p, P_dbl, P_dbl]),
+    'bb_tdot': (c_int, [c_void_p, P_dbl, P_dbl]),
+    'bb_fisher_diag': (c_int, [c_void_p, P_dbl, P_dbl]),
+    'bb_set_outcome': (c_int, [c_void_p, P_dbl, P_dbl]),
+    'bb_set_obs_prec': (c_int, [c_void_p, P_dbl]),
+    'bb_set_obs_prec_scalar': (c_int, [c_void_p, c_dbl]),
+    'bb_get_obs_prec': (c_int, [c_void_p, P_dbl]),
+    'bb_get_linear_predictor': (c_int, [c_void_p, P_dbl]),
+    'bb_cg_sample': (c_int, [c_void_p, P_dbl, P_dbl, P_dbl, P_dbl, P_dbl, c_dbl, c_int, c_int, P_dbl, P_dbl,
+                             c_u64, c_u64, P_dbl, P_int, P_int, P_dbl]),
+    'bb_pg_sample': (c_int, [c_void_p, c_i64, P_i32, P_dbl, c_u64, c_u64, c_i64, P_dbl]),
+    'bb_pg_from_coef': (c_int, [c_void_p, P_dbl, c_u64, c_u64, P_dbl, P_dbl]),
+    'bb_linear_rss': (c_int, [c_void_p, P_dbl, P_dbl]),
+    'bb_tilted_stable_sample': (c_int, [c_void_p, c_i64, c_dbl, P_dbl, c_u64, c_u64, c_i64, P_dbl]),
+    'bb_philox_normal': (c_int, [c_void_p, c_i64, c_int, c_u64, c_u64, c_i64, P_dbl]),
+    'bb_time_kernel': (c_int, [c_void_p, c_char_p, c_int, c_int, P_dbl]),
+}
+
+BB_NOISE_INJECT, BB_NOISE_PHILOX = 0, 1
+
+_lib = None
+
+
+def load():
+    """Load libbbgpu.so (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "libbbgpu.so not found at {}: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `make -C bayesbridge_b200/csrc`. There is no CPU fallback.".format(LIB_PATH))
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().bb_last_error()
+        raise RuntimeError("libbbgpu: " + (msg.decode() if msg else "error {}".format(rc)))
+
+
+def dptr(a):
+    """Pointer to a C-contiguous float64 array (None -> NULL)."""
+    if a is None:
+        return None
+    assert a.dtype == np.float64 and a.flags['C_CONTIGUOUS']
+    return a.ctypes.data_as(P_dbl)
+
+
+def iptr(a):
+    if a is None:
+        return None
+    assert a.dtype == np.int32 and a.flags['C_CONTIGUOUS']
+    return a.ctypes.data_as(P_i32)
+
+
+def as_f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def nccl_library_path():
+    """Path of the NCCL shared object bundled with torch (falls back to the system one)."""
+    try:
+        import nvidia.nccl
+        cand = os.path.join(list(nvidia.nccl.__path__)[0], 'lib', 'libnccl.so.2')
+        if os.path.exists(cand):
+            return cand
+    except Exception:
+        pass
+    return 'libnccl.so.2'
+
+
+class Context:
+    """One GPU + one stream (+ an optional communicator over the ranks of a torchrun job)."""
+
+    _default = None
+
+    def __init__(self, device=None):
+        lib = load()
+        if device is None:
+            device = int(os.environ.get('LOCAL_RANK', '0'))
+        handle = c_void_p()
+        check(lib.bb_init(int(device), ctypes.byref(handle)))
+        self.handle = handle
+        self.device = int(device)
+        self.nranks, self.rank = 1, 0
+
+    @classmethod
+    def default(cls):
+        if cls._default is None:
+            cls._default = cls()
+        return cls._default
+
+    def set_option(self, name, value):
+        check(load().bb_set_option(self.handle, name.encode(), int(value)))
+
+    def get_option(self, name):
+        v = c_i64()
+        check(load().bb_get_option(self.handle, name.encode(), ctypes.byref(v)))
+        return v.value
+
+    def launch_count(self):
+        v = c_i64()
+        check(load().bb_get_launch_count(self.handle, ctypes.byref(v)))
+        return v.value
+
+    def reset_launch_count(self):
+        check(load().bb_reset_launch_count(self.handle))
+
+    def init_comm_from_torch(self):
+        """Attach an NCCL communicator spanning the ranks of the current torch.distributed job.
+
+        torch.distributed is only the plumbing that carries the 128-byte NCCL unique id from rank 0
+        to the other ranks; the allreduces themselves are issued by libbbgpu on its own stream."""
+        import torch.distributed as dist
+        if not dist.is_initialized() or dist.get_world_size() == 1:
+            return
+        lib = load()
+        rank, world = dist.get_rank(), dist.get_world_size()
+        path = nccl_library_path().encode()
+        buf = ctypes.create_string_buffer(128)
+        if rank == 0:
+            check(lib.bb_comm_unique_id(path, buf))
+        box = [bytes(buf.raw)]
+        dist.broadcast_object_list(box, src=0)
+        check(lib.bb_comm_init(self.handle, path, world, rank, box[0]))
+        self.nranks, self.rank = world, rank
+
+    def allreduce_host(self, arr):
+        arr = as_f64(arr)
+        check(load().bb_comm_allreduce_host(self.handle, dptr(arr), arr.size))
+        return arr

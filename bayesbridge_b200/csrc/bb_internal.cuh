@@ -1,0 +1,261 @@
+// Internal declarations shared by the translation units of libbbgpu.so.  Not part of the ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string.h>
+#include <math.h>
+#include "../../include/bbgpu.h"
+
+typedef long long i64;
+
+void bb_set_error(const char* fmt, ...);
+
+#define BB_CUDA(expr)                                                                      \
+    do {                                                                                   \
+        cudaError_t e_ = (expr);                                                           \
+        if (e_ != cudaSuccess) {                                                           \
+            bb_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e_)); \
+            return BB_ERR_CUDA;                                                            \
+        }                                                                                  \
+    } while (0)
+
+#define BB_TRY(expr)                                                                       \
+    do {                                                                                   \
+        int rc_ = (expr);                                                                  \
+        if (rc_ != BB_OK) return rc_;                                                      \
+    } while (0)
+
+#define BB_ARG(cond, msg)                                                                  \
+    do {                                                                                   \
+        if (!(cond)) {                                                                     \
+            bb_set_error("%s:%d: invalid argument: %s", __FILE__, __LINE__, msg);          \
+            return BB_ERR_ARG;                                                             \
+        }                                                                                  \
+    } while (0)
+
+// counts a kernel launch and checks the launch error
+#define BB_LAUNCHED(ctx)                                                                   \
+    do {                                                                                   \
+        (ctx)->launches++;                                                                 \
+        cudaError_t e_ = cudaPeekAtLastError();                                            \
+        if (e_ != cudaSuccess) {                                                           \
+            bb_set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e_)); \
+            return BB_ERR_CUDA;                                                            \
+        }                                                                                  \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+struct bb_ctx {
+    int device;
+    cudaStream_t stream;
+    int sm_count;
+    size_t smem_optin;     // max dynamic shared memory per block (opt-in)
+    i64 launches;
+    // options
+    i64 opt_spmv_stage;    // 1: stage the gather vector in shared memory; 0: gather through L2
+    i64 opt_slab_width;    // max doubles of the gather vector staged per CTA (0 = auto)
+    i64 opt_cg_chunk;      // CG iterations enqueued between host checks (0 = adaptive)
+    i64 opt_use_graph;     // capture the CG iteration chunk into a CUDA graph
+    // communicator (NCCL via dlopen)
+    void* nccl_handle;
+    void* nccl_comm;
+    int nranks, rank;
+    // L2 flush scratch for bb_time_kernel
+    void* flush_buf;
+    size_t flush_bytes;
+    // generic host pinned staging
+    double* pinned;
+    size_t pinned_bytes;
+};
+
+int bb_ctx_pinned(bb_ctx* ctx, size_t bytes, double** out);
+int bb_allreduce_dev(bb_ctx* ctx, double* dbuf, i64 count);   // in place, on ctx->stream
+
+// ------------------------------------------------------------------------------------------
+// Slab format: the nnz of a compressed (CSR or CSC) matrix regrouped so that every contiguous
+// run of nnz gathers from one <=W-wide window of the input vector (a "slab"), which one CTA
+// stages in shared memory.  Virtual segment v = slab * n_seg + seg.
+struct TileMeta { int start, end, vlo, vhi; };   // nnz range; owns virtual segments [vlo, vhi)
+struct WorkUnit { int slab, tile_lo, tile_hi, pad; };
+
+struct SlabFmt {
+    int   nslab;
+    i64   n_seg;        // rows (dot format) or columns (Tdot format)
+    i64   n_gather;     // length of the gathered vector
+    int   W;            // slab width (gather indices [slab*W, slab*W+W))
+    i64   nnz;
+    int*  ptr;          // [nslab*n_seg + 1] nnz offsets of the virtual segments
+    int*  idx;          // [nnz] gather index (global)
+    double* val;        // [nnz] or NULL (pattern-only)
+    bool  owns_arrays;  // false when aliasing the canonical CSR/CSC (nslab == 1)
+    int   ntiles;
+    TileMeta* tiles;    // [ntiles]
+    int*  head_seg;     // [ntiles] virtual segment continued from the previous tile, or -1
+    int   nunits;
+    WorkUnit* units;    // [nunits] one CTA each
+    double* part;       // [nslab*n_seg] per-slab partial sums (output of the kernel)
+    double* head_part;  // [ntiles]
+};
+
+struct CgScalars {
+    double rho[2];
+    double atol_eff;
+    double bnorm;
+    double rnorm;
+    int    iter;      // completed CG iterations
+    int    done;      // 0 running, 1 converged, 2 maxiter reached, 3 zero right-hand side
+    int    maxiter;
+    int    pad;
+};
+
+struct bb_mat {
+    bb_ctx* ctx;
+    int  is_sparse, is_binary, add_intercept, centered;
+    i64  n, p, P, nnz;          // local rows, predictors, P = p + intercept
+    i64  row_offset, n_global;
+    // canonical storage (bit-exact images of scipy's arrays)
+    int *csr_ptr, *csr_idx; double* csr_val;
+    int *csc_ptr, *csc_idx; double* csc_val;
+    SlabFmt fdot, ftdot;
+    double* col_offset;         // [p] (zeros when not centred)
+    // dense storage: row-major [n x p], raw (no intercept / centring)
+    double* Xd;
+    // resident n-vectors
+    double *omega, *n_trial, *n_success, *eta, *w_n, *u_n, *eps_n;
+    int has_outcome, is_linear;
+    double omega_scalar; int use_omega_scalar;   // linear model: omega = scalar * 1_n
+    // P-vectors
+    double *v_P, *sv, *traw /*[1+p]*/, *t_P, *x, *r, *pvec, *q, *b, *s, *D, *pps, *z, *x0, *eps_P, *out_P;
+    // reduction scratch
+    double* red;                // [RED_SLOTS * RED_MAX]
+    CgScalars* cg;              // device
+    CgScalars* cg_host;         // pinned
+    int last_n_iter;
+    cudaGraphExec_t cg_graph; int cg_graph_launches;   // kernels per captured CG iteration
+    int nred_w;                 // number of valid partials in red[RED_W]
+    // dense Tdot partials [dense_nblk x p]
+    double* dense_part; int dense_nblk;
+    // cached z = X' kappa for the logit model (kappa = n_success - n_trial/2 is constant)
+    double* zk; int zk_valid;
+};
+
+enum { RED_MAX = 1024, RED_SLOTS = 8 };
+enum { RED_SHIFT = 0, RED_W = 1, RED_PQ = 2, RED_RR = 3, RED_BB = 4, RED_MISC = 5, RED_X0 = 6, RED_LL = 7 };
+
+// device-side op pipeline (all on ctx->stream, no sync)
+//   sv_shift: computes mat->sv (gather vector, p entries) and the shift partials from a P-vector
+int bb_op_prepare(bb_mat* m, const double* vP, const double* scale /*nullable*/);
+//   u_n = X sv + shift  (mode 0) ;  w_n = omega .* u_n with sum(w) partials (mode 1)
+int bb_op_dot(bb_mat* m, int mode);
+//   traw[0] = sum(w_n), traw[1+j] = (X' w_n)_j ; allreduced over shards
+int bb_op_tdot(bb_mat* m, const double* w);
+//   t_P from traw (intercept + centring)
+int bb_op_tdot_finish(bb_mat* m, double* tP);
+
+int bb_op_prepare_flag(bb_mat* m, const double* vP, const double* scale, const int* done_flag);
+int bb_op_dot_flag(bb_mat* m, int mode, const int* done_flag);
+int bb_op_tdot_flag(bb_mat* m, const double* w, bool have_w_partials, const int* done_flag);
+int bb_mat_alloc_work(bb_mat* m);
+
+int bb_slab_free(SlabFmt* f);
+
+// ------------------------------------------------------------------------------------------
+// device helpers
+#ifdef __CUDACC__
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// deterministic block sum; result valid in every thread. blockDim.x multiple of 32, <= 1024.
+__device__ __forceinline__ double block_sum(double v, double* sm32 /* >= 33 doubles */) {
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) sm32[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        double t = (lane < nw) ? sm32[lane] : 0.0;
+        t = warp_sum(t);
+        if (lane == 0) sm32[32] = t;
+    }
+    __syncthreads();
+    return sm32[32];
+}
+
+// fixed-order sum of `count` partials by one warp (all 32 lanes must call); result in all lanes
+__device__ __forceinline__ double warp_sum_partials(const double* buf, int count) {
+    int lane = threadIdx.x & 31;
+    double t = 0.0;
+    for (int i = lane; i < count; i += 32) t += buf[i];
+    return warp_sum(t);
+}
+
+// ---- Philox4x32-10 (Salmon et al. 2011), counter-based ----
+struct Philox {
+    uint32_t c[4];
+    uint32_t k[2];
+};
+
+__host__ __device__ __forceinline__ void philox_round(uint32_t c[4], uint32_t k0, uint32_t k1) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+    uint64_t p0 = (uint64_t)M0 * c[0];
+    uint64_t p1 = (uint64_t)M1 * c[2];
+    uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+    uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+    uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+}
+
+__host__ __device__ __forceinline__ void philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    uint32_t c[4] = {ctr[0], ctr[1], ctr[2], ctr[3]};
+    uint32_t k0 = key[0], k1 = key[1];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        philox_round(c, k0, k1);
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
+}
+
+// A per-element random stream: element `index` of call `offset` of stream `stream_id` under `seed`.
+// Each refill consumes one counter value and yields two 53-bit uniforms in (0,1).
+struct RandStream {
+    uint32_t ctr[4];
+    uint32_t key[2];
+    double   spare;
+    int      has_spare;
+    __host__ __device__ void init(uint64_t seed, uint64_t offset, uint64_t index, uint32_t stream_id) {
+        key[0] = (uint32_t)seed; key[1] = (uint32_t)(seed >> 32);
+        ctr[0] = (uint32_t)index;
+        ctr[1] = (uint32_t)offset;
+        ctr[2] = 0u;                                  // draw counter
+        ctr[3] = (stream_id << 24) | ((uint32_t)((index >> 32) & 0xFFu) << 16) | (uint32_t)((offset >> 32) & 0xFFFFu);
+        has_spare = 0; spare = 0.0;
+    }
+    __host__ __device__ double uniform() {
+        if (has_spare) { has_spare = 0; return spare; }
+        uint32_t o[4];
+        philox4x32_10(ctr, key, o);
+        ctr[2] += 1u;
+        uint64_t a = (((uint64_t)o[0] << 32) | o[1]) >> 11;
+        uint64_t b = (((uint64_t)o[2] << 32) | o[3]) >> 11;
+        spare = ((double)b + 0.5) * (1.0 / 9007199254740992.0);
+        has_spare = 1;
+        return ((double)a + 0.5) * (1.0 / 9007199254740992.0);
+    }
+    // Box-Muller; consumes exactly two uniforms, returns one normal (the sine branch is dropped so
+    // that the stream position after a normal does not depend on caching).
+    __host__ __device__ double normal() {
+        double u1 = uniform(), u2 = uniform();
+        return sqrt(-2.0 * log(u1)) * cos(6.283185307179586476925286766559 * u2);
+    }
+};
+
+enum { STREAM_EPS1 = 0, STREAM_EPS2 = 1, STREAM_PG = 2, STREAM_TS = 3 };
+
+#endif  // __CUDACC__

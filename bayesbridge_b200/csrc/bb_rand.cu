@@ -1,0 +1,453 @@
+// Device random variates: Polya-Gamma (reference: bayesbridge/random/polya_gamma/polya_gamma.pyx:40-216,
+// log_ndtr from scipy_ndtr.c:367-396), exponentially tilted stable (tilted_stable.pyx:65-332) and the
+// Gaussian streams of the CG right-hand side.  One thread per variate; each variate owns a
+// counter-based Philox4x32-10 stream keyed by (seed, call offset, GLOBAL element index, stream id),
+// so results do not depend on how rows are sharded across GPUs and a chain can be resumed from
+// (seed, offset) alone.
+#include "bb_internal.cuh"
+
+#define BB_PI 3.14159265358979323846264338327950288
+
+// ---- log of the standard normal CDF, three regimes as in scipy_ndtr.c:367-396 ----------------
+__device__ double dev_log_ndtr(double a) {
+    if (a > 6.0) return -normcdf(-a);           // log(1 - eps) ~ -eps
+    if (a > -20.0) return log(normcdf(a));
+    double log_lhs = -0.5 * a * a - log(-a) - 0.5 * log(2.0 * BB_PI);
+    double last_total = 0.0, rhs = 1.0, numerator = 1.0, denom_factor = 1.0, denom_cons = 1.0 / (a * a);
+    double sign = 1.0;
+    long i = 0;
+    while (fabs(last_total - rhs) > 2.2204460492503131e-16) {
+        i += 1;
+        last_total = rhs;
+        sign = -sign;
+        denom_factor *= denom_cons;
+        numerator *= (double)(2 * i - 1);
+        rhs += sign * numerator * denom_factor;
+    }
+    return log_lhs + log(rhs);
+}
+
+// ---- Polya-Gamma ------------------------------------------------------------------------------
+#define PG_T 0.63661977236758134308   /* 2/pi: where the two series representations meet */
+#define PG_MAX_TERMS 100
+
+// a_n(x): terms of the alternating series, Polson-Scott-Windle (2013) eq. (12)-(13)
+__device__ __forceinline__ double pg_series_term(int n, double x) {
+    double nh = (double)n + 0.5;
+    double lr = log(BB_PI * nh);
+    if (x <= PG_T) lr += -1.5 * log(0.5 * x * BB_PI) - 2.0 * nh * nh / x;
+    else lr += -0.5 * x * BB_PI * BB_PI * nh * nh;
+    return exp(lr);
+}
+
+__device__ double pg_prob_right(double z, double K) {
+    double lm_expo = -log(K) - K * PG_T + log(0.25 * BB_PI);
+    double st = sqrt(PG_T);
+    double lm_ig1 = -z + dev_log_ndtr((PG_T * z - 1.0) / st);
+    double lm_ig2 = z + dev_log_ndtr(-(PG_T * z + 1.0) / st);
+    double ratio = exp(lm_ig1 - lm_expo) + exp(lm_ig2 - lm_expo);
+    return 1.0 / (1.0 + ratio);
+}
+
+// inverse Gaussian(mean 1/z, shape 1) restricted to (0, t)
+__device__ double pg_trunc_invgauss(RandStream& rs, double z) {
+    double X;
+    double mean = 1.0 / z;
+    if (mean > PG_T) {
+        // 1/chi^2_1 restricted to (0, t) as proposal; accept with exp(-z^2 X / 2)
+        for (;;) {
+            double E;
+            for (;;) {   // chi^2_1 left-truncated at 1/t: shifted Exp(2) proposal
+                E = 0.5 * BB_PI - 2.0 * log(1.0 - rs.uniform());
+                if (rs.uniform() <= sqrt(0.5 * BB_PI / E)) break;
+            }
+            X = 1.0 / E;
+            if (log(rs.uniform()) < -0.5 * X * z * z) break;
+        }
+    } else {
+        for (;;) {   // Michael-Schucany-Haas, repeated until it lands below t
+            double N = rs.normal();
+            double V = N * N;
+            X = mean + 0.5 * mean * (mean * V - sqrt(4.0 * mean * V + mean * mean * V * V));
+            if (rs.uniform() > mean / (mean + X)) X = mean * mean / X;
+            if (X < PG_T) break;
+        }
+    }
+    return X;
+}
+
+// J*(1, z): Devroye's alternating-series rejection sampler
+__device__ double pg_tilted_jacobi(RandStream& rs, double z) {
+    const double K = 0.5 * z * z + 0.125 * BB_PI * BB_PI;
+    const double p_right = pg_prob_right(z, K);
+    for (;;) {
+        double X;
+        if (rs.uniform() < p_right) X = PG_T - log(1.0 - rs.uniform()) / K;
+        else X = pg_trunc_invgauss(rs, z);
+        const double a0 = pg_series_term(0, X);
+        const double U = rs.uniform() * a0;
+        double partial = a0;
+        int n = 1;
+        double sign = -1.0;
+        for (;;) {
+            partial += sign * pg_series_term(n, X);
+            n += 1;
+            if (sign < 0.0) { if (U <= partial) return X; }
+            else {
+                if (U > partial) break;                 // rejected
+                if (n >= PG_MAX_TERMS) return X;        // lower bound taken as the target
+            }
+            sign = -sign;
+        }
+    }
+}
+
+__device__ double pg_draw(RandStream& rs, int shape, double tilt) {
+    const double z = 0.5 * fabs(tilt);
+    double acc = 0.0;
+    for (int j = 0; j < shape; ++j) acc += 0.25 * pg_tilted_jacobi(rs, z);
+    return acc;
+}
+
+__global__ void k_pg_sample(i64 n, const int* __restrict__ shape, const double* __restrict__ shape_d,
+                            const double* __restrict__ tilt, uint64_t seed, uint64_t offset, i64 index_offset,
+                            double* __restrict__ out) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    RandStream rs;
+    rs.init(seed, offset, (uint64_t)(index_offset + i), STREAM_PG);
+    int b = shape ? shape[i] : (int)shape_d[i];
+    out[i] = pg_draw(rs, b, tilt[i]);
+}
+
+// fused: omega_i ~ PG(n_trial_i, eta_i) and the logistic log-likelihood terms
+__global__ void k_pg_loglik(i64 n, const double* __restrict__ n_trial, const double* __restrict__ n_success,
+                            const double* __restrict__ eta, uint64_t seed, uint64_t offset, i64 index_offset,
+                            double* __restrict__ omega, double* __restrict__ red_ll) {
+    __shared__ double sm[33];
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    double ll = 0.0;
+    if (i < n) {
+        RandStream rs;
+        rs.init(seed, offset, (uint64_t)(index_offset + i), STREAM_PG);
+        double e = eta[i], nt = n_trial[i];
+        omega[i] = pg_draw(rs, (int)nt, e);
+        // logistic_model.py:52-55   n_success*eta - n_trial*logaddexp(0, eta)
+        double lae = (e > 0.0) ? e + log1p(exp(-e)) : log1p(exp(e));
+        ll = n_success[i] * e - nt * lae;
+    }
+    ll = block_sum(ll, sm);
+    if (threadIdx.x == 0) red_ll[blockIdx.x] = ll;
+}
+
+// ---- exponentially tilted stable ---------------------------------------------------------------
+__device__ __forceinline__ double ts_sinc(double x) {
+    if (fabs(x) < 0.01) { double x2 = x * x; return 1.0 - x2 / 6.0 * (1.0 - x2 / 20.0); }
+    return sin(x) / x;
+}
+__device__ double ts_zolotarev(double x, double al) {
+    double v = pow((1.0 - al) * ts_sinc((1.0 - al) * x), 1.0 - al) * pow(al * ts_sinc(al * x), al) / ts_sinc(x);
+    return pow(v, 1.0 / (1.0 - al));
+}
+__device__ double ts_zolotarev_pdf_exp(double x, double al) {
+    double den = pow(ts_sinc(al * x), al) * pow(ts_sinc((1.0 - al) * x), 1.0 - al);
+    return ts_sinc(x) / den;
+}
+
+__device__ double ts_divide_conquer(RandStream& rs, double al, double tilt) {
+    double tp = floor(pow(tilt, al));
+    long m = (tp >= 1.0) ? (long)tp : 1;
+    double c = pow(1.0 / (double)m, 1.0 / al);
+    double X = 0.0;
+    for (long i = 0; i < m; ++i) {
+        double S;
+        for (;;) {
+            double u1 = rs.uniform(), u2 = rs.uniform();
+            S = c * pow(-ts_zolotarev(BB_PI * u1, al) / log(u2), (1.0 - al) / al);
+            if (rs.uniform() < exp(-tilt * S)) break;
+        }
+        X += S;
+    }
+    return X;
+}
+
+__device__ double ts_double_rejection(RandStream& rs, double al, double tilt) {
+    const double b = pow(tilt, al);
+    const double gam = b * al * (1.0 - al);
+    const double sg = sqrt(gam);
+    const double c2 = 2.0 + sqrt(0.5 * BB_PI);
+    const double xi = (1.0 + sqrt(2.0 * gam) * c2) / BB_PI;
+    const double psi = sqrt(gam / BB_PI) * c2 * exp(-gam * BB_PI * BB_PI / 8.0);
+    const double w1 = sqrt(0.5 * BB_PI / gam) * xi, w2 = 2.0 * sqrt(BB_PI) * psi, w3 = xi * BB_PI;
+    const double odds = (1.0 - al) / al;
+    for (;;) {
+        // auxiliary variable U (and V, z)
+        double U, V, z;
+        for (;;) {
+            double Vs = rs.uniform();
+            if (gam >= 1.0) {
+                if (Vs < w1 / (w1 + w2)) U = fabs(rs.normal()) / sg;
+                else { double W = rs.uniform(); U = BB_PI * (1.0 - W * W); }
+            } else {
+                double W = rs.uniform();
+                if (Vs < w3 / (w2 + w3)) U = BB_PI * W;
+                else U = BB_PI * (1.0 - W * W);
+            }
+            if (U > BB_PI) continue;
+            double zeta = sqrt(ts_zolotarev_pdf_exp(U, al));
+            z = 1.0 / (1.0 - pow(1.0 + al * zeta / sg, -1.0 / al));
+            double inv = BB_PI * exp(-b * (1.0 - 1.0 / (zeta * zeta))) / ((1.0 + sqrt(0.5 * BB_PI)) * sg / zeta + z);
+            double d = 0.0;
+            if (U >= 0.0 && gam >= 1.0) d += xi * exp(-gam * U * U / 2.0);
+            if (U > 0.0 && U < BB_PI) d += psi / sqrt(BB_PI - U);
+            if (U >= 0.0 && U <= BB_PI && gam < 1.0) d += xi;
+            inv *= d;
+            double accept_prob = 1.0 / inv;
+            if (accept_prob > 0.0) {
+                V = rs.uniform() / accept_prob;
+                if (U < BB_PI && V <= 1.0) break;
+            }
+        }
+        // reference variable X given U
+        double a = ts_zolotarev(U, al);
+        double left = pow(odds / a, al) * b;
+        double delta = sqrt(left * al / a);
+        double right = left + delta;
+        double m_left = delta * sqrt(0.5 * BB_PI), m_mid = delta, m_right = z / a;
+        double total = m_left + m_mid + m_right;
+        double Vr = rs.uniform();
+        double N = 0.0, E = 0.0, X;
+        if (Vr < m_left / total) { N = rs.normal(); X = left - delta * fabs(N); }
+        else if (Vr < (m_left + m_mid) / total) X = left + delta * rs.uniform();
+        else { E = -log(rs.uniform()); X = right + E * m_right; }
+        double lacc;
+        if (X < 0.0) lacc = -INFINITY;
+        else {
+            lacc = -(a * (X - left) + exp(log(b) / al - odds * log(left)) * (pow(left / X, odds) - 1.0));
+            if (X < left) lacc += N * N / 2.0;
+            else if (X > right) lacc += E;
+        }
+        if (lacc > log(V)) return pow(X, -odds);
+    }
+}
+
+__global__ void k_tilted_stable(i64 n, double al, const double* __restrict__ tilt, uint64_t seed, uint64_t offset,
+                                i64 index_offset, double* __restrict__ out) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    RandStream rs;
+    rs.init(seed, offset, (uint64_t)(index_offset + i), STREAM_TS);
+    double t = tilt[i];
+    // tilted_stable.pyx:103-108: divide-and-conquer is cheaper while tilt^alpha < 2
+    out[i] = (pow(t, al) < 2.0) ? ts_divide_conquer(rs, al, t) : ts_double_rejection(rs, al, t);
+}
+
+__global__ void k_philox_normal(i64 n, int stream, uint64_t seed, uint64_t offset, i64 index_offset, double* __restrict__ out) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    RandStream rs;
+    rs.init(seed, offset, (uint64_t)(index_offset + i), (uint32_t)stream);
+    out[i] = rs.normal();
+}
+
+__global__ void k_rss(i64 n, const double* __restrict__ y, const double* __restrict__ eta, double* __restrict__ red) {
+    __shared__ double sm[33];
+    double acc = 0.0;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        double d = y[i] - eta[i];
+        acc += d * d;
+    }
+    acc = block_sum(acc, sm);
+    if (threadIdx.x == 0) red[blockIdx.x] = acc;
+}
+
+__global__ void k_finish_scalar(const double* __restrict__ red, int nred, double* __restrict__ out) {
+    double s = warp_sum_partials(red, nred);
+    if (threadIdx.x == 0) out[0] = s;
+}
+
+// ---- host entry points -------------------------------------------------------------------------
+static int scratch_vec(bb_ctx* ctx, void** d, size_t bytes) {
+    BB_CUDA(cudaMalloc(d, bytes ? bytes : 1));
+    return BB_OK;
+}
+
+extern "C" int bb_pg_sample(bb_ctx* ctx, int64_t n, const int32_t* shape, const double* tilt,
+                            uint64_t seed, uint64_t offset, int64_t index_offset, double* out) {
+    BB_ARG(ctx && n >= 0, "ctx/n");
+    if (n == 0) return BB_OK;
+    BB_ARG(shape && tilt && out, "null pointer");
+    for (i64 i = 0; i < n; ++i) BB_ARG(shape[i] >= 0, "shape must be non-negative");
+    BB_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    int* d_shape = nullptr; double *d_tilt = nullptr, *d_out = nullptr;
+    BB_TRY(scratch_vec(ctx, (void**)&d_shape, (size_t)n * sizeof(int)));
+    BB_TRY(scratch_vec(ctx, (void**)&d_tilt, (size_t)n * sizeof(double)));
+    BB_TRY(scratch_vec(ctx, (void**)&d_out, (size_t)n * sizeof(double)));
+    int rc = BB_OK;
+    cudaError_t e;
+    e = cudaMemcpyAsync(d_shape, shape, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_tilt, tilt, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        k_pg_sample<<<(int)((n + 127) / 128), 128, 0, st>>>(n, d_shape, nullptr, d_tilt, seed, offset, index_offset, d_out);
+        ctx->launches++;
+        e = cudaPeekAtLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { bb_set_error("bb_pg_sample: %s", cudaGetErrorString(e)); rc = BB_ERR_CUDA; }
+    cudaFree(d_shape); cudaFree(d_tilt); cudaFree(d_out);
+    return rc;
+}
+
+extern "C" int bb_tilted_stable_sample(bb_ctx* ctx, int64_t n, double char_exp, const double* tilt,
+                                       uint64_t seed, uint64_t offset, int64_t index_offset, double* out) {
+    BB_ARG(ctx && n >= 0, "ctx/n");
+    if (n == 0) return BB_OK;
+    BB_ARG(tilt && out, "null pointer");
+    BB_ARG(char_exp > 0.0 && char_exp < 1.0, "characteristic exponent must be in (0,1)");
+    BB_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    double *d_tilt = nullptr, *d_out = nullptr;
+    BB_TRY(scratch_vec(ctx, (void**)&d_tilt, (size_t)n * sizeof(double)));
+    BB_TRY(scratch_vec(ctx, (void**)&d_out, (size_t)n * sizeof(double)));
+    int rc = BB_OK;
+    cudaError_t e = cudaMemcpyAsync(d_tilt, tilt, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        k_tilted_stable<<<(int)((n + 127) / 128), 128, 0, st>>>(n, char_exp, d_tilt, seed, offset, index_offset, d_out);
+        ctx->launches++;
+        e = cudaPeekAtLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { bb_set_error("bb_tilted_stable_sample: %s", cudaGetErrorString(e)); rc = BB_ERR_CUDA; }
+    cudaFree(d_tilt); cudaFree(d_out);
+    return rc;
+}
+
+extern "C" int bb_philox_normal(bb_ctx* ctx, int64_t n, int stream, uint64_t seed, uint64_t offset,
+                                int64_t index_offset, double* out) {
+    BB_ARG(ctx && n >= 0 && (n == 0 || out), "ctx/n/out");
+    if (n == 0) return BB_OK;
+    BB_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    double* d_out = nullptr;
+    BB_TRY(scratch_vec(ctx, (void**)&d_out, (size_t)n * sizeof(double)));
+    k_philox_normal<<<(int)((n + 255) / 256), 256, 0, st>>>(n, stream, seed, offset, index_offset, d_out);
+    ctx->launches++;
+    cudaError_t e = cudaPeekAtLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_out);
+    if (e != cudaSuccess) { bb_set_error("bb_philox_normal: %s", cudaGetErrorString(e)); return BB_ERR_CUDA; }
+    return BB_OK;
+}
+
+// ---- resident observation-side vectors ---------------------------------------------------------
+extern "C" int bb_set_outcome(bb_mat* m, const double* n_trial, const double* n_success) {
+    BB_ARG(m && n_success, "mat/n_success");
+    bb_ctx* ctx = m->ctx;
+    BB_CUDA(cudaSetDevice(ctx->device));
+    size_t nb = (size_t)m->n * sizeof(double);
+    BB_CUDA(cudaMemcpyAsync(m->n_success, n_success, nb, cudaMemcpyHostToDevice, ctx->stream));
+    if (n_trial) BB_CUDA(cudaMemcpyAsync(m->n_trial, n_trial, nb, cudaMemcpyHostToDevice, ctx->stream));
+    BB_CUDA(cudaStreamSynchronize(ctx->stream));
+    m->is_linear = (n_trial == nullptr);
+    m->has_outcome = 1;
+    m->zk_valid = 0;
+    return BB_OK;
+}
+
+extern "C" int bb_set_obs_prec(bb_mat* m, const double* omega) {
+    BB_ARG(m && omega, "mat/omega");
+    BB_CUDA(cudaSetDevice(m->ctx->device));
+    BB_CUDA(cudaMemcpyAsync(m->omega, omega, (size_t)m->n * sizeof(double), cudaMemcpyHostToDevice, m->ctx->stream));
+    BB_CUDA(cudaStreamSynchronize(m->ctx->stream));
+    m->use_omega_scalar = 0;
+    return BB_OK;
+}
+
+extern "C" int bb_set_obs_prec_scalar(bb_mat* m, double omega) {
+    BB_ARG(m != nullptr, "mat");
+    m->omega_scalar = omega;
+    m->use_omega_scalar = 1;
+    return BB_OK;
+}
+
+extern "C" int bb_get_obs_prec(bb_mat* m, double* out) {
+    BB_ARG(m && out, "mat/out");
+    BB_CUDA(cudaSetDevice(m->ctx->device));
+    if (m->use_omega_scalar) { for (i64 i = 0; i < m->n; ++i) out[i] = m->omega_scalar; return BB_OK; }
+    BB_CUDA(cudaMemcpyAsync(out, m->omega, (size_t)m->n * sizeof(double), cudaMemcpyDeviceToHost, m->ctx->stream));
+    BB_CUDA(cudaStreamSynchronize(m->ctx->stream));
+    return BB_OK;
+}
+
+extern "C" int bb_get_linear_predictor(bb_mat* m, double* out) {
+    BB_ARG(m && out, "mat/out");
+    BB_CUDA(cudaSetDevice(m->ctx->device));
+    BB_CUDA(cudaMemcpyAsync(out, m->eta, (size_t)m->n * sizeof(double), cudaMemcpyDeviceToHost, m->ctx->stream));
+    BB_CUDA(cudaStreamSynchronize(m->ctx->stream));
+    return BB_OK;
+}
+
+static int N_grid(i64 n) { i64 g = (n + 1023) / 1024; if (g < 1) g = 1; if (g > RED_MAX) g = RED_MAX; return (int)g; }
+
+// eta = X coef into m->eta (device)
+static int linear_predictor(bb_mat* m, const double* coef) {
+    bb_ctx* ctx = m->ctx;
+    BB_CUDA(cudaMemcpyAsync(m->v_P, coef, (size_t)m->P * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    BB_TRY(bb_op_prepare(m, m->v_P, nullptr));
+    BB_TRY(bb_op_dot(m, 0));
+    BB_CUDA(cudaMemcpyAsync(m->eta, m->u_n, (size_t)m->n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    return BB_OK;
+}
+
+extern "C" int bb_pg_from_coef(bb_mat* m, const double* coef, uint64_t seed, uint64_t offset,
+                               double* omega_out, double* loglik) {
+    BB_ARG(m && coef, "mat/coef");
+    if (!m->has_outcome || m->is_linear) { bb_set_error("bb_pg_from_coef needs a logit outcome (bb_set_outcome)"); return BB_ERR_STATE; }
+    bb_ctx* ctx = m->ctx;
+    cudaStream_t st = ctx->stream;
+    BB_CUDA(cudaSetDevice(ctx->device));
+    BB_TRY(linear_predictor(m, coef));
+    const int TB = 128;
+    i64 nblk = (m->n + TB - 1) / TB;
+    if (nblk < 1) nblk = 1;
+    // partial log-likelihoods: one per block; collapse in passes of RED_MAX
+    double* red_ll = nullptr;
+    BB_CUDA(cudaMalloc((void**)&red_ll, (size_t)nblk * sizeof(double)));
+    k_pg_loglik<<<(int)nblk, TB, 0, st>>>(m->n, m->n_trial, m->n_success, m->eta, seed, offset, m->row_offset, m->omega, red_ll);
+    ctx->launches++;
+    m->use_omega_scalar = 0;
+    // simple and deterministic: one warp sums all block partials in fixed order
+    k_finish_scalar<<<1, 32, 0, st>>>(red_ll, (int)nblk, m->traw);
+    ctx->launches++;
+    BB_TRY(bb_allreduce_dev(ctx, m->traw, 1));
+    double ll = 0.0;
+    BB_CUDA(cudaMemcpyAsync(&ll, m->traw, sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (omega_out) BB_CUDA(cudaMemcpyAsync(omega_out, m->omega, (size_t)m->n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    cudaError_t e = cudaStreamSynchronize(st);
+    cudaFree(red_ll);
+    if (e != cudaSuccess) { bb_set_error("bb_pg_from_coef: %s", cudaGetErrorString(e)); return BB_ERR_CUDA; }
+    if (loglik) *loglik = ll;
+    return BB_OK;
+}
+
+extern "C" int bb_linear_rss(bb_mat* m, const double* coef, double* rss) {
+    BB_ARG(m && coef && rss, "mat/coef/rss");
+    if (!m->has_outcome) { bb_set_error("bb_linear_rss needs bb_set_outcome"); return BB_ERR_STATE; }
+    bb_ctx* ctx = m->ctx;
+    cudaStream_t st = ctx->stream;
+    BB_CUDA(cudaSetDevice(ctx->device));
+    BB_TRY(linear_predictor(m, coef));
+    int g = N_grid(m->n);
+    k_rss<<<g, 256, 0, st>>>(m->n, m->n_success, m->eta, m->red + RED_LL * RED_MAX);
+    ctx->launches++;
+    k_finish_scalar<<<1, 32, 0, st>>>(m->red + RED_LL * RED_MAX, g, m->traw);
+    ctx->launches++;
+    BB_TRY(bb_allreduce_dev(ctx, m->traw, 1));
+    BB_CUDA(cudaMemcpyAsync(rss, m->traw, sizeof(double), cudaMemcpyDeviceToHost, st));
+    BB_CUDA(cudaStreamSynchronize(st));
+    return BB_OK;
+}

@@ -1,0 +1,822 @@
+// Sparse design matrix: CSR upload, bit-exact CSC construction, slab formats and the SpMV kernels.
+//
+// Reference seams: bayesbridge/design_matrix/sparse_matrix.py:21-49 (construction; X.tocsr()),
+// :68-101 (dot), :103-129 (Tdot), :164-177 (fisher diag).  scipy's csr_tocsc (called by the
+// reference's `X.T.dot`) is a stable counting sort by column; the device CSC below is a stable
+// LSD radix sort by column of the CSR nnz sequence, which yields the same arrays bit for bit.
+#include "bb_internal.cuh"
+#include <cub/cub.cuh>
+#include <vector>
+#include <algorithm>
+#include <stdlib.h>
+
+constexpr int SPMV_THREADS = 1024;
+constexpr int SPMV_ITEMS = 4;
+constexpr int SPMV_TILE = SPMV_THREADS * SPMV_ITEMS;   // nnz per tile
+constexpr int SPMV_WPART = 4 * 32;                      // block-path scratch (doubles)
+
+// ------------------------------------------------------------------------------------------
+// setup kernels (run once per matrix)
+__global__ void k_iota(int* a, i64 n) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = (int)i;
+}
+
+// seg_of[k] = segment containing nnz k  (largest s with ptr[s] <= k)
+__global__ void k_expand_ptr(const int* __restrict__ ptr, i64 n_seg, i64 nnz, int* __restrict__ seg_of) {
+    i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nnz) return;
+    i64 lo = 0, hi = n_seg;   // find first s in [0, n_seg] with ptr[s] > k, answer s-1
+    while (lo < hi) {
+        i64 mid = (lo + hi) >> 1;
+        if (ptr[mid] <= (int)k) lo = mid + 1; else hi = mid;
+    }
+    seg_of[k] = (int)(lo - 1);
+}
+
+__global__ void k_gather_i(const int* __restrict__ src, const int* __restrict__ perm, i64 n, int* __restrict__ dst) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[perm[i]];
+}
+__global__ void k_gather_d(const double* __restrict__ src, const int* __restrict__ perm, i64 n, double* __restrict__ dst) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[perm[i]];
+}
+__global__ void k_slab_key(const int* __restrict__ idx, i64 n, int W, int* __restrict__ key) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) key[i] = idx[i] / W;
+}
+__global__ void k_vkey(const int* __restrict__ slab_sorted, const int* __restrict__ seg_of,
+                       const int* __restrict__ perm, i64 n, i64 n_seg, i64* __restrict__ vkey) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) vkey[i] = (i64)slab_sorted[i] * n_seg + seg_of[perm[i]];
+}
+// out[v] = first position m with key[m] >= v, for v in [0, nv]
+template <typename K>
+__global__ void k_lower_bound(const K* __restrict__ key, i64 n, i64 nv, int* __restrict__ out) {
+    i64 v = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v > nv) return;
+    i64 lo = 0, hi = n;
+    while (lo < hi) {
+        i64 mid = (lo + hi) >> 1;
+        if ((i64)key[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    out[v] = (int)lo;
+}
+
+// per-tile ownership: slab/last flags are packed in vlo/vhi on input
+__global__ void k_tile_meta(const int* __restrict__ ptr, i64 V, i64 n_seg, int ntiles,
+                            TileMeta* __restrict__ tiles, int* __restrict__ head_seg) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntiles) return;
+    TileMeta m = tiles[t];
+    int slab = m.vlo, is_last = m.vhi;
+    i64 vbeg = (i64)slab * n_seg, vend = vbeg + n_seg;
+    // vlo = first v in [vbeg, vend] with ptr[v] >= start
+    i64 lo = vbeg, hi = vend;
+    while (lo < hi) {
+        i64 mid = (lo + hi) >> 1;
+        if (ptr[mid] < m.start) lo = mid + 1; else hi = mid;
+    }
+    i64 vlo = lo;
+    i64 vhi = vend;
+    if (!is_last) {
+        lo = vlo; hi = vend;
+        while (lo < hi) {
+            i64 mid = (lo + hi) >> 1;
+            if (ptr[mid] < m.end) lo = mid + 1; else hi = mid;
+        }
+        vhi = lo;
+    }
+    m.vlo = (int)vlo;
+    m.vhi = (int)vhi;
+    tiles[t] = m;
+    head_seg[t] = (ptr[vlo] > m.start) ? (int)(vlo - 1) : -1;
+}
+
+// ------------------------------------------------------------------------------------------
+// The SpMV kernel.  One CTA per work unit (a run of tiles inside one slab).  The CTA stages its
+// slab of the gather vector in shared memory, then streams its tiles: coalesced loads of
+// (idx,val) into registers (software-prefetched one tile ahead), products into shared memory,
+// and a segmented reduction whose shape (lanes per segment) is fixed by static tile metadata,
+// so the result is bit-reproducible.
+template <bool BINARY, bool STAGE>
+__global__ void __launch_bounds__(SPMV_THREADS, 1)
+k_seg_spmv(const int* __restrict__ ptr, const int* __restrict__ idx, const double* __restrict__ val,
+           const TileMeta* __restrict__ tiles, const WorkUnit* __restrict__ units,
+           const double* __restrict__ gvec, int W, i64 n_gather, int wstage,
+           double* __restrict__ part, double* __restrict__ head_part, const int* __restrict__ done_flag)
+{
+    if (done_flag != nullptr && *done_flag) return;
+    extern __shared__ double smem[];
+    double* sv = smem;
+    double* prod = smem + wstage;
+    double* wpart = prod + SPMV_TILE;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const WorkUnit u = units[blockIdx.x];
+    const i64 gbase = (i64)u.slab * W;
+    if (STAGE) {
+        i64 rem = n_gather - gbase;
+        int wlen = rem < (i64)W ? (int)rem : W;
+        for (int i = tid; i < wlen; i += SPMV_THREADS) sv[i] = gvec[gbase + i];
+    }
+    int ri[SPMV_ITEMS];
+    double rv[SPMV_ITEMS];
+    TileMeta m = tiles[u.tile_lo];
+#pragma unroll
+    for (int j = 0; j < SPMV_ITEMS; ++j) {
+        int k = m.start + j * SPMV_THREADS + tid;
+        bool ok = k < m.end;
+        ri[j] = ok ? idx[k] : -1;
+        if (!BINARY) rv[j] = ok ? val[k] : 0.0;
+    }
+    if (STAGE) __syncthreads();
+
+    for (int t = u.tile_lo; t < u.tile_hi; ++t) {
+        // products of the current tile -> shared memory
+#pragma unroll
+        for (int j = 0; j < SPMV_ITEMS; ++j) {
+            if (ri[j] >= 0) {
+                double g = STAGE ? sv[ri[j] - (int)gbase] : __ldg(gvec + ri[j]);
+                prod[j * SPMV_THREADS + tid] = BINARY ? g : rv[j] * g;
+            }
+        }
+        __syncthreads();
+        const TileMeta cur = m;
+        if (t + 1 < u.tile_hi) {     // prefetch the next tile; in flight during the reduction
+            m = tiles[t + 1];
+#pragma unroll
+            for (int j = 0; j < SPMV_ITEMS; ++j) {
+                int k = m.start + j * SPMV_THREADS + tid;
+                bool ok = k < m.end;
+                ri[j] = ok ? idx[k] : -1;
+                if (!BINARY) rv[j] = ok ? val[k] : 0.0;
+            }
+        }
+        // segmented reduction; item 0 is the head (segment continued from the previous tile)
+        const int items = cur.vhi - cur.vlo + 1;
+        if (items <= 4) {
+            for (int it = 0; it < items; ++it) {
+                int a, b;
+                if (it == 0) { a = 0; b = min(ptr[cur.vlo], cur.end) - cur.start; }
+                else { int v = cur.vlo + it - 1; a = ptr[v] - cur.start; b = min(ptr[v + 1], cur.end) - cur.start; }
+                double s = 0.0;
+                for (int e = a + tid; e < b; e += SPMV_THREADS) s += prod[e];
+                s = warp_sum(s);
+                if (lane == 0) wpart[it * 32 + warp] = s;
+            }
+            __syncthreads();
+            if (warp < items) {
+                double s = warp_sum(wpart[warp * 32 + lane]);
+                if (lane == 0) {
+                    if (warp == 0) head_part[t] = s; else part[cur.vlo + warp - 1] = s;
+                }
+            }
+        } else {
+            int G = 32;
+            if (items > 32) {
+                int x = SPMV_THREADS / items;
+                G = (x >= 1) ? (1 << (31 - __clz(x))) : 1;
+            }
+            const int groups = SPMV_THREADS / G;
+            const int grp = tid / G, gl = tid % G;
+            for (int base = 0; base < items; base += groups) {
+                int it = base + grp;
+                bool valid = it < items;
+                int a = 0, b = 0;
+                if (valid) {
+                    if (it == 0) { a = 0; b = min(ptr[cur.vlo], cur.end) - cur.start; }
+                    else { int v = cur.vlo + it - 1; a = ptr[v] - cur.start; b = min(ptr[v + 1], cur.end) - cur.start; }
+                }
+                double s = 0.0;
+                for (int e = a + gl; e < b; e += G) s += prod[e];
+                for (int o = G >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                if (valid && gl == 0) {
+                    if (it == 0) head_part[t] = s; else part[cur.vlo + it - 1] = s;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// adds the head partials (tails of segments that straddle tiles) in tile order
+__global__ void k_fixup(const int* __restrict__ head_seg, int ntiles, const double* __restrict__ head_part,
+                        double* __restrict__ part, const int* __restrict__ done_flag) {
+    if (done_flag != nullptr && *done_flag) return;
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntiles) return;
+    int v = head_seg[t];
+    if (v < 0) return;
+    if (t > 0 && head_seg[t - 1] == v) return;   // not the first continuation tile
+    double acc = 0.0;
+    for (int tt = t; tt < ntiles && head_seg[tt] == v; ++tt) acc += head_part[tt];
+    part[v] += acc;
+}
+
+// ------------------------------------------------------------------------------------------
+// element-wise kernels around the SpMV
+// sv[j] = (scale? scale[j]:1) * v[j]; shift partial = sum_{j<icpt} sv[j] - sum_j c[j] sv[icpt+j]
+__global__ void k_prepare(const double* __restrict__ v, const double* __restrict__ scale, i64 P, int icpt,
+                          const double* __restrict__ c, double* __restrict__ sv, double* __restrict__ red_shift,
+                          const int* __restrict__ done_flag) {
+    if (done_flag != nullptr && *done_flag) return;
+    __shared__ double sm[33];
+    double acc = 0.0;
+    for (i64 j = (i64)blockIdx.x * blockDim.x + threadIdx.x; j < P; j += (i64)gridDim.x * blockDim.x) {
+        double x = scale ? scale[j] * v[j] : v[j];
+        sv[j] = x;
+        acc += (j < icpt) ? x : -c[j - icpt] * x;
+    }
+    acc = block_sum(acc, sm);
+    if (threadIdx.x == 0) red_shift[blockIdx.x] = acc;
+}
+
+// u_i = shift + sum_s part[s*n+i];  MODE 0: out=u ; MODE 1: out = omega*u, partial sums of out
+template <int MODE>
+__global__ void k_dot_finish(const double* __restrict__ part, int nslab, i64 n,
+                             const double* __restrict__ red_shift, int nshift,
+                             const double* __restrict__ omega, double omega_scalar,
+                             double* __restrict__ out, double* __restrict__ u_out, double* __restrict__ red_w,
+                             const int* __restrict__ done_flag) {
+    if (done_flag != nullptr && *done_flag) return;
+    __shared__ double sm[33];
+    const double shift = warp_sum_partials(red_shift, nshift);
+    double acc = 0.0;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        double u = 0.0;
+        for (int s = 0; s < nslab; ++s) u += part[(i64)s * n + i];
+        u += shift;
+        if (MODE == 0) {
+            out[i] = u;
+        } else {
+            double w = (omega ? omega[i] : omega_scalar) * u;
+            out[i] = w;
+            if (u_out) u_out[i] = u;
+            acc += w;
+        }
+    }
+    if (MODE == 1) {
+        acc = block_sum(acc, sm);
+        if (threadIdx.x == 0) red_w[blockIdx.x] = acc;
+    }
+}
+
+__global__ void k_sum_partials(const double* __restrict__ w, i64 n, double* __restrict__ red) {
+    __shared__ double sm[33];
+    double acc = 0.0;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) acc += w[i];
+    acc = block_sum(acc, sm);
+    if (threadIdx.x == 0) red[blockIdx.x] = acc;
+}
+
+// traw[0] = sum of the w partials; traw[1+j] = sum_r part[r*p+j]
+__global__ void k_tdot_collect(const double* __restrict__ part, int nslab, i64 p,
+                               const double* __restrict__ red_w, int nred, double* __restrict__ traw,
+                               const int* __restrict__ done_flag) {
+    if (done_flag != nullptr && *done_flag) return;
+    if (blockIdx.x == 0 && threadIdx.x < 32) {
+        double s = warp_sum_partials(red_w, nred);
+        if (threadIdx.x == 0) traw[0] = s;
+    }
+    for (i64 j = (i64)blockIdx.x * blockDim.x + threadIdx.x; j < p; j += (i64)gridDim.x * blockDim.x) {
+        double t = 0.0;
+        for (int r = 0; r < nslab; ++r) t += part[(i64)r * p + j];
+        traw[1 + j] = t;
+    }
+}
+
+// t_P from the (allreduced) traw: t[0] = sum w (intercept); t[icpt+j] = traw[1+j] - sum_w * c[j]
+__global__ void k_tdot_finish(const double* __restrict__ traw, i64 p, int icpt, const double* __restrict__ c,
+                              double* __restrict__ tP) {
+    const double sw = traw[0];
+    for (i64 j = (i64)blockIdx.x * blockDim.x + threadIdx.x; j < p + icpt; j += (i64)gridDim.x * blockDim.x) {
+        if (j < icpt) tP[j] = sw;
+        else tP[j] = traw[1 + (j - icpt)] - sw * c[j - icpt];
+    }
+}
+
+__global__ void k_mul(const double* __restrict__ a, const double* __restrict__ b, i64 n, double* __restrict__ out) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) out[i] = a[i] * b[i];
+}
+
+// fisher diag: sum_i weight_i X_ij^2 (values squared on the fly): reuse the Tdot format with a
+// squared-value pass; implemented as a column-parallel gather over the canonical CSC.
+__global__ void k_fisher_diag_csc(const int* __restrict__ cptr, const int* __restrict__ cidx, const double* __restrict__ cval,
+                                  i64 p, const double* __restrict__ weight, double* __restrict__ d2, double* __restrict__ d1) {
+    // one warp per column
+    i64 j = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (j >= p) return;
+    double a2 = 0.0, a1 = 0.0;
+    for (int k = cptr[j] + lane; k < cptr[j + 1]; k += 32) {
+        double x = cval ? cval[k] : 1.0;
+        double w = weight[cidx[k]];
+        a2 += w * x * x;
+        a1 += w * x;
+    }
+    a2 = warp_sum(a2);
+    a1 = warp_sum(a1);
+    if (lane == 0) { d2[j] = a2; d1[j] = a1; }
+}
+
+// ------------------------------------------------------------------------------------------
+static inline int grid_for(i64 n, int threads, int cap) {
+    i64 g = (n + threads - 1) / threads;
+    if (g < 1) g = 1;
+    if (g > cap) g = cap;
+    return (int)g;
+}
+
+template <typename KeyT>
+static int sort_pairs(bb_ctx* ctx, const KeyT* kin, KeyT* kout, const int* vin, int* vout, i64 n, int end_bit) {
+    size_t tmp_bytes = 0;
+    BB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, kin, kout, vin, vout, (int)n, 0, end_bit, ctx->stream));
+    void* tmp = nullptr;
+    BB_CUDA(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1));
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, kin, kout, vin, vout, (int)n, 0, end_bit, ctx->stream);
+    cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+    cudaFree(tmp);
+    if (e != cudaSuccess || e2 != cudaSuccess) {
+        bb_set_error("radix sort failed: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
+        return BB_ERR_CUDA;
+    }
+    ctx->launches += 4;
+    return BB_OK;
+}
+
+static int bits_for(i64 maxval) {   // number of bits needed to represent values in [0, maxval]
+    int b = 1;
+    while (b < 63 && ((i64)1 << b) <= maxval) ++b;
+    return b;
+}
+
+int bb_slab_free(SlabFmt* f) {
+    if (f->owns_arrays) {
+        if (f->ptr) cudaFree(f->ptr);
+        if (f->idx) cudaFree(f->idx);
+        if (f->val) cudaFree(f->val);
+    }
+    if (f->tiles) cudaFree(f->tiles);
+    if (f->head_seg) cudaFree(f->head_seg);
+    if (f->units) cudaFree(f->units);
+    if (f->part) cudaFree(f->part);
+    if (f->head_part) cudaFree(f->head_part);
+    memset(f, 0, sizeof(*f));
+    return BB_OK;
+}
+
+static i64 max_stage_width(bb_ctx* ctx) {
+    i64 avail = (i64)ctx->smem_optin - (i64)(SPMV_TILE + SPMV_WPART) * 8 - 64;
+    i64 w = avail / 8;
+    w &= ~(i64)31;
+    if (w < 32) w = 32;
+    return w;
+}
+
+// Build a slab format from a canonical compressed matrix (ptr[n_seg+1], idx, val).
+static int build_slab_format(bb_ctx* ctx, const int* cptr, const int* cidx, const double* cval,
+                             i64 n_seg, i64 n_gather, i64 nnz, SlabFmt* f) {
+    memset(f, 0, sizeof(*f));
+    cudaStream_t st = ctx->stream;
+    i64 wmax = max_stage_width(ctx);
+    if (ctx->opt_slab_width > 0) {
+        i64 w = (ctx->opt_slab_width + 31) & ~(i64)31;
+        if (w < wmax) wmax = w;
+    }
+    i64 ng = n_gather > 0 ? n_gather : 1;
+    i64 nslab = (ng + wmax - 1) / wmax;
+    i64 W = ((ng + nslab - 1) / nslab + 31) & ~(i64)31;
+    if (W > wmax) W = wmax;
+    nslab = (ng + W - 1) / W;
+    i64 V = nslab * n_seg;
+    if (V + 1 >= ((i64)1 << 31)) { bb_set_error("slab format too large (nslab*n_seg = %lld)", (long long)V); return BB_ERR_ARG; }
+    f->nslab = (int)nslab;
+    f->n_seg = n_seg;
+    f->n_gather = n_gather;
+    f->W = (int)W;
+    f->nnz = nnz;
+    const int TB = 256;
+    if (nslab == 1) {
+        f->ptr = (int*)cptr; f->idx = (int*)cidx; f->val = (double*)cval;
+        f->owns_arrays = false;
+    } else {
+        f->owns_arrays = true;
+        BB_CUDA(cudaMalloc((void**)&f->ptr, (size_t)(V + 1) * sizeof(int)));
+        BB_CUDA(cudaMalloc((void**)&f->idx, (size_t)(nnz > 0 ? nnz : 1) * sizeof(int)));
+        if (cval) BB_CUDA(cudaMalloc((void**)&f->val, (size_t)(nnz > 0 ? nnz : 1) * sizeof(double)));
+        int *seg_of = nullptr, *key = nullptr, *key_sorted = nullptr, *iota = nullptr, *perm = nullptr;
+        i64* vkey = nullptr;
+        size_t nb = (size_t)(nnz > 0 ? nnz : 1);
+        BB_CUDA(cudaMalloc((void**)&seg_of, nb * sizeof(int)));
+        BB_CUDA(cudaMalloc((void**)&key, nb * sizeof(int)));
+        BB_CUDA(cudaMalloc((void**)&key_sorted, nb * sizeof(int)));
+        BB_CUDA(cudaMalloc((void**)&iota, nb * sizeof(int)));
+        BB_CUDA(cudaMalloc((void**)&perm, nb * sizeof(int)));
+        BB_CUDA(cudaMalloc((void**)&vkey, nb * sizeof(i64)));
+        int rc = BB_OK;
+        if (nnz > 0) {
+            int g = (int)((nnz + TB - 1) / TB);
+            k_expand_ptr<<<g, TB, 0, st>>>(cptr, n_seg, nnz, seg_of);
+            k_slab_key<<<g, TB, 0, st>>>(cidx, nnz, (int)W, key);
+            k_iota<<<g, TB, 0, st>>>(iota, nnz);
+            ctx->launches += 3;
+            rc = sort_pairs<int>(ctx, key, key_sorted, iota, perm, nnz, bits_for(nslab - 1));
+            if (rc == BB_OK) {
+                k_gather_i<<<g, TB, 0, st>>>(cidx, perm, nnz, f->idx);
+                if (cval) k_gather_d<<<g, TB, 0, st>>>(cval, perm, nnz, f->val);
+                k_vkey<<<g, TB, 0, st>>>(key_sorted, seg_of, perm, nnz, n_seg, vkey);
+                ctx->launches += 3;
+            }
+        }
+        if (rc == BB_OK) {
+            int g = (int)((V + 1 + TB - 1) / TB);
+            k_lower_bound<i64><<<g, TB, 0, st>>>(vkey, nnz, V, f->ptr);
+            ctx->launches += 1;
+            cudaError_t e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) { bb_set_error("slab build: %s", cudaGetErrorString(e)); rc = BB_ERR_CUDA; }
+        }
+        cudaFree(seg_of); cudaFree(key); cudaFree(key_sorted); cudaFree(iota); cudaFree(perm); cudaFree(vkey);
+        BB_TRY(rc);
+    }
+    // slab nnz ranges -> tiles (host), ownership (device)
+    std::vector<int> slab_off((size_t)nslab + 1);
+    for (i64 s = 0; s <= nslab; ++s)
+        BB_CUDA(cudaMemcpyAsync(&slab_off[(size_t)s], f->ptr + s * n_seg, sizeof(int), cudaMemcpyDeviceToHost, st));
+    BB_CUDA(cudaStreamSynchronize(st));
+    std::vector<TileMeta> tiles;
+    std::vector<int> slab_tile0((size_t)nslab + 1);
+    for (i64 s = 0; s < nslab; ++s) {
+        slab_tile0[(size_t)s] = (int)tiles.size();
+        int a = slab_off[(size_t)s], b = slab_off[(size_t)s + 1];
+        int nt = (b - a + SPMV_TILE - 1) / SPMV_TILE;
+        if (nt < 1) nt = 1;
+        for (int t = 0; t < nt; ++t) {
+            TileMeta m;
+            m.start = a + t * SPMV_TILE;
+            m.end = std::min(b, m.start + SPMV_TILE);
+            if (m.end < m.start) m.end = m.start;
+            m.vlo = (int)s;               // packed inputs for k_tile_meta
+            m.vhi = (t == nt - 1) ? 1 : 0;
+            tiles.push_back(m);
+        }
+    }
+    slab_tile0[(size_t)nslab] = (int)tiles.size();
+    f->ntiles = (int)tiles.size();
+    BB_CUDA(cudaMalloc((void**)&f->tiles, tiles.size() * sizeof(TileMeta)));
+    BB_CUDA(cudaMalloc((void**)&f->head_seg, tiles.size() * sizeof(int)));
+    BB_CUDA(cudaMemcpyAsync(f->tiles, tiles.data(), tiles.size() * sizeof(TileMeta), cudaMemcpyHostToDevice, st));
+    k_tile_meta<<<(f->ntiles + TB - 1) / TB, TB, 0, st>>>(f->ptr, V, n_seg, f->ntiles, f->tiles, f->head_seg);
+    ctx->launches += 1;
+    // work units: ~one per SM, never crossing a slab
+    int target = (f->ntiles + ctx->sm_count - 1) / ctx->sm_count;
+    if (target < 1) target = 1;
+    std::vector<WorkUnit> units;
+    for (i64 s = 0; s < nslab; ++s) {
+        int t0 = slab_tile0[(size_t)s], t1 = slab_tile0[(size_t)s + 1];
+        int nt = t1 - t0;
+        int nu = (nt + target - 1) / target;
+        for (int k = 0; k < nu; ++k) {
+            WorkUnit u;
+            u.slab = (int)s;
+            u.tile_lo = t0 + (int)((i64)nt * k / nu);
+            u.tile_hi = t0 + (int)((i64)nt * (k + 1) / nu);
+            u.pad = 0;
+            if (u.tile_hi > u.tile_lo) units.push_back(u);
+        }
+    }
+    f->nunits = (int)units.size();
+    BB_CUDA(cudaMalloc((void**)&f->units, units.size() * sizeof(WorkUnit)));
+    BB_CUDA(cudaMemcpyAsync(f->units, units.data(), units.size() * sizeof(WorkUnit), cudaMemcpyHostToDevice, st));
+    BB_CUDA(cudaMalloc((void**)&f->part, (size_t)(V > 0 ? V : 1) * sizeof(double)));
+    BB_CUDA(cudaMalloc((void**)&f->head_part, (size_t)f->ntiles * sizeof(double)));
+    BB_CUDA(cudaMemsetAsync(f->part, 0, (size_t)(V > 0 ? V : 1) * sizeof(double), st));
+    BB_CUDA(cudaMemsetAsync(f->head_part, 0, (size_t)f->ntiles * sizeof(double), st));
+    BB_CUDA(cudaStreamSynchronize(st));
+    return BB_OK;
+}
+
+// launch the SpMV + fix-up for one format; gvec has f->n_gather entries
+static int launch_spmv(bb_mat* m, SlabFmt* f, const double* gvec, const int* done_flag) {
+    bb_ctx* ctx = m->ctx;
+    const bool stage = ctx->opt_spmv_stage != 0;
+    int wstage = stage ? f->W : 0;
+    size_t smem = (size_t)(wstage + SPMV_TILE + SPMV_WPART) * sizeof(double);
+    static bool attr_set = false;
+    if (!attr_set) {
+        int mx = (int)ctx->smem_optin;
+        BB_CUDA(cudaFuncSetAttribute(k_seg_spmv<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+        BB_CUDA(cudaFuncSetAttribute(k_seg_spmv<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+        BB_CUDA(cudaFuncSetAttribute(k_seg_spmv<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+        BB_CUDA(cudaFuncSetAttribute(k_seg_spmv<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+        attr_set = true;
+    }
+    if (smem > ctx->smem_optin) { bb_set_error("spmv shared memory %zu exceeds %zu", smem, ctx->smem_optin); return BB_ERR_ARG; }
+    const bool binary = (f->val == nullptr);
+    dim3 grid(f->nunits), block(SPMV_THREADS);
+#define SPMV_ARGS f->ptr, f->idx, f->val, f->tiles, f->units, gvec, f->W, f->n_gather, wstage, f->part, f->head_part, done_flag
+    if (binary && stage) k_seg_spmv<true, true><<<grid, block, smem, ctx->stream>>>(SPMV_ARGS);
+    else if (binary && !stage) k_seg_spmv<true, false><<<grid, block, smem, ctx->stream>>>(SPMV_ARGS);
+    else if (!binary && stage) k_seg_spmv<false, true><<<grid, block, smem, ctx->stream>>>(SPMV_ARGS);
+    else k_seg_spmv<false, false><<<grid, block, smem, ctx->stream>>>(SPMV_ARGS);
+#undef SPMV_ARGS
+    BB_LAUNCHED(ctx);
+    k_fixup<<<(f->ntiles + 255) / 256, 256, 0, ctx->stream>>>(f->head_seg, f->ntiles, f->head_part, f->part, done_flag);
+    BB_LAUNCHED(ctx);
+    return BB_OK;
+}
+
+// ---- op pipeline (sparse part; dense twin in bb_dense.cu) ----------------------------------
+int bb_dense_dot(bb_mat* m, int mode, const int* done_flag);
+int bb_dense_tdot(bb_mat* m, const double* w, const int* done_flag);
+
+static int P_grid(i64 P) { return grid_for(P, 1024, RED_MAX); }   // 256 threads, ~4 elements each
+static int N_grid(i64 n) { return grid_for(n, 1024, RED_MAX); }
+
+int bb_op_prepare_flag(bb_mat* m, const double* vP, const double* scale, const int* done_flag) {
+    bb_ctx* ctx = m->ctx;
+    k_prepare<<<P_grid(m->P), 256, 0, ctx->stream>>>(vP, scale, m->P, m->add_intercept, m->col_offset, m->sv,
+                                                     m->red + RED_SHIFT * RED_MAX, done_flag);
+    BB_LAUNCHED(ctx);
+    return BB_OK;
+}
+int bb_op_prepare(bb_mat* m, const double* vP, const double* scale) { return bb_op_prepare_flag(m, vP, scale, nullptr); }
+
+int bb_op_dot_flag(bb_mat* m, int mode, const int* done_flag) {
+    bb_ctx* ctx = m->ctx;
+    if (!m->is_sparse) return bb_dense_dot(m, mode, done_flag);
+    BB_TRY(launch_spmv(m, &m->fdot, m->sv + m->add_intercept, done_flag));
+    const double* red_shift = m->red + RED_SHIFT * RED_MAX;
+    int nshift = P_grid(m->P);
+    if (mode == 0) {
+        k_dot_finish<0><<<N_grid(m->n), 256, 0, ctx->stream>>>(m->fdot.part, m->fdot.nslab, m->n, red_shift, nshift,
+                                                             nullptr, 0.0, m->u_n, nullptr, nullptr, done_flag);
+    } else {
+        k_dot_finish<1><<<N_grid(m->n), 256, 0, ctx->stream>>>(m->fdot.part, m->fdot.nslab, m->n, red_shift, nshift,
+                                                             m->use_omega_scalar ? nullptr : m->omega, m->omega_scalar, m->w_n, nullptr,
+                                                             m->red + RED_W * RED_MAX, done_flag);
+        m->nred_w = N_grid(m->n);
+    }
+    BB_LAUNCHED(ctx);
+    return BB_OK;
+}
+int bb_op_dot(bb_mat* m, int mode) { return bb_op_dot_flag(m, mode, nullptr); }
+
+// traw = [sum w; X' w], allreduced.  have_w_partials: red[RED_W] already holds N_grid(n) partial sums of w
+int bb_op_tdot_flag(bb_mat* m, const double* w, bool have_w_partials, const int* done_flag) {
+    bb_ctx* ctx = m->ctx;
+    if (!have_w_partials) {
+        k_sum_partials<<<N_grid(m->n), 256, 0, ctx->stream>>>(w, m->n, m->red + RED_W * RED_MAX);
+        BB_LAUNCHED(ctx);
+        m->nred_w = N_grid(m->n);
+    }
+    if (!m->is_sparse) {
+        BB_TRY(bb_dense_tdot(m, w, done_flag));
+        k_tdot_collect<<<grid_for(m->p, 1024, RED_MAX), 256, 0, ctx->stream>>>(
+            m->dense_part, m->dense_nblk, m->p, m->red + RED_W * RED_MAX, m->nred_w, m->traw, done_flag);
+        BB_LAUNCHED(ctx);
+    } else {
+        BB_TRY(launch_spmv(m, &m->ftdot, w, done_flag));
+        k_tdot_collect<<<grid_for(m->p, 1024, RED_MAX), 256, 0, ctx->stream>>>(
+            m->ftdot.part, m->ftdot.nslab, m->p, m->red + RED_W * RED_MAX, m->nred_w, m->traw, done_flag);
+        BB_LAUNCHED(ctx);
+    }
+    BB_TRY(bb_allreduce_dev(ctx, m->traw, m->p + 1));
+    return BB_OK;
+}
+int bb_op_tdot(bb_mat* m, const double* w) { return bb_op_tdot_flag(m, w, false, nullptr); }
+
+int bb_op_tdot_finish(bb_mat* m, double* tP) {
+    bb_ctx* ctx = m->ctx;
+    k_tdot_finish<<<P_grid(m->P), 256, 0, ctx->stream>>>(m->traw, m->p, m->add_intercept, m->col_offset, tP);
+    BB_LAUNCHED(ctx);
+    return BB_OK;
+}
+
+// ---- matrix lifetime -------------------------------------------------------------------------
+static int alloc_d(double** p, i64 n) {
+    BB_CUDA(cudaMalloc((void**)p, (size_t)(n > 0 ? n : 1) * sizeof(double)));
+    BB_CUDA(cudaMemset(*p, 0, (size_t)(n > 0 ? n : 1) * sizeof(double)));
+    return BB_OK;
+}
+
+int bb_mat_alloc_work(bb_mat* m) {
+    BB_TRY(alloc_d(&m->omega, m->n)); BB_TRY(alloc_d(&m->n_trial, m->n)); BB_TRY(alloc_d(&m->n_success, m->n));
+    BB_TRY(alloc_d(&m->eta, m->n)); BB_TRY(alloc_d(&m->w_n, m->n)); BB_TRY(alloc_d(&m->u_n, m->n));
+    BB_TRY(alloc_d(&m->eps_n, m->n));
+    double** pv[] = {&m->v_P, &m->sv, &m->t_P, &m->x, &m->r, &m->pvec, &m->q, &m->b, &m->s, &m->D, &m->pps,
+                     &m->z, &m->x0, &m->eps_P, &m->out_P};
+    for (auto pp : pv) BB_TRY(alloc_d(pp, m->P + 1));
+    BB_TRY(alloc_d(&m->traw, m->p + 1));
+    BB_TRY(alloc_d(&m->zk, m->P + 1));
+    BB_TRY(alloc_d(&m->red, (i64)RED_SLOTS * RED_MAX));
+    BB_CUDA(cudaMalloc((void**)&m->cg, sizeof(CgScalars)));
+    BB_CUDA(cudaMemset(m->cg, 0, sizeof(CgScalars)));
+    BB_CUDA(cudaMallocHost((void**)&m->cg_host, sizeof(CgScalars)));
+    m->omega_scalar = 1.0;
+    m->use_omega_scalar = 0;
+    m->last_n_iter = 0;
+    return BB_OK;
+}
+
+extern "C" int bb_mat_free(bb_mat* m) {
+    if (!m) return BB_OK;
+    cudaSetDevice(m->ctx->device);
+    cudaStreamSynchronize(m->ctx->stream);
+    if (m->cg_graph) cudaGraphExecDestroy(m->cg_graph);
+    bb_slab_free(&m->fdot);
+    bb_slab_free(&m->ftdot);
+    void* ptrs[] = {m->csr_ptr, m->csr_idx, m->csr_val, m->csc_ptr, m->csc_idx, m->csc_val, m->col_offset, m->Xd,
+                    m->omega, m->n_trial, m->n_success, m->eta, m->w_n, m->u_n, m->eps_n, m->dense_part, m->zk,
+                    m->v_P, m->sv, m->traw, m->t_P, m->x, m->r, m->pvec, m->q, m->b, m->s, m->D, m->pps, m->z, m->x0,
+                    m->eps_P, m->out_P, m->red, m->cg};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    if (m->cg_host) cudaFreeHost(m->cg_host);
+    free(m);
+    return BB_OK;
+}
+
+extern "C" int bb_csr_upload(bb_ctx* ctx, int64_t n, int64_t p, int64_t nnz,
+                             const int32_t* indptr, const int32_t* indices, const double* data,
+                             const double* column_offset, int add_intercept,
+                             int64_t row_offset, int64_t n_global, bb_mat** out) {
+    BB_ARG(ctx && out && indptr, "ctx/out/indptr");
+    BB_ARG(n >= 0 && p >= 0 && nnz >= 0, "negative size");
+    BB_ARG(nnz == 0 || indices != nullptr, "indices");
+    BB_ARG(n < ((i64)1 << 31) - 1 && p < ((i64)1 << 31) - 1 && nnz < ((i64)1 << 31) - 1, "int32 index range exceeded");
+    BB_ARG(indptr[0] == 0 && indptr[n] == nnz, "indptr[0] != 0 or indptr[n] != nnz");
+    BB_CUDA(cudaSetDevice(ctx->device));
+    bb_mat* m = (bb_mat*)calloc(1, sizeof(bb_mat));
+    m->ctx = ctx;
+    m->is_sparse = 1;
+    m->is_binary = (data == nullptr);
+    m->add_intercept = add_intercept ? 1 : 0;
+    m->centered = (column_offset != nullptr);
+    m->n = n; m->p = p; m->P = p + m->add_intercept; m->nnz = nnz;
+    m->row_offset = row_offset; m->n_global = n_global > 0 ? n_global : n;
+    cudaStream_t st = ctx->stream;
+    size_t nb = (size_t)(nnz > 0 ? nnz : 1);
+    int rc = BB_OK;
+    do {
+#define CK(e) if ((rc = (e)) != BB_OK) break
+#define CKC(e) { cudaError_t e_ = (e); if (e_ != cudaSuccess) { bb_set_error("%s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(e_)); rc = BB_ERR_CUDA; break; } }
+        CKC(cudaMalloc((void**)&m->csr_ptr, (size_t)(n + 1) * sizeof(int)));
+        CKC(cudaMalloc((void**)&m->csr_idx, nb * sizeof(int)));
+        CKC(cudaMemcpyAsync(m->csr_ptr, indptr, (size_t)(n + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+        if (nnz > 0) CKC(cudaMemcpyAsync(m->csr_idx, indices, (size_t)nnz * sizeof(int), cudaMemcpyHostToDevice, st));
+        if (data) {
+            CKC(cudaMalloc((void**)&m->csr_val, nb * sizeof(double)));
+            if (nnz > 0) CKC(cudaMemcpyAsync(m->csr_val, data, (size_t)nnz * sizeof(double), cudaMemcpyHostToDevice, st));
+        }
+        CK(alloc_d(&m->col_offset, p));
+        if (column_offset && p > 0)
+            CKC(cudaMemcpyAsync(m->col_offset, column_offset, (size_t)p * sizeof(double), cudaMemcpyHostToDevice, st));
+        // canonical CSC: stable sort of the CSR nnz sequence by column
+        CKC(cudaMalloc((void**)&m->csc_ptr, (size_t)(p + 1) * sizeof(int)));
+        CKC(cudaMalloc((void**)&m->csc_idx, nb * sizeof(int)));
+        if (data) CKC(cudaMalloc((void**)&m->csc_val, nb * sizeof(double)));
+        int *row_of = nullptr, *iota = nullptr, *perm = nullptr, *col_sorted = nullptr;
+        CKC(cudaMalloc((void**)&row_of, nb * sizeof(int)));
+        CKC(cudaMalloc((void**)&iota, nb * sizeof(int)));
+        CKC(cudaMalloc((void**)&perm, nb * sizeof(int)));
+        CKC(cudaMalloc((void**)&col_sorted, nb * sizeof(int)));
+        const int TB = 256;
+        if (nnz > 0) {
+            int g = (int)((nnz + TB - 1) / TB);
+            k_expand_ptr<<<g, TB, 0, st>>>(m->csr_ptr, n, nnz, row_of);
+            k_iota<<<g, TB, 0, st>>>(iota, nnz);
+            ctx->launches += 2;
+            rc = sort_pairs<int>(ctx, m->csr_idx, col_sorted, iota, perm, nnz, bits_for(p > 0 ? p - 1 : 0));
+            if (rc == BB_OK) {
+                k_gather_i<<<g, TB, 0, st>>>(row_of, perm, nnz, m->csc_idx);
+                if (data) k_gather_d<<<g, TB, 0, st>>>(m->csr_val, perm, nnz, m->csc_val);
+                ctx->launches += 2;
+            }
+        }
+        if (rc == BB_OK) {
+            k_lower_bound<int><<<(int)((p + 1 + TB - 1) / TB), TB, 0, st>>>(col_sorted, nnz, p, m->csc_ptr);
+            ctx->launches += 1;
+            cudaError_t e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) { bb_set_error("csc build: %s", cudaGetErrorString(e)); rc = BB_ERR_CUDA; }
+        }
+        cudaFree(row_of); cudaFree(iota); cudaFree(perm); cudaFree(col_sorted);
+        if (rc != BB_OK) break;
+        CK(build_slab_format(ctx, m->csr_ptr, m->csr_idx, m->csr_val, n, p, nnz, &m->fdot));
+        CK(build_slab_format(ctx, m->csc_ptr, m->csc_idx, m->csc_val, p, n, nnz, &m->ftdot));
+        CK(bb_mat_alloc_work(m));
+        CKC(cudaStreamSynchronize(st));
+#undef CK
+#undef CKC
+    } while (0);
+    if (rc != BB_OK) { bb_mat_free(m); return rc; }
+    *out = m;
+    return BB_OK;
+}
+
+extern "C" int bb_mat_info(bb_mat* m, int64_t* n_local, int64_t* P, int64_t* nnz, int* is_sparse, int* is_binary) {
+    BB_ARG(m != nullptr, "mat");
+    if (n_local) *n_local = m->n;
+    if (P) *P = m->P;
+    if (nnz) *nnz = m->nnz;
+    if (is_sparse) *is_sparse = m->is_sparse;
+    if (is_binary) *is_binary = m->is_binary;
+    return BB_OK;
+}
+
+static int export_compressed(bb_mat* m, const int* dptr, i64 nptr, const int* didx, const double* dval,
+                             int32_t* indptr, int32_t* indices, double* data) {
+    BB_ARG(m->is_sparse, "not a sparse matrix");
+    cudaStream_t st = m->ctx->stream;
+    BB_CUDA(cudaSetDevice(m->ctx->device));
+    if (indptr) BB_CUDA(cudaMemcpyAsync(indptr, dptr, (size_t)nptr * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (indices && m->nnz > 0) BB_CUDA(cudaMemcpyAsync(indices, didx, (size_t)m->nnz * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (data && m->nnz > 0) {
+        if (dval) BB_CUDA(cudaMemcpyAsync(data, dval, (size_t)m->nnz * sizeof(double), cudaMemcpyDeviceToHost, st));
+        else for (i64 k = 0; k < m->nnz; ++k) data[k] = 1.0;
+    }
+    BB_CUDA(cudaStreamSynchronize(st));
+    return BB_OK;
+}
+
+extern "C" int bb_mat_export_csr(bb_mat* m, int32_t* indptr, int32_t* indices, double* data) {
+    BB_ARG(m != nullptr, "mat");
+    return export_compressed(m, m->csr_ptr, m->n + 1, m->csr_idx, m->csr_val, indptr, indices, data);
+}
+extern "C" int bb_mat_export_csc(bb_mat* m, int32_t* indptr, int32_t* indices, double* data) {
+    BB_ARG(m != nullptr, "mat");
+    return export_compressed(m, m->csc_ptr, m->p + 1, m->csc_idx, m->csc_val, indptr, indices, data);
+}
+
+// ---- host-buffer products (seam 1) -------------------------------------------------------------
+extern "C" int bb_dot(bb_mat* m, const double* v, double* out) {
+    BB_ARG(m && v && out, "mat/v/out");
+    bb_ctx* ctx = m->ctx;
+    BB_CUDA(cudaSetDevice(ctx->device));
+    BB_CUDA(cudaMemcpyAsync(m->v_P, v, (size_t)m->P * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    BB_TRY(bb_op_prepare(m, m->v_P, nullptr));
+    BB_TRY(bb_op_dot(m, 0));
+    BB_CUDA(cudaMemcpyAsync(out, m->u_n, (size_t)m->n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    BB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return BB_OK;
+}
+
+extern "C" int bb_tdot(bb_mat* m, const double* w, double* out) {
+    BB_ARG(m && w && out, "mat/w/out");
+    bb_ctx* ctx = m->ctx;
+    BB_CUDA(cudaSetDevice(ctx->device));
+    BB_CUDA(cudaMemcpyAsync(m->eps_n, w, (size_t)m->n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    BB_TRY(bb_op_tdot(m, m->eps_n));
+    BB_TRY(bb_op_tdot_finish(m, m->t_P));
+    BB_CUDA(cudaMemcpyAsync(out, m->t_P, (size_t)m->P * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    BB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return BB_OK;
+}
+
+// diag(X' W X) with the intercept / centring algebra of sparse_matrix.py:164-177:
+//   d_j = sum_i w_i x_ij^2 - 2 c_j sum_i w_i x_ij + (sum w) c_j^2 ; intercept entry = sum w
+__global__ void k_fisher_finish(const double* __restrict__ d2, const double* __restrict__ d1, const double* __restrict__ sw_p,
+                                const double* __restrict__ c, i64 p, int icpt, int centered, double* __restrict__ out) {
+    const double sw = sw_p[0];
+    for (i64 j = (i64)blockIdx.x * blockDim.x + threadIdx.x; j < p + icpt; j += (i64)gridDim.x * blockDim.x) {
+        if (j < icpt) { out[j] = sw; continue; }
+        i64 k = j - icpt;
+        double d = d2[1 + k];
+        if (centered) { d -= 2.0 * c[k] * d1[1 + k]; d += sw * c[k] * c[k]; }
+        out[j] = d;
+    }
+}
+
+int bb_dense_fisher_diag(bb_mat* m, const double* weight_dev, double* d2, double* d1);
+
+extern "C" int bb_fisher_diag(bb_mat* m, const double* weight, double* out) {
+    BB_ARG(m && weight && out, "mat/weight/out");
+    bb_ctx* ctx = m->ctx;
+    cudaStream_t st = ctx->stream;
+    BB_CUDA(cudaSetDevice(ctx->device));
+    BB_CUDA(cudaMemcpyAsync(m->eps_n, weight, (size_t)m->n * sizeof(double), cudaMemcpyHostToDevice, st));
+    // d2 -> q[1..p], d1 -> b[1..p], sum w -> traw[0]; all three allreduced
+    double *d2 = m->q, *d1 = m->b;
+    if (m->is_sparse) {
+        if (m->p > 0) {
+            i64 threads = m->p * 32;
+            k_fisher_diag_csc<<<(int)((threads + 255) / 256), 256, 0, st>>>(m->csc_ptr, m->csc_idx, m->csc_val, m->p,
+                                                                            m->eps_n, d2 + 1, d1 + 1);
+            BB_LAUNCHED(ctx);
+        }
+    } else {
+        BB_TRY(bb_dense_fisher_diag(m, m->eps_n, d2 + 1, d1 + 1));
+    }
+    k_sum_partials<<<N_grid(m->n), 256, 0, st>>>(m->eps_n, m->n, m->red + RED_MISC * RED_MAX);
+    BB_LAUNCHED(ctx);
+    k_tdot_collect<<<1, 256, 0, st>>>(nullptr, 0, 0, m->red + RED_MISC * RED_MAX, N_grid(m->n), m->traw, nullptr);
+    BB_LAUNCHED(ctx);
+    BB_CUDA(cudaMemcpyAsync(d2, m->traw, sizeof(double), cudaMemcpyDeviceToDevice, st));
+    BB_TRY(bb_allreduce_dev(ctx, d2, m->p + 1));
+    BB_TRY(bb_allreduce_dev(ctx, d1 + 1, m->p));
+    k_fisher_finish<<<P_grid(m->P), 256, 0, st>>>(d2, d1, d2, m->col_offset, m->p, m->add_intercept, m->centered, m->out_P);
+    BB_LAUNCHED(ctx);
+    BB_CUDA(cudaMemcpyAsync(out, m->out_P, (size_t)m->P * sizeof(double), cudaMemcpyDeviceToHost, st));
+    BB_CUDA(cudaStreamSynchronize(st));
+    return BB_OK;
+}

@@ -1,0 +1,114 @@
+"""Coefficient update of the Gibbs sampler (reference: reg_coef_sampler/reg_coef_sampler.py).
+
+Only the Gaussian-posterior path (linear / logistic likelihood, 'cg' method) is offered: that is
+the path this package re-implements on the GPU.  `search_mode` (chain initialisation) runs scipy's
+L-BFGS-B on the host and reaches the device through the design matrix' dot / Tdot."""
+from warnings import warn
+
+import numpy as np
+import scipy.optimize
+
+from .cg_sampler import ConjugateGradientSampler
+from .reg_coef_posterior_summarizer import RegressionCoeffficientPosteriorSummarizer
+
+
+class SparseRegressionCoefficientSampler():
+
+    def __init__(self, n_coef, prior_sd_for_unshrunk, sampling_method,
+                 stability_estimate_stabilized=False, regularizing_slab_size=float('inf')):
+        if sampling_method != 'cg':
+            raise ValueError("Only the 'cg' sampler is implemented for device-resident design matrices.")
+        self.prior_sd_for_unshrunk = prior_sd_for_unshrunk
+        self.n_unshrunk = len(prior_sd_for_unshrunk)
+        self.regularizing_slab_size = regularizing_slab_size
+        self.regcoef_summarizer = RegressionCoeffficientPosteriorSummarizer(
+            n_coef, self.n_unshrunk, regularizing_slab_size)
+        self.cg_sampler = ConjugateGradientSampler(self.n_unshrunk)
+        self._sampling_info_attributes = ['regcoef_summarizer']
+
+    def get_internal_state(self):
+        return {a: getattr(self, a) for a in self._sampling_info_attributes if hasattr(self, a)}
+
+    def set_internal_state(self, state):
+        for a in self._sampling_info_attributes:
+            if hasattr(self, a) and a in state:
+                setattr(self, a, state[a])
+
+    def compute_prior_shrunk_scale(self, gscale, lscale):
+        """tau*lambda damped by the slab (reg_coef_sampler.py:194-201)."""
+        scale = gscale * lscale
+        scale /= np.sqrt(1 + (scale / self.regularizing_slab_size) ** 2)
+        return scale
+
+    def sample_gaussian_posterior(self, y, design, obs_prec, gscale, lscale, method='cg',
+                                  noise='host', philox=None, z=None):
+        """
+        beta | omega, tau, lambda ~ N(Phi^{-1} X' Omega y, Phi^{-1}) (reg_coef_sampler.py:60-103).
+
+        y, obs_prec : arrays; or both None when the outcome and the precision live on the device
+                      (then X'(Omega y) is formed there too).
+        """
+        if method != 'cg':
+            raise NotImplementedError("Only method='cg' is available on the device.")
+        if z is None and obs_prec is not None:
+            z = design.Tdot(obs_prec * y)
+        prior_sd = np.concatenate((
+            self.prior_sd_for_unshrunk, self.compute_prior_shrunk_scale(gscale, lscale)))
+        prior_prec_sqrt = 1 / prior_sd
+        x0 = self.regcoef_summarizer.extrapolate_coef_condmean(gscale, lscale)
+        scaled_sd = self.regcoef_summarizer.estimate_coef_precond_scale_sd()
+        coef, cg_info = self.cg_sampler.sample(
+            design, obs_prec, prior_prec_sqrt, z,
+            coef_cg_init=x0, precond_by='prior', coef_scaled_sd=scaled_sd,
+            maxiter=500, atol=10e-6 * np.sqrt(design.shape[1]),
+            noise=noise, philox=philox)
+        self.regcoef_summarizer.update(coef, gscale, lscale)
+        return coef, {'n_cg_iter': cg_info['n_iter']}
+
+    # ---- chain initialisation ---------------------------------------------------------------
+    def compute_preconditioning_scale(self, gscale, lscale, post_sd, prior_sd_for_unshrunk, target=1.):
+        n_coef = len(post_sd)
+        k = n_coef - len(lscale)
+        scale = np.ones(n_coef)
+        scale[k:] = self.compute_prior_shrunk_scale(gscale, lscale)
+        if k > 0:
+            scale[:k] = target * post_sd[:k]
+        prior_prec = np.concatenate(((prior_sd_for_unshrunk / scale[:k]) ** -2, np.ones(len(lscale))))
+        return scale, prior_prec
+
+    def search_mode(self, coef, lscale, gscale, obs_prec, model, optim_maxiter=None,
+                    warn_optim_failure=False):
+        """Conditional posterior mode of the coefficients by L-BFGS-B in prior-preconditioned
+        coordinates (reg_coef_sampler.py:281-327)."""
+        scale, prior_prec = self.compute_preconditioning_scale(
+            gscale, lscale, np.ones(coef.size), self.prior_sd_for_unshrunk)
+        loglik_args = (obs_prec,) if model.name == 'linear' else ()
+
+        def logp_and_grad(theta, loglik_only=False):
+            logp, grad = model.compute_loglik_and_gradient(scale * theta, *loglik_args, loglik_only=loglik_only)
+            logp += np.sum(- prior_prec * theta ** 2) / 2
+            if grad is not None and np.isfinite(logp):
+                grad = scale * grad - prior_prec * theta
+            else:
+                grad = None
+            return logp, grad
+
+        maxiter = 250 if optim_maxiter is None else optim_maxiter
+        tol = 10 ** -6 / np.sqrt(len(coef))
+        design = model.design
+        design.memoize_dot(True)
+        design.reset_matvec_count()
+        res = scipy.optimize.minimize(
+            lambda th: - logp_and_grad(th, loglik_only=True)[0], coef / scale,
+            jac=lambda th: - logp_and_grad(th)[1], method='L-BFGS-B',
+            options={'maxiter': maxiter, 'gtol': tol, 'maxcor': 200})
+        design.memoize_dot(False)
+        if (not res.success) and warn_optim_failure:
+            warn("The regression coefficient mode could not be located within {:d} optimization "
+                 "steps. Proceeding with the current best estimate.".format(res.nit))
+        info = {
+            'is_success': res.success, 'method': 'L-BFGS-B', 'n_iter': res['nit'],
+            'n_logp_eval': res['nfev'], 'n_grad_eval': res.get('njev', 0), 'n_hess_eval': 0,
+            'n_design_matvec': design.n_matvec,
+        }
+        return scale * res.x, info

@@ -1,0 +1,139 @@
+/*
+ * bbgpu.h -- C-ABI of libbbgpu.so: the B200 (sm_100a) implementation of bayesbridge's
+ * CG-accelerated coefficient update and Polya-Gamma draw.
+ *
+ * Every entry point replaces one seam of the reference (OHDSI/bayes-bridge v0.2.6, paths
+ * relative to the reference root); the cited lines are what a maintainer would re-bind:
+ *
+ *   seam 1  design matrix      bayesbridge/design_matrix/sparse_matrix.py:21-49   (construction)
+ *                              bayesbridge/design_matrix/sparse_matrix.py:68-101  (dot)
+ *                              bayesbridge/design_matrix/sparse_matrix.py:103-129 (Tdot)
+ *                              bayesbridge/design_matrix/sparse_matrix.py:164-177 (fisher diag)
+ *                              bayesbridge/design_matrix/dense_matrix.py:9-58     (dense twin)
+ *   seam 2  CG sampler         bayesbridge/reg_coef_sampler/cg_sampler.py:20-94
+ *                              (+ scipy.sparse.linalg.cg, the third-party loop it calls)
+ *   seam 3  random variates    bayesbridge/random/random.py:37-41 -> polya_gamma.pyx:40-74,
+ *                              tilted_stable.pyx:65-135
+ *
+ * Conventions: plain pointers and sizes only; all host buffers are caller-owned, C-contiguous,
+ * fp64 / int32, and are only touched during the call (every call returns after its stream has
+ * been synchronised).  Device memory is owned by the handles.  Every function returns 0 on
+ * success, non-zero on failure; bb_last_error() then holds the message.  A handle is not
+ * thread-safe.  One process drives one GPU; multi-GPU = one process per GPU + bb_comm_*.
+ */
+#ifndef BBGPU_H
+#define BBGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bb_ctx bb_ctx;   /* device + stream + (optional) communicator            */
+typedef struct bb_mat bb_mat;   /* one row shard of the design matrix + its workspaces  */
+
+enum { BB_OK = 0, BB_ERR_CUDA = 1, BB_ERR_ARG = 2, BB_ERR_NCCL = 3, BB_ERR_STATE = 4 };
+
+/* noise source of the CG right-hand side (cg_sampler.py:61-67) */
+enum { BB_NOISE_INJECT = 0,   /* eps1[n_local], eps2[P] supplied by the caller (parity mode)   */
+       BB_NOISE_PHILOX = 1 }; /* generated on device, Philox4x32-10 keyed by (seed, offset, global row) */
+
+/* spmv kernel variants (bb_set_option "spmv_stage"): */
+enum { BB_SPMV_STAGE_SMEM = 1, BB_SPMV_STAGE_L2 = 0 };
+
+/* ---- library ---------------------------------------------------------------------------- */
+const char* bb_last_error(void);
+int  bb_version(void);
+int  bb_device_count(int* count);
+
+/* ---- context ---------------------------------------------------------------------------- */
+int  bb_init(int device, bb_ctx** out);
+int  bb_destroy(bb_ctx* ctx);
+int  bb_set_option(bb_ctx* ctx, const char* name, int64_t value);
+int  bb_get_option(bb_ctx* ctx, const char* name, int64_t* value);
+/* kernel launches issued by this library since bb_init / the last reset */
+int  bb_get_launch_count(bb_ctx* ctx, int64_t* launches);
+int  bb_reset_launch_count(bb_ctx* ctx);
+int  bb_sync(bb_ctx* ctx);
+
+/* ---- communicator: row-sharding, one process per GPU (new) ----------- */
+int  bb_comm_unique_id(const char* nccl_lib_path, char* id_out_128);
+int  bb_comm_init(bb_ctx* ctx, const char* nccl_lib_path, int nranks, int rank, const char* id_128);
+int  bb_comm_allreduce_host(bb_ctx* ctx, double* buf, int64_t count);  /* in-place sum, host buffer */
+
+/* ---- design matrix (seam 1) ------------------------------------------------------------- */
+/* CSR shard [n_local x p]; data==NULL => pattern-only (all stored values are 1.0).
+ * column_offset==NULL => not centred.  row_offset/n_global place the shard in the global matrix. */
+int  bb_csr_upload(bb_ctx* ctx, int64_t n_local, int64_t p, int64_t nnz,
+                   const int32_t* indptr, const int32_t* indices, const double* data,
+                   const double* column_offset, int add_intercept,
+                   int64_t row_offset, int64_t n_global, bb_mat** out);
+/* dense shard, row-major [n_local x p] WITHOUT intercept column / centring (applied implicitly) */
+int  bb_dense_upload(bb_ctx* ctx, int64_t n_local, int64_t p, const double* X,
+                     const double* column_offset, int add_intercept,
+                     int64_t row_offset, int64_t n_global, bb_mat** out);
+int  bb_mat_free(bb_mat* mat);
+int  bb_mat_info(bb_mat* mat, int64_t* n_local, int64_t* P, int64_t* nnz, int* is_sparse, int* is_binary);
+/* bit-exactness hooks: what the device holds, copied back */
+int  bb_mat_export_csr(bb_mat* mat, int32_t* indptr, int32_t* indices, double* data);
+int  bb_mat_export_csc(bb_mat* mat, int32_t* indptr, int32_t* indices, double* data);
+
+/* y[n_local] = X v  (with intercept + centring algebra);  v has P = p + add_intercept entries */
+int  bb_dot(bb_mat* mat, const double* v, double* out);
+/* t[P] = X' w, summed over all shards when a communicator is attached */
+int  bb_tdot(bb_mat* mat, const double* w, double* out);
+/* diag(X' diag(weight) X)[P], summed over shards */
+int  bb_fisher_diag(bb_mat* mat, const double* weight, double* out);
+
+/* ---- resident observation-side vectors (avoid n-length PCIe traffic per Gibbs iteration) - */
+/* logit: n_trial, n_success;  linear: n_trial==NULL, n_success = y */
+int  bb_set_outcome(bb_mat* mat, const double* n_trial, const double* n_success);
+int  bb_set_obs_prec(bb_mat* mat, const double* omega);          /* H2D, n_local            */
+int  bb_set_obs_prec_scalar(bb_mat* mat, double omega);          /* linear model: omega*1_n */
+int  bb_get_obs_prec(bb_mat* mat, double* omega_out);            /* D2H                     */
+int  bb_get_linear_predictor(bb_mat* mat, double* eta_out);      /* D2H of the last X beta  */
+
+/* ---- CG sampler (seam 2) ---------------------------------------------------------------- */
+/* Draws beta ~ N(Phi^-1 z, Phi^-1), Phi = X' Omega X + diag(prior_prec_sqrt)^2, by running
+ * scipy.sparse.linalg.cg's recurrences on the system pre-scaled by precond_scale.
+ *   omega           NULL => use the resident obs_prec
+ *   z               NULL => z = X'(omega .* y_gaussian) from the resident outcome
+ *                           (logit: X' (n_success - n_trial/2); linear: omega * X' y)
+ *   x0              initial guess for beta (un-scaled), P
+ *   precond_scale   s in cg_sampler.py:123-138, P
+ *   eps1, eps2      BB_NOISE_INJECT only
+ * out: coef[P]; n_iter = completed CG iterations; info = 0 converged / maxiter otherwise.
+ * stats (may be NULL): [0]=||b||, [1]=final ||r||, [2]=device ms of the call */
+int  bb_cg_sample(bb_mat* mat, const double* omega, const double* prior_prec_sqrt,
+                  const double* z, const double* x0, const double* precond_scale,
+                  double atol, int maxiter, int noise_mode,
+                  const double* eps1, const double* eps2, uint64_t seed, uint64_t offset,
+                  double* coef_out, int* n_iter, int* info, double* stats);
+
+/* ---- random variates (seam 3) ----------------------------------------------------------- */
+/* omega_i ~ PG(shape_i, tilt_i); index_offset = global index of element 0 (sharding-invariant streams) */
+int  bb_pg_sample(bb_ctx* ctx, int64_t n, const int32_t* shape, const double* tilt,
+                  uint64_t seed, uint64_t offset, int64_t index_offset, double* out);
+/* fused Gibbs step: eta = X coef; omega ~ PG(n_trial, eta) kept resident; loglik = sum(n_success*eta
+ * - n_trial*log(1+e^eta)) over all shards.  omega_out may be NULL. */
+int  bb_pg_from_coef(bb_mat* mat, const double* coef, uint64_t seed, uint64_t offset,
+                     double* omega_out, double* loglik);
+/* linear model: sum of squared residuals ||y - X coef||^2 over all shards */
+int  bb_linear_rss(bb_mat* mat, const double* coef, double* rss);
+/* exponentially tilted stable draws (tilted_stable.pyx:65-135); char_exp scalar */
+int  bb_tilted_stable_sample(bb_ctx* ctx, int64_t n, double char_exp, const double* tilt,
+                             uint64_t seed, uint64_t offset, int64_t index_offset, double* out);
+/* standard normals from the same Philox streams the CG sampler uses (stream 0: eps1, 1: eps2) */
+int  bb_philox_normal(bb_ctx* ctx, int64_t n, int stream, uint64_t seed, uint64_t offset,
+                      int64_t index_offset, double* out);
+
+/* ---- timing ----------------------------------------------------------------------------- */
+/* runs `reps` launches of one kernel class on resident data and returns mean device ms:
+ * what = "dot" | "tdot" | "op" (one application of X' Omega X v) | "pg" | "fisher_diag" */
+int  bb_time_kernel(bb_mat* mat, const char* what, int reps, int flush_l2, double* ms_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BBGPU_H */
