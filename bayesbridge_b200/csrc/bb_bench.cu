@@ -28,7 +28,10 @@ extern "C" int bb_time_kernel(bb_mat* m, const char* what, int reps, int do_flus
     if (!strcmp(what, "dot")) kind = 0;
     else if (!strcmp(what, "tdot")) kind = 1;
     else if (!strcmp(what, "op")) kind = 2;
-    BB_ARG(kind >= 0, "what must be dot | tdot | op");
+    else if (!strcmp(what, "spmv_dot")) kind = 3;     // the SpMV kernel alone (+ its fix-up)
+    else if (!strcmp(what, "spmv_tdot")) kind = 4;
+    BB_ARG(kind >= 0, "what must be dot | tdot | op | spmv_dot | spmv_tdot");
+    BB_ARG(kind < 3 || m->is_sparse, "spmv_* needs a sparse matrix");
     // deterministic, non-trivial inputs
     k_fill_test<<<256, 256, 0, st>>>(m->v_P, m->P, 1e-3);
     k_fill_test<<<256, 256, 0, st>>>(m->eps_n, m->n, 1e-3);
@@ -47,10 +50,14 @@ extern "C" int bb_time_kernel(bb_mat* m, const char* what, int reps, int do_flus
             BB_TRY(bb_op_dot(m, 0));
         } else if (kind == 1) {
             BB_TRY(bb_op_tdot(m, m->eps_n));
-        } else {
+        } else if (kind == 2) {
             BB_TRY(bb_op_prepare(m, m->v_P, nullptr));
             BB_TRY(bb_op_dot(m, 1));
             BB_TRY(bb_op_tdot_flag(m, m->w_n, true, nullptr));
+        } else if (kind == 3) {
+            BB_TRY(bb_launch_spmv(m, &m->fdot, m->v_P + m->add_intercept, nullptr));
+        } else {
+            BB_TRY(bb_launch_spmv(m, &m->ftdot, m->eps_n, nullptr));
         }
         BB_CUDA(cudaEventRecord(e1, st));
         BB_CUDA(cudaEventSynchronize(e1));

@@ -160,6 +160,7 @@ int bb_op_tdot_flag(bb_mat* m, const double* w, bool have_w_partials, const int*
 int bb_mat_alloc_work(bb_mat* m);
 
 int bb_slab_free(SlabFmt* f);
+int bb_launch_spmv(bb_mat* m, SlabFmt* f, const double* gvec, const int* done_flag);
 
 // ------------------------------------------------------------------------------------------
 // device helpers

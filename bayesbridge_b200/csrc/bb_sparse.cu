@@ -10,10 +10,11 @@
 #include <algorithm>
 #include <stdlib.h>
 
-constexpr int SPMV_THREADS = 1024;
-constexpr int SPMV_ITEMS = 4;
-constexpr int SPMV_TILE = SPMV_THREADS * SPMV_ITEMS;   // nnz per tile
-constexpr int SPMV_WPART = 4 * 32;                      // block-path scratch (doubles)
+constexpr int SPMV_THREADS = 1024;                      // one CTA per SM, 32 independent warps
+constexpr int SPMV_WARPS = SPMV_THREADS / 32;
+constexpr int SPMV_ITEMS = 8;                           // nnz per lane per tile
+constexpr int SPMV_TILE = 32 * SPMV_ITEMS;              // nnz per (warp) tile
+constexpr int SPMV_REG_ITEMS = 8;                       // <= this many segments in a tile: register path
 
 // ------------------------------------------------------------------------------------------
 // setup kernels (run once per matrix)
@@ -95,11 +96,38 @@ __global__ void k_tile_meta(const int* __restrict__ ptr, i64 V, i64 n_seg, int n
 }
 
 // ------------------------------------------------------------------------------------------
-// The SpMV kernel.  One CTA per work unit (a run of tiles inside one slab).  The CTA stages its
-// slab of the gather vector in shared memory, then streams its tiles: coalesced loads of
-// (idx,val) into registers (software-prefetched one tile ahead), products into shared memory,
-// and a segmented reduction whose shape (lanes per segment) is fixed by static tile metadata,
-// so the result is bit-reproducible.
+// The SpMV kernel.  One CTA per work unit (a run of tiles inside one slab); the CTA stages its slab
+// of the gather vector in shared memory once, after which its 32 warps run independently (no block
+// barrier): each warp streams 256-nnz tiles with coalesced loads of (idx, val) into registers,
+// software-prefetched one tile ahead, multiplies by the staged vector and reduces the products by
+// segment.  The segment boundaries of a tile are its "cut points" c_k = min(ptr[vlo+k], end)-start;
+// piece k = [c_{k-1}, c_k) belongs to the head (k = 0: a segment continued from the previous tile,
+// goes to head_part) or to owned segment vlo+k-1 (goes to part).  Few pieces: predicated register
+// sums + warp shuffles.  Many pieces: products to a per-warp shared buffer, one lane per piece.
+// The reduction shape depends only on static metadata, so results are bit-reproducible.
+struct TileRegs {
+    int ri[SPMV_ITEMS];
+    double rv[SPMV_ITEMS];
+    TileMeta m;
+    int cut;       // lane l: ptr[vlo + l] (l <= nown, capped at 31)
+};
+
+template <bool BINARY>
+__device__ __forceinline__ void tile_load(TileRegs& R, int t, const TileMeta* __restrict__ tiles,
+                                          const int* __restrict__ ptr, const int* __restrict__ idx,
+                                          const double* __restrict__ val, int lane) {
+    R.m = tiles[t];
+#pragma unroll
+    for (int j = 0; j < SPMV_ITEMS; ++j) {
+        int k = R.m.start + j * 32 + lane;
+        bool ok = k < R.m.end;
+        R.ri[j] = ok ? idx[k] : -1;
+        if (!BINARY) R.rv[j] = ok ? val[k] : 0.0;
+    }
+    int nown = R.m.vhi - R.m.vlo;
+    R.cut = (lane <= nown) ? ptr[R.m.vlo + lane] : 0x7fffffff;
+}
+
 template <bool BINARY, bool STAGE>
 __global__ void __launch_bounds__(SPMV_THREADS, 1)
 k_seg_spmv(const int* __restrict__ ptr, const int* __restrict__ idx, const double* __restrict__ val,
@@ -110,10 +138,9 @@ k_seg_spmv(const int* __restrict__ ptr, const int* __restrict__ idx, const doubl
     if (done_flag != nullptr && *done_flag) return;
     extern __shared__ double smem[];
     double* sv = smem;
-    double* prod = smem + wstage;
-    double* wpart = prod + SPMV_TILE;
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
+    double* wprod = smem + wstage + warp * SPMV_TILE;      // per-warp product buffer
     const WorkUnit u = units[blockIdx.x];
     const i64 gbase = (i64)u.slab * W;
     if (STAGE) {
@@ -121,83 +148,70 @@ k_seg_spmv(const int* __restrict__ ptr, const int* __restrict__ idx, const doubl
         int wlen = rem < (i64)W ? (int)rem : W;
         for (int i = tid; i < wlen; i += SPMV_THREADS) sv[i] = gvec[gbase + i];
     }
-    int ri[SPMV_ITEMS];
-    double rv[SPMV_ITEMS];
-    TileMeta m = tiles[u.tile_lo];
-#pragma unroll
-    for (int j = 0; j < SPMV_ITEMS; ++j) {
-        int k = m.start + j * SPMV_THREADS + tid;
-        bool ok = k < m.end;
-        ri[j] = ok ? idx[k] : -1;
-        if (!BINARY) rv[j] = ok ? val[k] : 0.0;
-    }
-    if (STAGE) __syncthreads();
+    int t = u.tile_lo + warp;
+    TileRegs R;
+    if (t < u.tile_hi) tile_load<BINARY>(R, t, tiles, ptr, idx, val, lane);
+    if (STAGE) __syncthreads();          // the only block barrier
 
-    for (int t = u.tile_lo; t < u.tile_hi; ++t) {
-        // products of the current tile -> shared memory
+    while (t < u.tile_hi) {
+        // products of the current tile
+        double pr[SPMV_ITEMS];
 #pragma unroll
         for (int j = 0; j < SPMV_ITEMS; ++j) {
-            if (ri[j] >= 0) {
-                double g = STAGE ? sv[ri[j] - (int)gbase] : __ldg(gvec + ri[j]);
-                prod[j * SPMV_THREADS + tid] = BINARY ? g : rv[j] * g;
-            }
+            double g = 0.0;
+            if (R.ri[j] >= 0) g = STAGE ? sv[R.ri[j] - (int)gbase] : __ldg(gvec + R.ri[j]);
+            pr[j] = BINARY ? g : R.rv[j] * g;
         }
-        __syncthreads();
-        const TileMeta cur = m;
-        if (t + 1 < u.tile_hi) {     // prefetch the next tile; in flight during the reduction
-            m = tiles[t + 1];
+        const TileMeta cur = R.m;
+        const int nown = cur.vhi - cur.vlo;
+        // cut point of this lane, relative to the tile
+        int c = min(R.cut, cur.end) - cur.start;
+        const int tnext = t + SPMV_WARPS;
+        if (tnext < u.tile_hi) tile_load<BINARY>(R, tnext, tiles, ptr, idx, val, lane);   // prefetch
+
+        if (nown < SPMV_REG_ITEMS) {
+            // register path: piece k = [c_{k-1}, c_k)
+            double mine = 0.0;
+            int a = 0;
+            for (int k = 0; k <= nown; ++k) {
+                int b = __shfl_sync(0xffffffffu, c, k);
+                double sacc = 0.0;
 #pragma unroll
-            for (int j = 0; j < SPMV_ITEMS; ++j) {
-                int k = m.start + j * SPMV_THREADS + tid;
-                bool ok = k < m.end;
-                ri[j] = ok ? idx[k] : -1;
-                if (!BINARY) rv[j] = ok ? val[k] : 0.0;
-            }
-        }
-        // segmented reduction; item 0 is the head (segment continued from the previous tile)
-        const int items = cur.vhi - cur.vlo + 1;
-        if (items <= 4) {
-            for (int it = 0; it < items; ++it) {
-                int a, b;
-                if (it == 0) { a = 0; b = min(ptr[cur.vlo], cur.end) - cur.start; }
-                else { int v = cur.vlo + it - 1; a = ptr[v] - cur.start; b = min(ptr[v + 1], cur.end) - cur.start; }
-                double s = 0.0;
-                for (int e = a + tid; e < b; e += SPMV_THREADS) s += prod[e];
-                s = warp_sum(s);
-                if (lane == 0) wpart[it * 32 + warp] = s;
-            }
-            __syncthreads();
-            if (warp < items) {
-                double s = warp_sum(wpart[warp * 32 + lane]);
-                if (lane == 0) {
-                    if (warp == 0) head_part[t] = s; else part[cur.vlo + warp - 1] = s;
+                for (int j = 0; j < SPMV_ITEMS; ++j) {
+                    int e = j * 32 + lane;
+                    sacc += (e >= a && e < b) ? pr[j] : 0.0;
                 }
+                sacc = warp_sum(sacc);
+                if (lane == k) mine = sacc;
+                a = b;
             }
+            if (lane == 0) head_part[t] = mine;
+            else if (lane <= nown) part[cur.vlo + lane - 1] = mine;
         } else {
-            int G = 32;
-            if (items > 32) {
-                int x = SPMV_THREADS / items;
-                G = (x >= 1) ? (1 << (31 - __clz(x))) : 1;
-            }
-            const int groups = SPMV_THREADS / G;
-            const int grp = tid / G, gl = tid % G;
-            for (int base = 0; base < items; base += groups) {
-                int it = base + grp;
-                bool valid = it < items;
-                int a = 0, b = 0;
-                if (valid) {
-                    if (it == 0) { a = 0; b = min(ptr[cur.vlo], cur.end) - cur.start; }
-                    else { int v = cur.vlo + it - 1; a = ptr[v] - cur.start; b = min(ptr[v + 1], cur.end) - cur.start; }
+            // shared path: one lane per piece, serial sum in nnz order
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < SPMV_ITEMS; ++j) wprod[j * 32 + lane] = pr[j];
+            __syncwarp();
+            if (nown < 32) {
+                int a = __shfl_up_sync(0xffffffffu, c, 1);
+                if (lane == 0) a = 0;
+                if (lane <= nown) {
+                    double sacc = 0.0;
+                    for (int e = a; e < c; ++e) sacc += wprod[e];
+                    if (lane == 0) head_part[t] = sacc; else part[cur.vlo + lane - 1] = sacc;
                 }
-                double s = 0.0;
-                for (int e = a + gl; e < b; e += G) s += prod[e];
-                for (int o = G >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                if (valid && gl == 0) {
-                    if (it == 0) head_part[t] = s; else part[cur.vlo + it - 1] = s;
+            } else {
+                for (int k = lane; k <= nown; k += 32) {
+                    int a = (k == 0) ? 0 : min(ptr[cur.vlo + k - 1], cur.end) - cur.start;
+                    int b = min(ptr[cur.vlo + k], cur.end) - cur.start;
+                    double sacc = 0.0;
+                    for (int e = a; e < b; ++e) sacc += wprod[e];
+                    if (k == 0) head_part[t] = sacc; else part[cur.vlo + k - 1] = sacc;
                 }
             }
         }
-        __syncthreads();
+        t = tnext;
     }
 }
 
@@ -368,7 +382,7 @@ int bb_slab_free(SlabFmt* f) {
 }
 
 static i64 max_stage_width(bb_ctx* ctx) {
-    i64 avail = (i64)ctx->smem_optin - (i64)(SPMV_TILE + SPMV_WPART) * 8 - 64;
+    i64 avail = (i64)ctx->smem_optin - (i64)(SPMV_WARPS * SPMV_TILE) * 8 - 64;
     i64 w = avail / 8;
     w &= ~(i64)31;
     if (w < 32) w = 32;
@@ -498,11 +512,11 @@ static int build_slab_format(bb_ctx* ctx, const int* cptr, const int* cidx, cons
 }
 
 // launch the SpMV + fix-up for one format; gvec has f->n_gather entries
-static int launch_spmv(bb_mat* m, SlabFmt* f, const double* gvec, const int* done_flag) {
+int bb_launch_spmv(bb_mat* m, SlabFmt* f, const double* gvec, const int* done_flag) {
     bb_ctx* ctx = m->ctx;
     const bool stage = ctx->opt_spmv_stage != 0;
     int wstage = stage ? f->W : 0;
-    size_t smem = (size_t)(wstage + SPMV_TILE + SPMV_WPART) * sizeof(double);
+    size_t smem = (size_t)(wstage + SPMV_WARPS * SPMV_TILE) * sizeof(double);
     static bool attr_set = false;
     if (!attr_set) {
         int mx = (int)ctx->smem_optin;
@@ -546,7 +560,7 @@ int bb_op_prepare(bb_mat* m, const double* vP, const double* scale) { return bb_
 int bb_op_dot_flag(bb_mat* m, int mode, const int* done_flag) {
     bb_ctx* ctx = m->ctx;
     if (!m->is_sparse) return bb_dense_dot(m, mode, done_flag);
-    BB_TRY(launch_spmv(m, &m->fdot, m->sv + m->add_intercept, done_flag));
+    BB_TRY(bb_launch_spmv(m, &m->fdot, m->sv + m->add_intercept, done_flag));
     const double* red_shift = m->red + RED_SHIFT * RED_MAX;
     int nshift = P_grid(m->P);
     if (mode == 0) {
@@ -577,7 +591,7 @@ int bb_op_tdot_flag(bb_mat* m, const double* w, bool have_w_partials, const int*
             m->dense_part, m->dense_nblk, m->p, m->red + RED_W * RED_MAX, m->nred_w, m->traw, done_flag);
         BB_LAUNCHED(ctx);
     } else {
-        BB_TRY(launch_spmv(m, &m->ftdot, w, done_flag));
+        BB_TRY(bb_launch_spmv(m, &m->ftdot, w, done_flag));
         k_tdot_collect<<<grid_for(m->p, 1024, RED_MAX), 256, 0, ctx->stream>>>(
             m->ftdot.part, m->ftdot.nslab, m->p, m->red + RED_W * RED_MAX, m->nred_w, m->traw, done_flag);
         BB_LAUNCHED(ctx);
@@ -595,24 +609,26 @@ int bb_op_tdot_finish(bb_mat* m, double* tP) {
 }
 
 // ---- matrix lifetime -------------------------------------------------------------------------
-static int alloc_d(double** p, i64 n) {
+// NB: ctx->stream is non-blocking, i.e. NOT ordered with the legacy default stream: every memset
+// must go to ctx->stream or it races with the async copies issued right after the allocation.
+static int alloc_d(cudaStream_t st, double** p, i64 n) {
     BB_CUDA(cudaMalloc((void**)p, (size_t)(n > 0 ? n : 1) * sizeof(double)));
-    BB_CUDA(cudaMemset(*p, 0, (size_t)(n > 0 ? n : 1) * sizeof(double)));
+    BB_CUDA(cudaMemsetAsync(*p, 0, (size_t)(n > 0 ? n : 1) * sizeof(double), st));
     return BB_OK;
 }
 
 int bb_mat_alloc_work(bb_mat* m) {
-    BB_TRY(alloc_d(&m->omega, m->n)); BB_TRY(alloc_d(&m->n_trial, m->n)); BB_TRY(alloc_d(&m->n_success, m->n));
-    BB_TRY(alloc_d(&m->eta, m->n)); BB_TRY(alloc_d(&m->w_n, m->n)); BB_TRY(alloc_d(&m->u_n, m->n));
-    BB_TRY(alloc_d(&m->eps_n, m->n));
+    BB_TRY(alloc_d(m->ctx->stream, &m->omega, m->n)); BB_TRY(alloc_d(m->ctx->stream, &m->n_trial, m->n)); BB_TRY(alloc_d(m->ctx->stream, &m->n_success, m->n));
+    BB_TRY(alloc_d(m->ctx->stream, &m->eta, m->n)); BB_TRY(alloc_d(m->ctx->stream, &m->w_n, m->n)); BB_TRY(alloc_d(m->ctx->stream, &m->u_n, m->n));
+    BB_TRY(alloc_d(m->ctx->stream, &m->eps_n, m->n));
     double** pv[] = {&m->v_P, &m->sv, &m->t_P, &m->x, &m->r, &m->pvec, &m->q, &m->b, &m->s, &m->D, &m->pps,
                      &m->z, &m->x0, &m->eps_P, &m->out_P};
-    for (auto pp : pv) BB_TRY(alloc_d(pp, m->P + 1));
-    BB_TRY(alloc_d(&m->traw, m->p + 1));
-    BB_TRY(alloc_d(&m->zk, m->P + 1));
-    BB_TRY(alloc_d(&m->red, (i64)RED_SLOTS * RED_MAX));
+    for (auto pp : pv) BB_TRY(alloc_d(m->ctx->stream, pp, m->P + 1));
+    BB_TRY(alloc_d(m->ctx->stream, &m->traw, m->p + 1));
+    BB_TRY(alloc_d(m->ctx->stream, &m->zk, m->P + 1));
+    BB_TRY(alloc_d(m->ctx->stream, &m->red, (i64)RED_SLOTS * RED_MAX));
     BB_CUDA(cudaMalloc((void**)&m->cg, sizeof(CgScalars)));
-    BB_CUDA(cudaMemset(m->cg, 0, sizeof(CgScalars)));
+    BB_CUDA(cudaMemsetAsync(m->cg, 0, sizeof(CgScalars), m->ctx->stream));
     BB_CUDA(cudaMallocHost((void**)&m->cg_host, sizeof(CgScalars)));
     m->omega_scalar = 1.0;
     m->use_omega_scalar = 0;
@@ -669,7 +685,7 @@ extern "C" int bb_csr_upload(bb_ctx* ctx, int64_t n, int64_t p, int64_t nnz,
             CKC(cudaMalloc((void**)&m->csr_val, nb * sizeof(double)));
             if (nnz > 0) CKC(cudaMemcpyAsync(m->csr_val, data, (size_t)nnz * sizeof(double), cudaMemcpyHostToDevice, st));
         }
-        CK(alloc_d(&m->col_offset, p));
+        CK(alloc_d(st, &m->col_offset, p));
         if (column_offset && p > 0)
             CKC(cudaMemcpyAsync(m->col_offset, column_offset, (size_t)p * sizeof(double), cudaMemcpyHostToDevice, st));
         // canonical CSC: stable sort of the CSR nnz sequence by column

@@ -1,0 +1,48 @@
+import os
+import sys
+import warnings
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+REF_DIR = os.path.join(ROOT, 'oracle', '_ref')
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
+
+
+def golden(name):
+    return np.load(os.path.join(GOLDEN, name), allow_pickle=False)
+
+
+def import_reference():
+    """The reference package built into oracle/_ref by oracle/build_ref.sh, or None."""
+    if not os.path.isdir(os.path.join(REF_DIR, 'bayesbridge')):
+        return None
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            import bayesbridge
+        return bayesbridge
+    except Exception:
+        return None
+
+
+@pytest.fixture(scope='session')
+def ctx():
+    from bayesbridge_b200 import _lib
+    return _lib.Context.default()
+
+
+@pytest.fixture(autouse=True)
+def _quiet():
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        yield

@@ -1,0 +1,137 @@
+"""GPU: the device CG sampler vs outputs of the reference's ConjugateGradientSampler (golden/cg_ref.npz,
+same injected noise: cg_sampler.py:51-52,61-62 re-seed np.random, so eps is regenerated identically) and
+vs the numpy oracle.  north_star tolerance: relative error <= 1e-8 in fp64."""
+import numpy as np
+import scipy.sparse as sp
+import pytest
+
+from conftest import golden
+from oracle import cg_oracle as co
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-8
+
+
+def relerr(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def _case(g, name, ctx):
+    from bayesbridge_b200.design_matrix import GpuSparseDesignMatrix, GpuDenseDesignMatrix
+    if name == 'dense':
+        X = g['dense_X']
+        return X, GpuDenseDesignMatrix(X.copy(), center_predictor=True, add_intercept=True, ctx=ctx)
+    X = sp.csr_matrix((g[name + '_data'], g[name + '_indices'], g[name + '_indptr']), shape=tuple(g[name + '_shape']))
+    return X, GpuSparseDesignMatrix(X, center_predictor=True, add_intercept=True, ctx=ctx)
+
+
+@pytest.mark.parametrize('name', ['sparse_bin', 'sparse_val', 'dense'])
+def test_cg_sample_matches_reference(ctx, name):
+    from bayesbridge_b200.reg_coef_sampler import ConjugateGradientSampler
+    g = golden('cg_ref.npz')
+    X, D = _case(g, name, ctx)
+    P = D.shape[1]
+    omega, pps, z, x0, sd = (g[name + '_' + k] for k in ('omega', 'pps', 'z', 'x0', 'sd'))
+    for k, (maxiter, atol_unit) in enumerate(g['rules']):
+        coef, info = ConjugateGradientSampler(1).sample(
+            D, omega, pps, z, x0.copy(), 'prior', sd, maxiter=int(maxiter), atol=atol_unit * np.sqrt(P), seed=7)
+        ref = g['%s_coef_%d' % (name, k)]
+        assert relerr(coef, ref) <= TOL, (name, maxiter, atol_unit)
+        assert info['n_iter'] == int(g['%s_niter_%d' % (name, k)])
+        assert info['converged'] == bool(g['%s_conv_%d' % (name, k)])
+
+
+@pytest.mark.parametrize('n,p,density', [(5000, 400, 0.05), (30000, 2500, 0.01)])
+def test_cg_sample_vs_oracle_and_dense_solve(ctx, n, p, density):
+    from bayesbridge_b200.design_matrix import GpuSparseDesignMatrix
+    from bayesbridge_b200.reg_coef_sampler import ConjugateGradientSampler
+    rs = np.random.RandomState(n)
+    X = sp.random(n, p, density=density, format='csr', random_state=rs, dtype=np.float64)
+    X.data[:] = 1.0
+    rng = np.random.default_rng(1)
+    D = GpuSparseDesignMatrix(X, center_predictor=True, add_intercept=True, ctx=ctx)
+    O = co.DesignOracle(X, True, True)
+    P = p + 1
+    omega = rng.random(n) * 0.25 + 0.01
+    pps = np.concatenate(([0.5], 1 / (0.1 * rng.random(p) + 1e-3)))
+    z, x0, sd = rng.standard_normal(P), 0.01 * rng.standard_normal(P), 0.5 + rng.random(P)
+    s = co.precond_scale_prior(pps, 1, sd)
+    for atol_unit in (1e-5, 1e-12):
+        np.random.seed(11)
+        e1, e2 = np.random.randn(n), np.random.randn(P)
+        ref, rinfo = co.cg_sample(O, omega, pps, z, x0, s, 500, atol_unit * np.sqrt(P), e1, e2)
+        coef, info = ConjugateGradientSampler(1).sample(
+            D, omega, pps, z, x0.copy(), 'prior', sd, maxiter=500, atol=atol_unit * np.sqrt(P), seed=11)
+        assert relerr(coef, ref) <= TOL
+        assert info['n_iter'] == rinfo['n_iter'] and info['converged']
+    if p <= 500:
+        # tight solve == the exact Gaussian draw: Phi beta = z + X' sqrt(omega) e1 + pps e2
+        rhs = z + O.Tdot(np.sqrt(omega) * e1) + pps * e2
+        exact = co.exact_gaussian_mean(O, omega, pps, rhs)
+        assert relerr(coef, exact) <= TOL
+
+
+def test_cg_warns_and_reports_when_not_converged(ctx):
+    from bayesbridge_b200.reg_coef_sampler import ConjugateGradientSampler
+    g = golden('cg_ref.npz')
+    _, D = _case(g, 'sparse_val', ctx)
+    omega, pps, z, x0, sd = (g['sparse_val_' + k] for k in ('omega', 'pps', 'z', 'x0', 'sd'))
+    import warnings
+    with warnings.catch_warnings(record=True) as rec:
+        warnings.simplefilter('always')
+        _, info = ConjugateGradientSampler(1).sample(D, omega, pps, z, x0, 'prior', sd, maxiter=2, atol=1e-12, seed=1)
+    assert info['n_iter'] == 2 and not info['converged']
+    assert any('did not achieve' in str(r.message) for r in rec)
+
+
+def test_cg_zero_rhs_and_zero_initial_guess(ctx):
+    from bayesbridge_b200.reg_coef_sampler import ConjugateGradientSampler
+    from bayesbridge_b200 import _lib
+    import ctypes
+    g = golden('cg_ref.npz')
+    _, D = _case(g, 'sparse_val', ctx)
+    n, P = D.shape
+    omega, pps, sd = (g['sparse_val_' + k] for k in ('omega', 'pps', 'sd'))
+    # zero right-hand side: scipy returns b (= 0) with info 0
+    coef = np.ones(P); n_iter, info = ctypes.c_int(), ctypes.c_int()
+    s = co.precond_scale_prior(pps, 1, sd)
+    _lib.check(_lib.load().bb_cg_sample(
+        D._mat, _lib.dptr(omega), _lib.dptr(pps), _lib.dptr(np.zeros(P)), _lib.dptr(np.ones(P)), _lib.dptr(s),
+        1e-6, 50, _lib.BB_NOISE_INJECT, _lib.dptr(np.zeros(n)), _lib.dptr(np.zeros(P)), 0, 0,
+        _lib.dptr(coef), ctypes.byref(n_iter), ctypes.byref(info), None))
+    assert np.all(coef == 0) and n_iter.value == 0 and info.value == 0
+    # x0 = 0 takes scipy's `r = b.copy()` branch: same answer as the oracle
+    z = g['sparse_val_z']
+    O = co.DesignOracle(sp.csr_matrix((g['sparse_val_data'], g['sparse_val_indices'], g['sparse_val_indptr']),
+                                      shape=tuple(g['sparse_val_shape'])), True, True)
+    np.random.seed(3)
+    e1, e2 = np.random.randn(n), np.random.randn(P)
+    ref, rinfo = co.cg_sample(O, omega, pps, z, np.zeros(P), s, 500, 1e-10, e1, e2)
+    got, ginfo = ConjugateGradientSampler(1).sample(D, omega, pps, z, np.zeros(P), 'prior', sd, maxiter=500, atol=1e-10, seed=3)
+    assert relerr(got, ref) <= TOL and ginfo['n_iter'] == rinfo['n_iter']
+
+
+def test_device_noise_is_reproducible_and_gaussian(ctx):
+    """BB_NOISE_PHILOX: same (seed, offset) -> same draw; the injected-noise path fed with the Philox
+    normals (bb_philox_normal exposes the same streams) gives the identical coefficient vector."""
+    from bayesbridge_b200.reg_coef_sampler import ConjugateGradientSampler
+    from bayesbridge_b200 import _lib
+    g = golden('cg_ref.npz')
+    _, D = _case(g, 'sparse_bin', ctx)
+    n, P = D.shape
+    omega, pps, z, x0, sd = (g['sparse_bin_' + k] for k in ('omega', 'pps', 'z', 'x0', 'sd'))
+    S = ConjugateGradientSampler(1)
+    a, _ = S.sample(D, omega, pps, z, x0, 'prior', sd, maxiter=500, atol=1e-9, noise='device', philox=(123, 4))
+    b, _ = S.sample(D, omega, pps, z, x0, 'prior', sd, maxiter=500, atol=1e-9, noise='device', philox=(123, 4))
+    c, _ = S.sample(D, omega, pps, z, x0, 'prior', sd, maxiter=500, atol=1e-9, noise='device', philox=(123, 5))
+    assert np.array_equal(a, b) and not np.array_equal(a, c)
+    e1, e2 = np.empty(n), np.empty(P)
+    lib = _lib.load()
+    _lib.check(lib.bb_philox_normal(ctx.handle, n, 0, 123, 4, 0, _lib.dptr(e1)))
+    _lib.check(lib.bb_philox_normal(ctx.handle, P, 1, 123, 4, 0, _lib.dptr(e2)))
+    assert abs(e1.mean()) < 5 / np.sqrt(n) and abs(e1.std() - 1) < 0.1
+    s = co.precond_scale_prior(pps, 1, sd)
+    O = co.DesignOracle(sp.csr_matrix((g['sparse_bin_data'], g['sparse_bin_indices'], g['sparse_bin_indptr']),
+                                      shape=tuple(g['sparse_bin_shape'])), True, True)
+    ref, _ = co.cg_sample(O, omega, pps, z, x0, s, 500, 1e-9, e1, e2)
+    assert relerr(a, ref) <= TOL

@@ -1,0 +1,162 @@
+"""GPU: design-matrix products through the C-ABI vs the oracle and vs outputs of the reference
+(golden/design_ref.npz); bit-exact CSR/CSC construction; edge cases."""
+import numpy as np
+import scipy.sparse as sp
+import pytest
+
+from conftest import golden
+from oracle import cg_oracle as co
+
+pytestmark = pytest.mark.gpu
+
+
+def _designs():
+    from bayesbridge_b200.design_matrix import GpuSparseDesignMatrix, GpuDenseDesignMatrix
+    return GpuSparseDesignMatrix, GpuDenseDesignMatrix
+
+
+def relerr(a, b):
+    return np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(b), 1e-300)
+
+
+def random_sparse(n, p, density, seed, binary=False, hot_column=True):
+    rs = np.random.RandomState(seed)
+    X = sp.random(n, p, density=density, format='csr', random_state=rs, dtype=np.float64)
+    if hot_column and n > 10 and p > 3:      # a column with n/2 entries: segments that straddle many tiles
+        rows = rs.choice(n, n // 2, replace=False)
+        X = (X + sp.csr_matrix((np.ones(n // 2), (rows, np.full(n // 2, 2))), shape=(n, p))).tocsr()
+    if binary:
+        X.data[:] = 1.0
+    return X
+
+
+def test_products_match_reference_outputs(ctx):
+    Sparse, Dense = _designs()
+    g = golden('design_ref.npz')
+    Xd = g['X_dense_image']
+    for c in (0, 1):
+        for i in (0, 1):
+            key = '%d%d' % (c, i)
+            for D, pre in ((Sparse(sp.csr_matrix(Xd), center_predictor=bool(c), add_intercept=bool(i), ctx=ctx), ''),
+                           (Dense(Xd.copy(), center_predictor=bool(c), add_intercept=bool(i), ctx=ctx), 'd')):
+                assert relerr(D.dot(g['v_' + key]), g[pre + 'dot_' + key]) < 1e-13
+                assert relerr(D.Tdot(g['w']), g[pre + 'tdot_' + key]) < 1e-13
+                assert relerr(D.compute_fisher_info(g['weight'], diag_only=True), g[pre + 'fisher_' + key]) < 1e-12
+
+
+@pytest.mark.parametrize('n,p,density', [(300, 40, 0.2), (20000, 700, 0.02), (60000, 3000, 0.004)])
+@pytest.mark.parametrize('binary', [False, True])
+@pytest.mark.parametrize('slab,stage', [(0, 1), (0, 0), (64, 1), (1024, 1), (1024, 0)])
+def test_sparse_products_vs_oracle(ctx, n, p, density, binary, slab, stage):
+    Sparse, _ = _designs()
+    ctx.set_option('slab_width', slab)
+    ctx.set_option('spmv_stage', stage)
+    try:
+        X = random_sparse(n, p, density, seed=n + p, binary=binary)
+        rng = np.random.default_rng(5)
+        for center in (False, True):
+            for icpt in (False, True):
+                D = Sparse(X, center_predictor=center, add_intercept=icpt, ctx=ctx)
+                assert D.is_binary == binary
+                O = co.DesignOracle(X, center, icpt)
+                v, w, wt = rng.standard_normal(D.shape[1]), rng.standard_normal(n), rng.random(n)
+                assert relerr(D.dot(v), O.dot(v)) < 1e-12
+                assert relerr(D.Tdot(w), O.Tdot(w)) < 1e-12
+                assert relerr(D.compute_fisher_info(wt, diag_only=True), O.fisher_diag(wt)) < 1e-12
+    finally:
+        ctx.set_option('slab_width', 0)
+        ctx.set_option('spmv_stage', 1)
+
+
+def test_products_are_bit_reproducible(ctx):
+    Sparse, _ = _designs()
+    X = random_sparse(30000, 900, 0.01, seed=3)
+    D = Sparse(X, center_predictor=True, add_intercept=True, ctx=ctx)
+    rng = np.random.default_rng(0)
+    v, w = rng.standard_normal(901), rng.standard_normal(30000)
+    assert np.array_equal(D.dot(v), D.dot(v))
+    assert np.array_equal(D.Tdot(w), D.Tdot(w))
+
+
+@pytest.mark.parametrize('n,p', [(200, 30), (5000, 1300)])
+def test_dense_products_vs_oracle(ctx, n, p):
+    _, Dense = _designs()
+    rng = np.random.default_rng(n)
+    X = rng.standard_normal((n, p))
+    for center in (False, True):
+        for icpt in (False, True):
+            D = Dense(X.copy(), center_predictor=center, add_intercept=icpt, ctx=ctx)
+            O = co.DesignOracle(X, center, icpt)
+            v, w, wt = rng.standard_normal(D.shape[1]), rng.standard_normal(n), rng.random(n)
+            assert relerr(D.dot(v), O.dot(v)) < 1e-12
+            assert relerr(D.Tdot(w), O.Tdot(w)) < 1e-12
+            assert relerr(D.compute_fisher_info(wt, diag_only=True), O.fisher_diag(wt)) < 1e-12
+
+
+def test_csr_upload_and_csc_construction_are_bit_exact(ctx):
+    """CSC on the device == scipy's tocsr().tocsc() byte for byte, including unsorted rows and duplicates."""
+    Sparse, _ = _designs()
+    rs = np.random.RandomState(4)
+    cases = [random_sparse(5000, 300, 0.03, 1), random_sparse(40000, 1200, 0.01, 2, binary=True)]
+    # unsorted column indices within rows + duplicate entries (scipy keeps both)
+    n, p, nnz = 700, 50, 9000
+    indptr = np.sort(np.concatenate(([0, nnz], rs.randint(0, nnz, n - 1)))).astype(np.int32)
+    indices = rs.randint(0, p, nnz).astype(np.int32)
+    data = rs.standard_normal(nnz)
+    cases.append(sp.csr_matrix((data, indices, indptr), shape=(n, p)))
+    for X in cases:
+        D = Sparse(X, center_predictor=False, add_intercept=False, ctx=ctx, pattern_only=False)
+        ip, ix, dv = D.export_csr()
+        assert np.array_equal(ip, X.indptr) and np.array_equal(ix, X.indices) and np.array_equal(dv, X.data)
+        C = X.tocsc()
+        ip, ix, dv = D.export_csc()
+        assert ip.dtype == C.indptr.dtype == np.int32
+        assert np.array_equal(ip, C.indptr) and np.array_equal(ix, C.indices) and np.array_equal(dv, C.data)
+        # and the products on the unsorted / duplicated matrix are still right
+        v = rs.standard_normal(X.shape[1])
+        assert relerr(D.dot(v), X @ v) < 1e-12
+
+
+def test_edge_cases(ctx):
+    Sparse, _ = _designs()
+    # empty rows, empty columns, an all-zero matrix, a single entry
+    X = sp.csr_matrix((np.array([2.0, -1.0, 3.0]), (np.array([0, 5, 5]), np.array([1, 1, 6]))), shape=(9, 8))
+    for Xc in (X, sp.csr_matrix((6, 4)), sp.csr_matrix(([1.5], ([2], [3])), shape=(4, 5))):
+        D = Sparse(Xc, center_predictor=False, add_intercept=True, ctx=ctx)
+        A = np.hstack((np.ones((Xc.shape[0], 1)), Xc.toarray()))
+        v, w = np.arange(1., A.shape[1] + 1), np.arange(1., A.shape[0] + 1)
+        assert np.allclose(D.dot(v), A @ v, rtol=1e-14, atol=1e-14)
+        assert np.allclose(D.Tdot(w), A.T @ w, rtol=1e-14, atol=1e-14)
+    with pytest.raises(ValueError):
+        D.dot(np.ones(3))
+    with pytest.raises(NotImplementedError):
+        D.compute_fisher_info(np.ones(4), diag_only=False)
+
+
+def test_constant_column_is_dropped_with_warning(ctx):
+    Sparse, Dense = _designs()
+    rng = np.random.default_rng(1)
+    X = rng.standard_normal((50, 6))
+    X[:, 2] = 1.0
+    import warnings
+    with warnings.catch_warnings(record=True) as rec:
+        warnings.simplefilter('always')
+        D = Dense(X.copy(), add_intercept=True, ctx=ctx)
+        S = Sparse(sp.csr_matrix(X), add_intercept=True, ctx=ctx)
+    assert D.shape == S.shape == (50, 6)       # 5 predictors + intercept
+    assert any('Intercept column' in str(r.message) for r in rec)
+
+
+def test_memoised_dot_and_counters(ctx):
+    Sparse, _ = _designs()
+    X = random_sparse(400, 30, 0.2, 8)
+    D = Sparse(X, center_predictor=True, add_intercept=True, ctx=ctx)
+    v = np.linspace(-1, 1, 31)
+    D.memoize_dot(True)
+    a = D.dot(v); b = D.dot(v.copy())
+    assert a is b and D.get_dot_count() == (1, 0)
+    D.memoize_dot(False)
+    D.Tdot(np.ones(400))
+    assert D.n_matvec == 2
+    D.reset_matvec_count()
+    assert D.n_matvec == 0

@@ -1,0 +1,147 @@
+"""GPU: the drop-in Gibbs sampler.
+(i)  compatibility mode -- host RNG for the CG noise (options={'noise': 'host'}) and the oracle's
+     bit-exact ports of the reference's PG / tilted-stable streams plugged into BasicRandom -- replays the
+     reference's regression test (tests/regression_tests/test_gibb.py, 'cg' combos) and the cupy parity
+     test template (tests/gpu_tests/test_gibbs.py): chain vs the reference chain and its saved vectors;
+(ii) device-RNG mode -- posterior summaries agree with a reference chain within Monte-Carlo error."""
+import os
+import numpy as np
+import scipy.sparse as sp
+import pytest
+
+from conftest import golden, GOLDEN, import_reference
+from oracle.rand_port import PolyaGammaPort, TiltedStablePort
+
+pytestmark = pytest.mark.gpu
+
+
+def _bb():
+    import bayesbridge_b200 as bb
+    return bb
+
+
+def _test_gibb_problem(family):
+    g = golden('chain_ref.npz')
+    X = g[family + '_X']
+    if family == 'logit':
+        return (g['logit_n_success'], g['logit_n_trial']), sp.csr_matrix(X), g
+    return g['linear_y'], X, g
+
+
+def _compat_bridge(family, ctx):
+    bb = _bb()
+    outcome, X, g = _test_gibb_problem(family)
+    prior = bb.RegressionCoefPrior(sd_for_intercept=2., regularizing_slab_size=1., bridge_exponent=0.25)
+    bridge = bb.BayesBridge(bb.RegressionModel(outcome, X, family, ctx=ctx), prior)
+    bridge.rg.pg, bridge.rg.ts = PolyaGammaPort(), TiltedStablePort()     # the reference's streams
+    return bridge, g
+
+
+@pytest.mark.parametrize('family', ['linear', 'logit'])
+def test_compat_chain_reproduces_reference(ctx, family):
+    bridge, g = _compat_bridge(family, ctx)
+    samples, info = bridge.gibbs(10, 0, init={'global_scale': 0.1, 'local_scale': np.ones(50)},
+                                 coef_sampler_type='cg', seed=0, params_to_save='all', options={'noise': 'host'})
+    saved = np.load(os.path.join(GOLDEN, 'ref_saved', family + '_cg_samples.npy'))
+    assert np.allclose(samples['coef'][:, -1], saved, rtol=.001, atol=10e-6)       # reference's own criterion
+    assert np.allclose(samples['coef'], g[family + '_coef'], rtol=0, atol=1e-5)   # cupy-parity criterion (atol 1e-5)
+    assert np.allclose(samples['global_scale'], g[family + '_gscale'], rtol=1e-4)
+    n_cg = info['_reg_coef_sampling_info']['n_cg_iter']
+    assert np.max(np.abs(n_cg - g[family + '_n_cg'])) <= 1
+
+
+def test_compat_chain_resume_equals_uninterrupted(ctx):
+    bridge, g = _compat_bridge('logit', ctx)
+    init = {'global_scale': 0.1, 'local_scale': np.ones(50)}
+    s1, i1 = bridge.gibbs(5, 0, init=init, coef_sampler_type='cg', seed=0, params_to_save='all', options={'noise': 'host'})
+    bridge2, _ = _compat_bridge('logit', ctx)
+    s2, i2 = bridge2.gibbs_resume(i1, 5, merge=True, prev_samples=s1)
+    assert s2['coef'].shape == (51, 10) and i2['n_iter'] == 10
+    assert np.allclose(s2['coef'], g['logit_coef'], rtol=0, atol=1e-5)
+
+
+def test_device_chain_resume_is_exact(ctx):
+    """Device RNG: the chain state (coef, scales, omega) + Philox (seed, offset) + numpy state resumes bit-exactly."""
+    bb = _bb()
+    outcome, X, _ = _test_gibb_problem('logit')
+    prior = bb.RegressionCoefPrior(sd_for_intercept=2., regularizing_slab_size=1., bridge_exponent=0.5)
+    init = {'global_scale': 0.1, 'local_scale': np.ones(50)}
+    full, _ = bb.BayesBridge(bb.RegressionModel(outcome, X, 'logit', ctx=ctx), prior).gibbs(
+        12, 0, init=init, coef_sampler_type='cg', seed=3, params_to_save='all')
+    b1 = bb.BayesBridge(bb.RegressionModel(outcome, X, 'logit', ctx=ctx), prior)
+    s1, i1 = b1.gibbs(6, 0, init=init, coef_sampler_type='cg', seed=3, params_to_save='all')
+    b2 = bb.BayesBridge(bb.RegressionModel(outcome, X, 'logit', ctx=ctx), prior)
+    s2, _ = b2.gibbs_resume(i1, 6, merge=True, prev_samples=s1)
+    assert np.array_equal(s2['coef'], full['coef'])
+    assert np.array_equal(s2['obs_prec'], full['obs_prec'])
+
+
+def _c1_like(n=4000, p=300, seed=0):
+    rs = np.random.RandomState(seed)
+    X = sp.random(n, p, density=0.03, format='csr', random_state=rs, dtype=np.float64)
+    X.data[:] = 1.0
+    beta = np.zeros(p)
+    beta[:5], beta[5:10] = 1.5, -1.0
+    y = rs.binomial(1, 1 / (1 + np.exp(-(X @ beta - 0.5))))
+    return y, X, beta
+
+
+def test_device_rng_chain_matches_reference_posterior(ctx):
+    """Posterior means of a device-RNG chain vs a reference chain (different random streams): agreement within
+    Monte-Carlo error. Uses the reference's saved chain summary in golden/posterior_ref.npz."""
+    bb = _bb()
+    g = golden('posterior_ref.npz')
+    y, X, beta = _c1_like()
+    assert np.array_equal(y, g['y'])
+    model = bb.RegressionModel(y, X, family='logit', ctx=ctx)
+    bridge = bb.BayesBridge(model, bb.RegressionCoefPrior(bridge_exponent=.5))
+    samples, info = bridge.gibbs(n_iter=1500, n_burnin=500, coef_sampler_type='cg', seed=1)
+    assert info['options']['coef_sampler_type'] == 'cg'
+    mean, sd = samples['coef'].mean(1), samples['coef'].std(1)
+    ref_mean, ref_sd = g['coef_mean'], g['coef_sd']
+    # MCMC standard errors: allow 6 se with an effective sample size of ~ N/10 on both sides, plus CG tolerance
+    se = np.sqrt(sd ** 2 + ref_sd ** 2) / np.sqrt(100)
+    assert np.all(np.abs(mean - ref_mean) < 6 * se + 1e-3)
+    big = np.abs(ref_mean) > 0.5
+    assert big.sum() >= 8 and np.allclose(mean[big], ref_mean[big], rtol=0.15)
+    assert np.log(samples['global_scale']).mean() == pytest.approx(float(g['log_gscale_mean']), abs=0.25)
+    assert samples['logp'].mean() == pytest.approx(float(g['logp_mean']), rel=0.02)
+    n_cg = info['_reg_coef_sampling_info']['n_cg_iter']
+    assert n_cg.mean() == pytest.approx(float(g['n_cg_mean']), rel=0.25)
+
+
+def test_linear_dense_device_chain_recovers_signal(ctx):
+    bb = _bb()
+    rng = np.random.default_rng(0)
+    n, p = 3000, 120
+    X = rng.standard_normal((n, p))
+    beta = np.zeros(p); beta[:6] = (2., -2., 1., -1., .5, -.5)
+    y = 1.0 + X @ beta + rng.standard_normal(n)
+    bridge = bb.BayesBridge(bb.RegressionModel(y, X, 'linear', ctx=ctx), bb.RegressionCoefPrior(bridge_exponent=.5))
+    s, info = bridge.gibbs(400, 100, coef_sampler_type='cg', seed=0, params_to_save='all')
+    m = s['coef'].mean(1)
+    assert m[0] == pytest.approx(1.0, abs=0.1)
+    assert np.allclose(m[1:7], beta[:6], atol=0.1)
+    assert np.abs(m[7:]).max() < 0.1
+    assert s['obs_prec'].mean() == pytest.approx(1.0, rel=0.15)
+
+
+def test_api_contract(ctx):
+    bb = _bb()
+    y, X, _ = _c1_like(600, 40)
+    model = bb.RegressionModel(y, X, family='logit', ctx=ctx)
+    assert model.design.use_gpu and model.design.is_sparse and not model.design.use_cupy
+    bridge = bb.BayesBridge(model, bb.RegressionCoefPrior())
+    for bad in ('cholesky', 'hmc'):                      # as the reference does for cupy matrices
+        with pytest.raises(ValueError):
+            bridge.gibbs(n_iter=1, coef_sampler_type=bad)
+    s, info = bridge.gibbs(n_iter=3, init={'coef': np.ones(model.n_pred)}, seed=1)   # gpu_tests/test_gibbs.py:32-44
+    assert info['options']['coef_sampler_type'] == 'cg'
+    assert s['coef'].shape == (41, 3) and s['logp'].shape == (3,)
+    for key in ('_markov_chain_state', '_random_gen_state', '_reg_coef_sampler_state', 'runtime'):
+        assert key in info
+    assert info['_markov_chain_state']['obs_prec'].shape == (600,)
+    with pytest.raises(NotImplementedError):
+        bb.RegressionModel((y, y), X, family='cox', ctx=ctx)
+    with pytest.raises(ValueError):
+        bb.RegressionModel(y[:-1], X, family='logit', ctx=ctx)
