@@ -28,6 +28,8 @@ SIGNATURES = {
     'bb_get_option': (c_int, [c_void_p, c_char_p, P_i64]),
     'bb_get_launch_count': (c_int, [c_void_p, P_i64]),
     'bb_reset_launch_count': (c_int, [c_void_p]),
+    'bb_get_device_ms': (c_int, [c_void_p, P_dbl]),
+    'bb_reset_device_ms': (c_int, [c_void_p]),
     'bb_sync': (c_int, [c_void_p]),
     'bb_comm_unique_id': (c_int, [c_char_p, ctypes.c_char_p]),
     'bb_comm_init': (c_int, [c_void_p, c_char_p, c_int, c_int, c_char_p]),
@@ -152,6 +154,18 @@ class Context:
 
     def reset_launch_count(self):
         check(load().bb_reset_launch_count(self.handle))
+
+    def device_ms(self):
+        """Device milliseconds spent inside library entry points since the last reset (CUDA events)."""
+        v = c_dbl()
+        check(load().bb_get_device_ms(self.handle, ctypes.byref(v)))
+        return v.value
+
+    def reset_device_ms(self):
+        check(load().bb_reset_device_ms(self.handle))
+
+    def sync(self):
+        check(load().bb_sync(self.handle))
 
     def init_comm_from_torch(self):
         """Attach an NCCL communicator spanning the ranks of the current torch.distributed job.

@@ -229,6 +229,7 @@ extern "C" int bb_cg_sample(bb_mat* m, const double* omega, const double* prior_
     bb_ctx* ctx = m->ctx;
     cudaStream_t st = ctx->stream;
     BB_CUDA(cudaSetDevice(ctx->device));
+    BBTimer timer_(ctx);
     const size_t Pb = (size_t)m->P * sizeof(double), nb = (size_t)m->n * sizeof(double);
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (stats) { BB_CUDA(cudaEventCreate(&ev0)); BB_CUDA(cudaEventCreate(&ev1)); BB_CUDA(cudaEventRecord(ev0, st)); }
@@ -304,7 +305,9 @@ extern "C" int bb_cg_sample(bb_mat* m, const double* omega, const double* prior_
     BB_LAUNCHED(ctx);
     BB_CUDA(cudaMemcpyAsync(coef_out, m->out_P, Pb, cudaMemcpyDeviceToHost, st));
     if (stats) BB_CUDA(cudaEventRecord(ev1, st));
+    timer_.end();
     BB_CUDA(cudaStreamSynchronize(st));
+    timer_.commit();
     const int done = m->cg_host->done;
     m->last_n_iter = m->cg_host->iter;
     if (n_iter) *n_iter = m->cg_host->iter;

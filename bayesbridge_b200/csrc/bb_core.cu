@@ -43,6 +43,8 @@ extern "C" int bb_init(int device, bb_ctx** out) {
     c->opt_use_graph = 1;
     c->nranks = 1;
     c->rank = 0;
+    BB_CUDA(cudaEventCreate(&c->tev0));
+    BB_CUDA(cudaEventCreate(&c->tev1));
     *out = c;
     return BB_OK;
 }
@@ -57,6 +59,8 @@ extern "C" int bb_destroy(bb_ctx* c) {
     }
     if (c->flush_buf) cudaFree(c->flush_buf);
     if (c->pinned) cudaFreeHost(c->pinned);
+    cudaEventDestroy(c->tev0);
+    cudaEventDestroy(c->tev1);
     cudaStreamDestroy(c->stream);
     free(c);
     return BB_OK;
@@ -104,6 +108,18 @@ extern "C" int bb_get_launch_count(bb_ctx* c, int64_t* launches) {
 extern "C" int bb_reset_launch_count(bb_ctx* c) {
     BB_ARG(c != nullptr, "ctx");
     c->launches = 0;
+    return BB_OK;
+}
+
+extern "C" int bb_get_device_ms(bb_ctx* c, double* ms) {
+    BB_ARG(c && ms, "ctx/ms");
+    *ms = c->dev_ms;
+    return BB_OK;
+}
+
+extern "C" int bb_reset_device_ms(bb_ctx* c) {
+    BB_ARG(c != nullptr, "ctx");
+    c->dev_ms = 0.0;
     return BB_OK;
 }
 

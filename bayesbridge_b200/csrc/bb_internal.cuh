@@ -68,9 +68,26 @@ struct bb_ctx {
     // generic host pinned staging
     double* pinned;
     size_t pinned_bytes;
+    // device-time accounting of the public entry points (CUDA events on `stream`)
+    cudaEvent_t tev0, tev1;
+    double dev_ms;
+    int timer_depth;
 };
 
 int bb_ctx_pinned(bb_ctx* ctx, size_t bytes, double** out);
+// bracket the device work of one entry point: begin() before the first enqueue, end() after the
+// last enqueue and BEFORE the final stream sync, commit() after that sync.
+struct BBTimer {
+    bb_ctx* c; bool active;
+    explicit BBTimer(bb_ctx* ctx) : c(ctx), active(false) {
+        if (c->timer_depth++ == 0) { active = (cudaEventRecord(c->tev0, c->stream) == cudaSuccess); }
+    }
+    void end() { if (active) cudaEventRecord(c->tev1, c->stream); }
+    void commit() {
+        if (active) { float ms = 0.f; if (cudaEventElapsedTime(&ms, c->tev0, c->tev1) == cudaSuccess) c->dev_ms += ms; active = false; }
+    }
+    ~BBTimer() { c->timer_depth--; }
+};
 int bb_allreduce_dev(bb_ctx* ctx, double* dbuf, i64 count);   // in place, on ctx->stream
 
 // ------------------------------------------------------------------------------------------
@@ -93,8 +110,9 @@ struct SlabFmt {
     int   ntiles;
     TileMeta* tiles;    // [ntiles]
     int*  head_seg;     // [ntiles] virtual segment continued from the previous tile, or -1
-    int   nunits;
-    WorkUnit* units;    // [nunits] one CTA each
+    int2* tmeta;        // [ntiles] {first owned virtual segment, number owned}
+    int*  slab_tile0;   // [nslab+1] first tile of each slab
+    int*  slab_nnz0;    // [nslab+1] first nnz of each slab
     double* part;       // [nslab*n_seg] per-slab partial sums (output of the kernel)
     double* head_part;  // [ntiles]
 };

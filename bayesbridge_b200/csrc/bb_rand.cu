@@ -279,6 +279,7 @@ extern "C" int bb_pg_sample(bb_ctx* ctx, int64_t n, const int32_t* shape, const 
     BB_ARG(shape && tilt && out, "null pointer");
     for (i64 i = 0; i < n; ++i) BB_ARG(shape[i] >= 0, "shape must be non-negative");
     BB_CUDA(cudaSetDevice(ctx->device));
+    BBTimer timer_(ctx);
     cudaStream_t st = ctx->stream;
     int* d_shape = nullptr; double *d_tilt = nullptr, *d_out = nullptr;
     BB_TRY(scratch_vec(ctx, (void**)&d_shape, (size_t)n * sizeof(int)));
@@ -294,7 +295,9 @@ extern "C" int bb_pg_sample(bb_ctx* ctx, int64_t n, const int32_t* shape, const 
         e = cudaPeekAtLastError();
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st);
+    timer_.end();
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    timer_.commit();
     if (e != cudaSuccess) { bb_set_error("bb_pg_sample: %s", cudaGetErrorString(e)); rc = BB_ERR_CUDA; }
     cudaFree(d_shape); cudaFree(d_tilt); cudaFree(d_out);
     return rc;
@@ -307,6 +310,7 @@ extern "C" int bb_tilted_stable_sample(bb_ctx* ctx, int64_t n, double char_exp, 
     BB_ARG(tilt && out, "null pointer");
     BB_ARG(char_exp > 0.0 && char_exp < 1.0, "characteristic exponent must be in (0,1)");
     BB_CUDA(cudaSetDevice(ctx->device));
+    BBTimer timer_(ctx);
     cudaStream_t st = ctx->stream;
     double *d_tilt = nullptr, *d_out = nullptr;
     BB_TRY(scratch_vec(ctx, (void**)&d_tilt, (size_t)n * sizeof(double)));
@@ -319,7 +323,9 @@ extern "C" int bb_tilted_stable_sample(bb_ctx* ctx, int64_t n, double char_exp, 
         e = cudaPeekAtLastError();
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st);
+    timer_.end();
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    timer_.commit();
     if (e != cudaSuccess) { bb_set_error("bb_tilted_stable_sample: %s", cudaGetErrorString(e)); rc = BB_ERR_CUDA; }
     cudaFree(d_tilt); cudaFree(d_out);
     return rc;
@@ -410,6 +416,7 @@ extern "C" int bb_pg_from_coef(bb_mat* m, const double* coef, uint64_t seed, uin
     bb_ctx* ctx = m->ctx;
     cudaStream_t st = ctx->stream;
     BB_CUDA(cudaSetDevice(ctx->device));
+    BBTimer timer_(ctx);
     BB_TRY(linear_predictor(m, coef));
     const int TB = 128;
     i64 nblk = (m->n + TB - 1) / TB;
@@ -427,7 +434,9 @@ extern "C" int bb_pg_from_coef(bb_mat* m, const double* coef, uint64_t seed, uin
     double ll = 0.0;
     BB_CUDA(cudaMemcpyAsync(&ll, m->traw, sizeof(double), cudaMemcpyDeviceToHost, st));
     if (omega_out) BB_CUDA(cudaMemcpyAsync(omega_out, m->omega, (size_t)m->n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    timer_.end();
     cudaError_t e = cudaStreamSynchronize(st);
+    timer_.commit();
     cudaFree(red_ll);
     if (e != cudaSuccess) { bb_set_error("bb_pg_from_coef: %s", cudaGetErrorString(e)); return BB_ERR_CUDA; }
     if (loglik) *loglik = ll;
@@ -440,6 +449,7 @@ extern "C" int bb_linear_rss(bb_mat* m, const double* coef, double* rss) {
     bb_ctx* ctx = m->ctx;
     cudaStream_t st = ctx->stream;
     BB_CUDA(cudaSetDevice(ctx->device));
+    BBTimer timer_(ctx);
     BB_TRY(linear_predictor(m, coef));
     int g = N_grid(m->n);
     k_rss<<<g, 256, 0, st>>>(m->n, m->n_success, m->eta, m->red + RED_LL * RED_MAX);
@@ -448,6 +458,8 @@ extern "C" int bb_linear_rss(bb_mat* m, const double* coef, double* rss) {
     ctx->launches++;
     BB_TRY(bb_allreduce_dev(ctx, m->traw, 1));
     BB_CUDA(cudaMemcpyAsync(rss, m->traw, sizeof(double), cudaMemcpyDeviceToHost, st));
+    timer_.end();
     BB_CUDA(cudaStreamSynchronize(st));
+    timer_.commit();
     return BB_OK;
 }

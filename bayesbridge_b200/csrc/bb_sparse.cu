@@ -95,44 +95,45 @@ __global__ void k_tile_meta(const int* __restrict__ ptr, i64 V, i64 n_seg, int n
     head_seg[t] = (ptr[vlo] > m.start) ? (int)(vlo - 1) : -1;
 }
 
+__global__ void k_compact_meta(const TileMeta* __restrict__ tiles, int ntiles, int2* __restrict__ tmeta) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < ntiles) tmeta[t] = make_int2(tiles[t].vlo, tiles[t].vhi - tiles[t].vlo);
+}
+
 // ------------------------------------------------------------------------------------------
-// The SpMV kernel.  One CTA per work unit (a run of tiles inside one slab); the CTA stages its slab
-// of the gather vector in shared memory once, after which its 32 warps run independently (no block
-// barrier): each warp streams 256-nnz tiles with coalesced loads of (idx, val) into registers,
-// software-prefetched one tile ahead, multiplies by the staged vector and reduces the products by
-// segment.  The segment boundaries of a tile are its "cut points" c_k = min(ptr[vlo+k], end)-start;
-// piece k = [c_{k-1}, c_k) belongs to the head (k = 0: a segment continued from the previous tile,
-// goes to head_part) or to owned segment vlo+k-1 (goes to part).  Few pieces: predicated register
-// sums + warp shuffles.  Many pieces: products to a per-warp shared buffer, one lane per piece.
-// The reduction shape depends only on static metadata, so results are bit-reproducible.
-struct TileRegs {
+// The SpMV kernel.  The tile sequence (all slabs concatenated) is cut into gridDim.x equal contiguous
+// ranges, one per CTA (grid = #SMs, one CTA per SM): perfectly balanced in nnz.  A CTA walks its
+// range slab by slab: it stages the slab of the gather vector in shared memory (block barrier), then
+// its 32 warps run independently over the slab's tiles: coalesced loads of (idx, val) into registers,
+// software-prefetched one tile ahead (the tile metadata two ahead, so no load in the steady state
+// waits on another), products into a per-warp shared buffer, and a segmented reduction in which
+// groups of G = 32/2^ceil(log2(pieces)) lanes each sum one piece.  The pieces of a tile are delimited
+// by its cut points c_k = min(ptr[vlo+k], end) - start: piece 0 is the head (a segment continued from
+// the previous tile -> head_part), piece k>0 is owned segment vlo+k-1 (-> part).  The reduction shape
+// depends only on static metadata, so results are bit-reproducible.
+template <bool BINARY>
+struct TileData {
     int ri[SPMV_ITEMS];
-    double rv[SPMV_ITEMS];
-    TileMeta m;
-    int cut;       // lane l: ptr[vlo + l] (l <= nown, capped at 31)
+    double rv[BINARY ? 1 : SPMV_ITEMS];
 };
 
 template <bool BINARY>
-__device__ __forceinline__ void tile_load(TileRegs& R, int t, const TileMeta* __restrict__ tiles,
-                                          const int* __restrict__ ptr, const int* __restrict__ idx,
-                                          const double* __restrict__ val, int lane) {
-    R.m = tiles[t];
+__device__ __forceinline__ void tile_fetch(TileData<BINARY>& R, int start, int end,
+                                           const int* __restrict__ idx, const double* __restrict__ val, int lane) {
 #pragma unroll
     for (int j = 0; j < SPMV_ITEMS; ++j) {
-        int k = R.m.start + j * 32 + lane;
-        bool ok = k < R.m.end;
+        int k = start + j * 32 + lane;
+        bool ok = k < end;
         R.ri[j] = ok ? idx[k] : -1;
         if (!BINARY) R.rv[j] = ok ? val[k] : 0.0;
     }
-    int nown = R.m.vhi - R.m.vlo;
-    R.cut = (lane <= nown) ? ptr[R.m.vlo + lane] : 0x7fffffff;
 }
 
 template <bool BINARY, bool STAGE>
 __global__ void __launch_bounds__(SPMV_THREADS, 1)
 k_seg_spmv(const int* __restrict__ ptr, const int* __restrict__ idx, const double* __restrict__ val,
-           const TileMeta* __restrict__ tiles, const WorkUnit* __restrict__ units,
-           const double* __restrict__ gvec, int W, i64 n_gather, int wstage,
+           const int2* __restrict__ tmeta, const int* __restrict__ slab_tile0, const int* __restrict__ slab_nnz0,
+           int nslab, int ntiles, const double* __restrict__ gvec, int W, i64 n_gather, int wstage,
            double* __restrict__ part, double* __restrict__ head_part, const int* __restrict__ done_flag)
 {
     if (done_flag != nullptr && *done_flag) return;
@@ -141,77 +142,102 @@ k_seg_spmv(const int* __restrict__ ptr, const int* __restrict__ idx, const doubl
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     double* wprod = smem + wstage + warp * SPMV_TILE;      // per-warp product buffer
-    const WorkUnit u = units[blockIdx.x];
-    const i64 gbase = (i64)u.slab * W;
-    if (STAGE) {
-        i64 rem = n_gather - gbase;
-        int wlen = rem < (i64)W ? (int)rem : W;
-        for (int i = tid; i < wlen; i += SPMV_THREADS) sv[i] = gvec[gbase + i];
+    const int t_lo = (int)((i64)ntiles * blockIdx.x / gridDim.x);
+    const int t_hi = (int)((i64)ntiles * (blockIdx.x + 1) / gridDim.x);
+    if (t_lo >= t_hi) return;
+    // slab containing tile t_lo: last s with slab_tile0[s] <= t_lo
+    int slab;
+    {
+        int lo = 0, hi = nslab;
+        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (slab_tile0[mid] <= t_lo) lo = mid; else hi = mid; }
+        slab = lo;
     }
-    int t = u.tile_lo + warp;
-    TileRegs R;
-    if (t < u.tile_hi) tile_load<BINARY>(R, t, tiles, ptr, idx, val, lane);
-    if (STAGE) __syncthreads();          // the only block barrier
-
-    while (t < u.tile_hi) {
-        // products of the current tile
-        double pr[SPMV_ITEMS];
-#pragma unroll
-        for (int j = 0; j < SPMV_ITEMS; ++j) {
-            double g = 0.0;
-            if (R.ri[j] >= 0) g = STAGE ? sv[R.ri[j] - (int)gbase] : __ldg(gvec + R.ri[j]);
-            pr[j] = BINARY ? g : R.rv[j] * g;
-        }
-        const TileMeta cur = R.m;
-        const int nown = cur.vhi - cur.vlo;
-        // cut point of this lane, relative to the tile
-        int c = min(R.cut, cur.end) - cur.start;
-        const int tnext = t + SPMV_WARPS;
-        if (tnext < u.tile_hi) tile_load<BINARY>(R, tnext, tiles, ptr, idx, val, lane);   // prefetch
-
-        if (nown < SPMV_REG_ITEMS) {
-            // register path: piece k = [c_{k-1}, c_k)
-            double mine = 0.0;
-            int a = 0;
-            for (int k = 0; k <= nown; ++k) {
-                int b = __shfl_sync(0xffffffffu, c, k);
-                double sacc = 0.0;
-#pragma unroll
-                for (int j = 0; j < SPMV_ITEMS; ++j) {
-                    int e = j * 32 + lane;
-                    sacc += (e >= a && e < b) ? pr[j] : 0.0;
-                }
-                sacc = warp_sum(sacc);
-                if (lane == k) mine = sacc;
-                a = b;
+    int cur = t_lo;
+    while (cur < t_hi) {
+        const int s_t0 = slab_tile0[slab];
+        const int sec_end = min(t_hi, slab_tile0[slab + 1]);
+        const int nnz0 = slab_nnz0[slab], nnz1 = slab_nnz0[slab + 1];
+        const i64 gbase = (i64)slab * W;
+        if (STAGE) {
+            __syncthreads();                               // previous section's readers are done
+            i64 rem = n_gather - gbase;
+            const int wlen = rem < (i64)W ? (int)rem : W;
+            const double* src = gvec + gbase;
+            int i = tid;
+            for (; i + 3 * SPMV_THREADS < wlen; i += 4 * SPMV_THREADS) {
+                double a0 = src[i], a1 = src[i + SPMV_THREADS], a2 = src[i + 2 * SPMV_THREADS], a3 = src[i + 3 * SPMV_THREADS];
+                sv[i] = a0; sv[i + SPMV_THREADS] = a1; sv[i + 2 * SPMV_THREADS] = a2; sv[i + 3 * SPMV_THREADS] = a3;
             }
-            if (lane == 0) head_part[t] = mine;
-            else if (lane <= nown) part[cur.vlo + lane - 1] = mine;
-        } else {
-            // shared path: one lane per piece, serial sum in nnz order
+            for (; i < wlen; i += SPMV_THREADS) sv[i] = src[i];
+        }
+        int t = cur + warp;
+        TileData<BINARY> R;
+        int2 m_cur = make_int2(0, 0), m_next = make_int2(0, 0);
+        int cut = 0;
+        if (t < sec_end) {
+            const int st0 = nnz0 + (t - s_t0) * SPMV_TILE;
+            tile_fetch<BINARY>(R, st0, min(st0 + SPMV_TILE, nnz1), idx, val, lane);
+            m_cur = tmeta[t];
+            if (t + SPMV_WARPS < sec_end) m_next = tmeta[t + SPMV_WARPS];
+            cut = (lane <= m_cur.y) ? ptr[m_cur.x + lane] : 0x7fffffff;
+        }
+        if (STAGE) __syncthreads();
+
+        while (t < sec_end) {
+            const int start = nnz0 + (t - s_t0) * SPMV_TILE;
+            const int end = min(start + SPMV_TILE, nnz1);
+            // products of the current tile -> per-warp shared buffer
             __syncwarp();
 #pragma unroll
-            for (int j = 0; j < SPMV_ITEMS; ++j) wprod[j * 32 + lane] = pr[j];
-            __syncwarp();
-            if (nown < 32) {
-                int a = __shfl_up_sync(0xffffffffu, c, 1);
-                if (lane == 0) a = 0;
-                if (lane <= nown) {
-                    double sacc = 0.0;
-                    for (int e = a; e < c; ++e) sacc += wprod[e];
-                    if (lane == 0) head_part[t] = sacc; else part[cur.vlo + lane - 1] = sacc;
-                }
-            } else {
-                for (int k = lane; k <= nown; k += 32) {
-                    int a = (k == 0) ? 0 : min(ptr[cur.vlo + k - 1], cur.end) - cur.start;
-                    int b = min(ptr[cur.vlo + k], cur.end) - cur.start;
-                    double sacc = 0.0;
-                    for (int e = a; e < b; ++e) sacc += wprod[e];
-                    if (k == 0) head_part[t] = sacc; else part[cur.vlo + k - 1] = sacc;
-                }
+            for (int j = 0; j < SPMV_ITEMS; ++j) {
+                double g = 0.0;
+                if (R.ri[j] >= 0) g = STAGE ? sv[R.ri[j] - (int)gbase] : __ldg(gvec + R.ri[j]);
+                wprod[j * 32 + lane] = BINARY ? g : R.rv[0 + (BINARY ? 0 : j)] * g;
             }
+            const int vlo = m_cur.x, nown = m_cur.y;
+            int c = min(cut, end) - start;                  // this lane's cut point (lane <= nown)
+            // prefetch: data and cut points of tile t+32, metadata of tile t+64
+            const int tn = t + SPMV_WARPS;
+            if (tn < sec_end) {
+                const int st1 = nnz0 + (tn - s_t0) * SPMV_TILE;
+                tile_fetch<BINARY>(R, st1, min(st1 + SPMV_TILE, nnz1), idx, val, lane);
+                m_cur = m_next;
+                cut = (lane <= m_cur.y) ? ptr[m_cur.x + lane] : 0x7fffffff;
+                if (tn + SPMV_WARPS < sec_end) m_next = tmeta[tn + SPMV_WARPS];
+            }
+            __syncwarp();
+            // segmented reduction, 32 pieces per pass
+            const int npieces = nown + 1;
+            int G = 32;
+            if (npieces > 1) { int lg = 32 - __clz(min(npieces, 32) - 1); G = 32 >> lg; }
+            const int gl = lane & (G - 1), grp = lane / G, ngrp = 32 / G;
+            int prev_last = 0;                              // c_{base-1}
+            for (int base = 0; base < npieces; base += 32) {
+                if (base > 0) {                             // rare: more than 32 pieces in a tile
+                    int k = base + lane;
+                    c = (k <= nown) ? min(ptr[vlo + k], end) - start : end - start;
+                }
+                for (int sub = 0; sub < 32; sub += ngrp) {
+                    const int pl = sub + grp;               // piece index within this pass
+                    if (base + sub >= npieces) break;       // warp-uniform
+                    int b = __shfl_sync(0xffffffffu, c, pl);
+                    int a = __shfl_sync(0xffffffffu, c, (pl > 0) ? pl - 1 : 0);
+                    if (pl == 0) a = prev_last;
+                    const bool valid = (base + pl) <= nown;
+                    double sacc = 0.0;
+                    if (valid) for (int e = a + gl; e < b; e += G) sacc += wprod[e];
+                    for (int o = G >> 1; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+                    if (valid && gl == 0) {
+                        const int k = base + pl;
+                        if (k == 0) head_part[t] = sacc; else part[vlo + k - 1] = sacc;
+                    }
+                }
+                prev_last = __shfl_sync(0xffffffffu, c, 31);
+            }
+            t = tn;
         }
-        t = tnext;
+        cur = sec_end;
+        slab += 1;
     }
 }
 
@@ -374,7 +400,9 @@ int bb_slab_free(SlabFmt* f) {
     }
     if (f->tiles) cudaFree(f->tiles);
     if (f->head_seg) cudaFree(f->head_seg);
-    if (f->units) cudaFree(f->units);
+    if (f->tmeta) cudaFree(f->tmeta);
+    if (f->slab_tile0) cudaFree(f->slab_tile0);
+    if (f->slab_nnz0) cudaFree(f->slab_nnz0);
     if (f->part) cudaFree(f->part);
     if (f->head_part) cudaFree(f->head_part);
     memset(f, 0, sizeof(*f));
@@ -483,26 +511,14 @@ static int build_slab_format(bb_ctx* ctx, const int* cptr, const int* cidx, cons
     BB_CUDA(cudaMemcpyAsync(f->tiles, tiles.data(), tiles.size() * sizeof(TileMeta), cudaMemcpyHostToDevice, st));
     k_tile_meta<<<(f->ntiles + TB - 1) / TB, TB, 0, st>>>(f->ptr, V, n_seg, f->ntiles, f->tiles, f->head_seg);
     ctx->launches += 1;
-    // work units: ~one per SM, never crossing a slab
-    int target = (f->ntiles + ctx->sm_count - 1) / ctx->sm_count;
-    if (target < 1) target = 1;
-    std::vector<WorkUnit> units;
-    for (i64 s = 0; s < nslab; ++s) {
-        int t0 = slab_tile0[(size_t)s], t1 = slab_tile0[(size_t)s + 1];
-        int nt = t1 - t0;
-        int nu = (nt + target - 1) / target;
-        for (int k = 0; k < nu; ++k) {
-            WorkUnit u;
-            u.slab = (int)s;
-            u.tile_lo = t0 + (int)((i64)nt * k / nu);
-            u.tile_hi = t0 + (int)((i64)nt * (k + 1) / nu);
-            u.pad = 0;
-            if (u.tile_hi > u.tile_lo) units.push_back(u);
-        }
-    }
-    f->nunits = (int)units.size();
-    BB_CUDA(cudaMalloc((void**)&f->units, units.size() * sizeof(WorkUnit)));
-    BB_CUDA(cudaMemcpyAsync(f->units, units.data(), units.size() * sizeof(WorkUnit), cudaMemcpyHostToDevice, st));
+    // compact per-tile metadata {vlo, nown} and the per-slab tile / nnz offsets read by the kernel
+    BB_CUDA(cudaMalloc((void**)&f->tmeta, tiles.size() * sizeof(int2)));
+    k_compact_meta<<<(f->ntiles + TB - 1) / TB, TB, 0, st>>>(f->tiles, f->ntiles, f->tmeta);
+    ctx->launches += 1;
+    BB_CUDA(cudaMalloc((void**)&f->slab_tile0, ((size_t)nslab + 1) * sizeof(int)));
+    BB_CUDA(cudaMalloc((void**)&f->slab_nnz0, ((size_t)nslab + 1) * sizeof(int)));
+    BB_CUDA(cudaMemcpyAsync(f->slab_tile0, slab_tile0.data(), ((size_t)nslab + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+    BB_CUDA(cudaMemcpyAsync(f->slab_nnz0, slab_off.data(), ((size_t)nslab + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
     BB_CUDA(cudaMalloc((void**)&f->part, (size_t)(V > 0 ? V : 1) * sizeof(double)));
     BB_CUDA(cudaMalloc((void**)&f->head_part, (size_t)f->ntiles * sizeof(double)));
     BB_CUDA(cudaMemsetAsync(f->part, 0, (size_t)(V > 0 ? V : 1) * sizeof(double), st));
@@ -528,8 +544,9 @@ int bb_launch_spmv(bb_mat* m, SlabFmt* f, const double* gvec, const int* done_fl
     }
     if (smem > ctx->smem_optin) { bb_set_error("spmv shared memory %zu exceeds %zu", smem, ctx->smem_optin); return BB_ERR_ARG; }
     const bool binary = (f->val == nullptr);
-    dim3 grid(f->nunits), block(SPMV_THREADS);
-#define SPMV_ARGS f->ptr, f->idx, f->val, f->tiles, f->units, gvec, f->W, f->n_gather, wstage, f->part, f->head_part, done_flag
+    int ncta = ctx->sm_count < f->ntiles ? ctx->sm_count : f->ntiles;
+    dim3 grid(ncta), block(SPMV_THREADS);
+#define SPMV_ARGS f->ptr, f->idx, f->val, f->tmeta, f->slab_tile0, f->slab_nnz0, f->nslab, f->ntiles, gvec, f->W, f->n_gather, wstage, f->part, f->head_part, done_flag
     if (binary && stage) k_seg_spmv<true, true><<<grid, block, smem, ctx->stream>>>(SPMV_ARGS);
     else if (binary && !stage) k_seg_spmv<true, false><<<grid, block, smem, ctx->stream>>>(SPMV_ARGS);
     else if (!binary && stage) k_seg_spmv<false, true><<<grid, block, smem, ctx->stream>>>(SPMV_ARGS);
@@ -769,11 +786,14 @@ extern "C" int bb_dot(bb_mat* m, const double* v, double* out) {
     BB_ARG(m && v && out, "mat/v/out");
     bb_ctx* ctx = m->ctx;
     BB_CUDA(cudaSetDevice(ctx->device));
+    BBTimer timer_(ctx);
     BB_CUDA(cudaMemcpyAsync(m->v_P, v, (size_t)m->P * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     BB_TRY(bb_op_prepare(m, m->v_P, nullptr));
     BB_TRY(bb_op_dot(m, 0));
     BB_CUDA(cudaMemcpyAsync(out, m->u_n, (size_t)m->n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    timer_.end();
     BB_CUDA(cudaStreamSynchronize(ctx->stream));
+    timer_.commit();
     return BB_OK;
 }
 
@@ -781,11 +801,14 @@ extern "C" int bb_tdot(bb_mat* m, const double* w, double* out) {
     BB_ARG(m && w && out, "mat/w/out");
     bb_ctx* ctx = m->ctx;
     BB_CUDA(cudaSetDevice(ctx->device));
+    BBTimer timer_(ctx);
     BB_CUDA(cudaMemcpyAsync(m->eps_n, w, (size_t)m->n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     BB_TRY(bb_op_tdot(m, m->eps_n));
     BB_TRY(bb_op_tdot_finish(m, m->t_P));
     BB_CUDA(cudaMemcpyAsync(out, m->t_P, (size_t)m->P * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    timer_.end();
     BB_CUDA(cudaStreamSynchronize(ctx->stream));
+    timer_.commit();
     return BB_OK;
 }
 
@@ -810,6 +833,7 @@ extern "C" int bb_fisher_diag(bb_mat* m, const double* weight, double* out) {
     bb_ctx* ctx = m->ctx;
     cudaStream_t st = ctx->stream;
     BB_CUDA(cudaSetDevice(ctx->device));
+    BBTimer timer_(ctx);
     BB_CUDA(cudaMemcpyAsync(m->eps_n, weight, (size_t)m->n * sizeof(double), cudaMemcpyHostToDevice, st));
     // d2 -> q[1..p], d1 -> b[1..p], sum w -> traw[0]; all three allreduced
     double *d2 = m->q, *d1 = m->b;
@@ -833,6 +857,8 @@ extern "C" int bb_fisher_diag(bb_mat* m, const double* weight, double* out) {
     k_fisher_finish<<<P_grid(m->P), 256, 0, st>>>(d2, d1, d2, m->col_offset, m->p, m->add_intercept, m->centered, m->out_P);
     BB_LAUNCHED(ctx);
     BB_CUDA(cudaMemcpyAsync(out, m->out_P, (size_t)m->P * sizeof(double), cudaMemcpyDeviceToHost, st));
+    timer_.end();
     BB_CUDA(cudaStreamSynchronize(st));
+    timer_.commit();
     return BB_OK;
 }

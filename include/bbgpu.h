@@ -55,6 +55,9 @@ int  bb_get_option(bb_ctx* ctx, const char* name, int64_t* value);
 /* kernel launches issued by this library since bb_init / the last reset */
 int  bb_get_launch_count(bb_ctx* ctx, int64_t* launches);
 int  bb_reset_launch_count(bb_ctx* ctx);
+/* device milliseconds (CUDA events on the library stream) spent inside the entry points below */
+int  bb_get_device_ms(bb_ctx* ctx, double* ms);
+int  bb_reset_device_ms(bb_ctx* ctx);
 int  bb_sync(bb_ctx* ctx);
 
 /* ---- communicator: row-sharding, one process per GPU (new) ----------- */

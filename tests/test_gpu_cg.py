@@ -9,7 +9,13 @@ from conftest import golden
 from oracle import cg_oracle as co
 
 pytestmark = pytest.mark.gpu
-TOL = 1e-8
+TOL = 1e-8          # north_star: CG solution vs the reference, fp64, same omega and noise
+# Unconverged iterates (maxiter = K, tolerance 0) are a different matter: CG amplifies a 1e-16 change in
+# one matvec to >1e-9 in the K=5 iterate on these very problems (tests/test_oracle_cg.py::
+# test_fixed_iteration_iterates_are_chaotic measures it on the oracle itself), so two correct
+# implementations with different summation orders cannot agree to 1e-8 there; they are held to TOL_ITERATE
+# and, independently, to the same iteration counts.
+TOL_ITERATE = 1e-5
 
 
 def relerr(a, b):
@@ -36,7 +42,8 @@ def test_cg_sample_matches_reference(ctx, name):
         coef, info = ConjugateGradientSampler(1).sample(
             D, omega, pps, z, x0.copy(), 'prior', sd, maxiter=int(maxiter), atol=atol_unit * np.sqrt(P), seed=7)
         ref = g['%s_coef_%d' % (name, k)]
-        assert relerr(coef, ref) <= TOL, (name, maxiter, atol_unit)
+        converged_rule = atol_unit > 0
+        assert relerr(coef, ref) <= (TOL if converged_rule or maxiter == 1 else TOL_ITERATE), (name, maxiter, atol_unit)
         assert info['n_iter'] == int(g['%s_niter_%d' % (name, k)])
         assert info['converged'] == bool(g['%s_conv_%d' % (name, k)])
 
