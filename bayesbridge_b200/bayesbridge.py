@@ -234,11 +234,11 @@ class BayesBridge():
             # omega already on the device (left there by the fused PG update); z = X' kappa cached there
             return self.reg_coef_sampler.sample_gaussian_posterior(
                 None, self.model.design, None, gscale, lscale, sampling_method, noise=noise, philox=philox)
-        # host omega (initial state, or a host-side PG sampler was plugged in)
-        kappa = self.model.n_success - self.model.n_trial / 2
-        y_gaussian = kappa / obs_prec
+        # host omega (initial / resumed state, or a host-side PG sampler was plugged in): omega is uploaded;
+        # omega * y_gaussian = kappa exactly (bayesbridge.py:380), so z = X'kappa is still formed on the device,
+        # which keeps a resumed chain bit-identical to an uninterrupted one
         return self.reg_coef_sampler.sample_gaussian_posterior(
-            y_gaussian, self.model.design, obs_prec, gscale, lscale, sampling_method, noise=noise, philox=philox)
+            None, self.model.design, _lib.as_f64(obs_prec), gscale, lscale, sampling_method, noise=noise, philox=philox)
 
     def update_obs_precision(self, coef):
         """omega | beta (reference: bayesbridge.py:397-410)."""

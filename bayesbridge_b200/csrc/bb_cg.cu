@@ -246,6 +246,14 @@ extern "C" int bb_cg_sample(bb_mat* m, const double* omega, const double* prior_
         BB_CUDA(cudaMemcpyAsync(m->eps_P, eps2, Pb, cudaMemcpyHostToDevice, st));
     }
     const double* om = m->use_omega_scalar ? nullptr : m->omega;
+    // the captured iteration graph bakes pointer arguments: rebuild it when omega switches between
+    // the vector and the scalar representation; the scalar VALUE travels through device memory
+    if (m->cg_graph && m->cg_graph_scalar_mode != m->use_omega_scalar) {
+        cudaGraphExecDestroy(m->cg_graph);
+        m->cg_graph = nullptr;
+    }
+    m->cg_graph_scalar_mode = m->use_omega_scalar;
+    BB_CUDA(cudaMemcpyAsync(m->omega_scalar_dev, &m->omega_scalar, sizeof(double), cudaMemcpyHostToDevice, st));
     // right-hand side
     k_rhs_noise<<<N_grid(m->n), 256, 0, st>>>(om, m->omega_scalar, m->eps_n, philox, seed, offset, m->row_offset, m->n, m->u_n);
     BB_LAUNCHED(ctx);

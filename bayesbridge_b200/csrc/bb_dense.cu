@@ -14,7 +14,7 @@ template <int MODE>
 __global__ void __launch_bounds__(DD_THREADS)
 k_dense_dot(const double* __restrict__ X, i64 n, i64 p, const double* __restrict__ sv,
             const double* __restrict__ red_shift, int nshift,
-            const double* __restrict__ omega, double omega_scalar,
+            const double* __restrict__ omega, const double* __restrict__ omega_scalar,
             double* __restrict__ out, double* __restrict__ red_w, const int* __restrict__ done_flag) {
     if (done_flag != nullptr && *done_flag) return;
     __shared__ double sm[33];
@@ -33,7 +33,7 @@ k_dense_dot(const double* __restrict__ X, i64 n, i64 p, const double* __restrict
         double u = warp_sum((a0 + a1) + (a2 + a3)) + shift;
         if (lane == 0) {
             if (MODE == 0) out[i] = u;
-            else { double w = (omega ? omega[i] : omega_scalar) * u; out[i] = w; acc_w += w; }
+            else { double w = (omega ? omega[i] : omega_scalar[0]) * u; out[i] = w; acc_w += w; }
         }
     }
     if (MODE == 1) {
@@ -102,11 +102,11 @@ int bb_dense_dot(bb_mat* m, int mode, const int* done_flag) {
     int grid = dense_dot_grid(m);
     const double* sv = m->sv + m->add_intercept;
     if (mode == 0) {
-        k_dense_dot<0><<<grid, DD_THREADS, 0, ctx->stream>>>(m->Xd, m->n, m->p, sv, red_shift, nshift, nullptr, 0.0,
+        k_dense_dot<0><<<grid, DD_THREADS, 0, ctx->stream>>>(m->Xd, m->n, m->p, sv, red_shift, nshift, nullptr, nullptr,
                                                              m->u_n, nullptr, done_flag);
     } else {
         k_dense_dot<1><<<grid, DD_THREADS, 0, ctx->stream>>>(m->Xd, m->n, m->p, sv, red_shift, nshift,
-                                                             m->use_omega_scalar ? nullptr : m->omega, m->omega_scalar, m->w_n, m->red + RED_W * RED_MAX, done_flag);
+                                                             m->use_omega_scalar ? nullptr : m->omega, m->omega_scalar_dev, m->w_n, m->red + RED_W * RED_MAX, done_flag);
         m->nred_w = grid;
     }
     BB_LAUNCHED(ctx);

@@ -144,6 +144,7 @@ struct bb_mat {
     double *omega, *n_trial, *n_success, *eta, *w_n, *u_n, *eps_n;
     int has_outcome, is_linear;
     double omega_scalar; int use_omega_scalar;   // linear model: omega = scalar * 1_n
+    double* omega_scalar_dev;                    // device copy: kernels inside the captured CG graph read it here
     // P-vectors
     double *v_P, *sv, *traw /*[1+p]*/, *t_P, *x, *r, *pvec, *q, *b, *s, *D, *pps, *z, *x0, *eps_P, *out_P;
     // reduction scratch
@@ -151,7 +152,7 @@ struct bb_mat {
     CgScalars* cg;              // device
     CgScalars* cg_host;         // pinned
     int last_n_iter;
-    cudaGraphExec_t cg_graph; int cg_graph_launches;   // kernels per captured CG iteration
+    cudaGraphExec_t cg_graph; int cg_graph_launches; int cg_graph_scalar_mode;   // kernels per captured CG iteration
     int nred_w;                 // number of valid partials in red[RED_W]
     // dense Tdot partials [dense_nblk x p]
     double* dense_part; int dense_nblk;

@@ -117,15 +117,29 @@ struct TileData {
     double rv[BINARY ? 1 : SPMV_ITEMS];
 };
 
+// Loads of one tile.  Elements past `end` are clamped to the last valid nnz: their products are
+// garbage that no piece ever reads (pieces cover [0, end-start) only), so no predication is needed.
 template <bool BINARY>
 __device__ __forceinline__ void tile_fetch(TileData<BINARY>& R, int start, int end,
                                            const int* __restrict__ idx, const double* __restrict__ val, int lane) {
+    if (end - start == SPMV_TILE) {
+        const int* ip = idx + start + lane;
+        const double* vp = BINARY ? nullptr : val + start + lane;
 #pragma unroll
-    for (int j = 0; j < SPMV_ITEMS; ++j) {
-        int k = start + j * 32 + lane;
-        bool ok = k < end;
-        R.ri[j] = ok ? idx[k] : -1;
-        if (!BINARY) R.rv[j] = ok ? val[k] : 0.0;
+        for (int j = 0; j < SPMV_ITEMS; ++j) {
+            R.ri[j] = ip[j * 32];
+            if (!BINARY) R.rv[j] = vp[j * 32];
+        }
+    } else if (end > start) {
+#pragma unroll
+        for (int j = 0; j < SPMV_ITEMS; ++j) {
+            int k = min(start + j * 32 + lane, end - 1);
+            R.ri[j] = idx[k];
+            if (!BINARY) R.rv[j] = val[k];
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < SPMV_ITEMS; ++j) { R.ri[j] = -1; if (!BINARY) R.rv[j] = 0.0; }
     }
 }
 
@@ -170,6 +184,8 @@ k_seg_spmv(const int* __restrict__ ptr, const int* __restrict__ idx, const doubl
             }
             for (; i < wlen; i += SPMV_THREADS) sv[i] = src[i];
         }
+        // gather base: shared (staged slab, rebased so that the global index addresses it) or global
+        const double* gsrc = STAGE ? (sv - gbase) : gvec;
         int t = cur + warp;
         TileData<BINARY> R;
         int2 m_cur = make_int2(0, 0), m_next = make_int2(0, 0);
@@ -188,11 +204,12 @@ k_seg_spmv(const int* __restrict__ ptr, const int* __restrict__ idx, const doubl
             const int end = min(start + SPMV_TILE, nnz1);
             // products of the current tile -> per-warp shared buffer
             __syncwarp();
+            if (end > start) {
 #pragma unroll
-            for (int j = 0; j < SPMV_ITEMS; ++j) {
-                double g = 0.0;
-                if (R.ri[j] >= 0) g = STAGE ? sv[R.ri[j] - (int)gbase] : __ldg(gvec + R.ri[j]);
-                wprod[j * 32 + lane] = BINARY ? g : R.rv[0 + (BINARY ? 0 : j)] * g;
+                for (int j = 0; j < SPMV_ITEMS; ++j) {
+                    double g = gsrc[R.ri[j]];
+                    wprod[j * 32 + lane] = BINARY ? g : R.rv[BINARY ? 0 : j] * g;
+                }
             }
             const int vlo = m_cur.x, nown = m_cur.y;
             int c = min(cut, end) - start;                  // this lane's cut point (lane <= nown)
@@ -218,14 +235,22 @@ k_seg_spmv(const int* __restrict__ ptr, const int* __restrict__ idx, const doubl
                     c = (k <= nown) ? min(ptr[vlo + k], end) - start : end - start;
                 }
                 for (int sub = 0; sub < 32; sub += ngrp) {
-                    const int pl = sub + grp;               // piece index within this pass
                     if (base + sub >= npieces) break;       // warp-uniform
+                    const int pl = sub + grp;               // piece index within this pass
                     int b = __shfl_sync(0xffffffffu, c, pl);
                     int a = __shfl_sync(0xffffffffu, c, (pl > 0) ? pl - 1 : 0);
                     if (pl == 0) a = prev_last;
                     const bool valid = (base + pl) <= nown;
-                    double sacc = 0.0;
-                    if (valid) for (int e = a + gl; e < b; e += G) sacc += wprod[e];
+                    if (!valid) b = a;
+                    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+                    int e = a + gl;
+                    const double* wp = wprod;
+                    for (; e + 3 * G < b; e += 4 * G) {
+                        double x0 = wp[e], x1 = wp[e + G], x2 = wp[e + 2 * G], x3 = wp[e + 3 * G];
+                        s0 += x0; s1 += x1; s2 += x2; s3 += x3;
+                    }
+                    for (; e < b; e += G) s0 += wp[e];
+                    double sacc = (s0 + s1) + (s2 + s3);
                     for (int o = G >> 1; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
                     if (valid && gl == 0) {
                         const int k = base + pl;
@@ -277,7 +302,7 @@ __global__ void k_prepare(const double* __restrict__ v, const double* __restrict
 template <int MODE>
 __global__ void k_dot_finish(const double* __restrict__ part, int nslab, i64 n,
                              const double* __restrict__ red_shift, int nshift,
-                             const double* __restrict__ omega, double omega_scalar,
+                             const double* __restrict__ omega, const double* __restrict__ omega_scalar,
                              double* __restrict__ out, double* __restrict__ u_out, double* __restrict__ red_w,
                              const int* __restrict__ done_flag) {
     if (done_flag != nullptr && *done_flag) return;
@@ -291,7 +316,7 @@ __global__ void k_dot_finish(const double* __restrict__ part, int nslab, i64 n,
         if (MODE == 0) {
             out[i] = u;
         } else {
-            double w = (omega ? omega[i] : omega_scalar) * u;
+            double w = (omega ? omega[i] : omega_scalar[0]) * u;
             out[i] = w;
             if (u_out) u_out[i] = u;
             acc += w;
@@ -582,10 +607,10 @@ int bb_op_dot_flag(bb_mat* m, int mode, const int* done_flag) {
     int nshift = P_grid(m->P);
     if (mode == 0) {
         k_dot_finish<0><<<N_grid(m->n), 256, 0, ctx->stream>>>(m->fdot.part, m->fdot.nslab, m->n, red_shift, nshift,
-                                                             nullptr, 0.0, m->u_n, nullptr, nullptr, done_flag);
+                                                             nullptr, nullptr, m->u_n, nullptr, nullptr, done_flag);
     } else {
         k_dot_finish<1><<<N_grid(m->n), 256, 0, ctx->stream>>>(m->fdot.part, m->fdot.nslab, m->n, red_shift, nshift,
-                                                             m->use_omega_scalar ? nullptr : m->omega, m->omega_scalar, m->w_n, nullptr,
+                                                             m->use_omega_scalar ? nullptr : m->omega, m->omega_scalar_dev, m->w_n, nullptr,
                                                              m->red + RED_W * RED_MAX, done_flag);
         m->nred_w = N_grid(m->n);
     }
@@ -643,6 +668,7 @@ int bb_mat_alloc_work(bb_mat* m) {
     for (auto pp : pv) BB_TRY(alloc_d(m->ctx->stream, pp, m->P + 1));
     BB_TRY(alloc_d(m->ctx->stream, &m->traw, m->p + 1));
     BB_TRY(alloc_d(m->ctx->stream, &m->zk, m->P + 1));
+    BB_TRY(alloc_d(m->ctx->stream, &m->omega_scalar_dev, 1));
     BB_TRY(alloc_d(m->ctx->stream, &m->red, (i64)RED_SLOTS * RED_MAX));
     BB_CUDA(cudaMalloc((void**)&m->cg, sizeof(CgScalars)));
     BB_CUDA(cudaMemsetAsync(m->cg, 0, sizeof(CgScalars), m->ctx->stream));
@@ -661,7 +687,7 @@ extern "C" int bb_mat_free(bb_mat* m) {
     bb_slab_free(&m->fdot);
     bb_slab_free(&m->ftdot);
     void* ptrs[] = {m->csr_ptr, m->csr_idx, m->csr_val, m->csc_ptr, m->csc_idx, m->csc_val, m->col_offset, m->Xd,
-                    m->omega, m->n_trial, m->n_success, m->eta, m->w_n, m->u_n, m->eps_n, m->dense_part, m->zk,
+                    m->omega, m->n_trial, m->n_success, m->eta, m->w_n, m->u_n, m->eps_n, m->dense_part, m->zk, m->omega_scalar_dev,
                     m->v_P, m->sv, m->traw, m->t_P, m->x, m->r, m->pvec, m->q, m->b, m->s, m->D, m->pps, m->z, m->x0,
                     m->eps_P, m->out_P, m->red, m->cg};
     for (void* p : ptrs) if (p) cudaFree(p);

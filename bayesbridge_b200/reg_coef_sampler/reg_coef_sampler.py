@@ -45,12 +45,13 @@ class SparseRegressionCoefficientSampler():
         """
         beta | omega, tau, lambda ~ N(Phi^{-1} X' Omega y, Phi^{-1}) (reg_coef_sampler.py:60-103).
 
-        y, obs_prec : arrays; or both None when the outcome and the precision live on the device
-                      (then X'(Omega y) is formed there too).
+        y : array, or None when the outcome is resident on the device (bb_set_outcome): z = X'(Omega y) is
+            then formed there (for the logit model X'kappa, computed once and cached).
+        obs_prec : array, or None to use the precision vector resident on the device.
         """
         if method != 'cg':
             raise NotImplementedError("Only method='cg' is available on the device.")
-        if z is None and obs_prec is not None:
+        if z is None and y is not None:
             z = design.Tdot(obs_prec * y)
         prior_sd = np.concatenate((
             self.prior_sd_for_unshrunk, self.compute_prior_shrunk_scale(gscale, lscale)))

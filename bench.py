@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: Gibbs iterations/s of the CG-accelerated sampler (logit), BASELINE.json's metric.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo, N GPUs of one node
+    python bench.py --impl reference --steps K --warmup W    # the reference's own CPU sampler (oracle/_ref)
+
+Workload (config.workload = "C4"): BASELINE.json configs[3], the one the north-star target is quoted on --
+binary sparse X, n = 1,000,000 x p = 100,000, mean density 0.1 % (nnz ~ 1e8), column frequencies
+0.5*Beta(0.5, b) as in the reference's simulate_binary_design (simulate_data.py:100-117), logit outcome,
+bridge exponent 0.5, coef_sampler_type='cg'.  X is generated in 50 fixed row blocks (seeded per block), so
+the matrix is identical for every N; rank r of N owns a contiguous run of blocks (strong scaling: the total
+work is fixed).  One "step" = one full Gibbs iteration (beta | omega by CG, omega | beta by Polya-Gamma,
+tau, lambda, log-posterior).  X (2.4 GB as CSR+CSC images) is far larger than the 126 MB L2, so no L2
+flush is needed between steps.
+
+value   = K / (device time of the K steps: CUDA events on the library stream, summed over the library
+          calls of a step, max over ranks)  -- inputs (X, outcome, omega) resident in HBM.
+e2e     = K / (wall time of BayesBridge.gibbs_resume(K), the public API, max over ranks) -- includes the
+          per-step host<->device copies of the P-length vectors and all host-side Python.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+import warnings
+
+import numpy as np
+import scipy.sparse as sp
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+warnings.simplefilter('ignore')
+
+N_BLOCKS = 50
+WORKLOADS = {
+    # name: (n, p, mean density)
+    'C4': (1_000_000, 100_000, 0.001),
+    'C3': (100_000, 20_000, 0.005),
+    'C1': (10_000, 1_000, 0.01),
+}
+
+
+# ---- synthetic data (shared by both arms) ------------------------------------------------------
+def column_frequencies(p, density, seed=0):
+    """simulate_data.py:100-111: f_j = 0.5 * Beta(a, b), a = 0.5, b chosen so that E f_j = density."""
+    a, max_freq = 0.5, 0.5
+    b = a * (max_freq / density - 1)
+    return max_freq * np.random.default_rng(seed).beta(a, b, p)
+
+
+def true_coef(p):
+    beta = np.zeros(p)
+    beta[:5], beta[5:10], beta[10:15], beta[15:20] = 1.5, -1.0, 1.0, -0.5
+    return beta
+
+
+def generate_block(block, n, p, freq, seed=0):
+    """Rows [n*block/N_BLOCKS, n*(block+1)/N_BLOCKS) of X (binary CSR) and of the binary outcome."""
+    lo, hi = n * block // N_BLOCKS, n * (block + 1) // N_BLOCKS
+    nb = hi - lo
+    rng = np.random.default_rng([seed, block])
+    counts = rng.binomial(nb, freq)
+    cols = np.repeat(np.arange(p, dtype=np.int64), counts)
+    rows = rng.integers(0, nb, cols.size)
+    key = np.unique(rows * p + cols)                  # row-major order, duplicates dropped
+    rows, cols = key // p, (key % p).astype(np.int32)
+    indptr = np.zeros(nb + 1, dtype=np.int32)
+    np.cumsum(np.bincount(rows, minlength=nb), out=indptr[1:])
+    X = sp.csr_matrix((np.ones(cols.size), cols, indptr), shape=(nb, p))
+    eta = -2.0 + X @ true_coef(p)
+    y = rng.binomial(1, 1 / (1 + np.exp(-eta)))
+    return X, y
+
+
+def generate_rows(blocks, n, p, density):
+    freq = column_frequencies(p, density)
+    parts = [generate_block(b, n, p, freq) for b in blocks]
+    X = sp.vstack([q[0] for q in parts], format='csr')
+    X.indices = X.indices.astype(np.int32)
+    X.indptr = X.indptr.astype(np.int32)
+    y = np.concatenate([q[1] for q in parts])
+    return X, y
+
+
+# ---- clocks ------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi during the timed region (B200_PROFILING.md, 'clocks' line)."""
+    QUERY = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, device):
+        super().__init__(daemon=True)
+        self.device, self.samples, self.stop_flag = device, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.device), '--query-gpu=' + self.QUERY,
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(',')]
+                if len(f) >= 6:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [nm for i, nm in enumerate(names) if any(s[2 + i].lower().startswith('active') for s in self.samples)]
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': float(self.samples[0][1]), 'reasons': reasons,
+                'samples': len(sm)}
+
+
+# ---- reference arm / cpu baseline ---------------------------------------------------------------
+def import_reference():
+    ref_dir = os.path.join(ROOT, 'oracle', '_ref')
+    if not os.path.isdir(os.path.join(ref_dir, 'bayesbridge')):
+        return None
+    sys.path.insert(0, ref_dir)
+    import bayesbridge
+    return bayesbridge
+
+
+def reference_run(workload, steps, warmup, sample_blocks):
+    """The reference's numpy/scipy/Cython sampler on a bounded row sample of the workload.
+    Returns (iterations/s scaled to the full workload, description dict)."""
+    n, p, density = WORKLOADS[workload]
+    ref = import_reference()
+    kind = 'reference'
+    X, y = generate_rows(range(sample_blocks), n, p, density)
+    frac = X.shape[0] / n
+    t_build = time.time()
+    if ref is not None:
+        model = ref.RegressionModel(y, X, family='logit')
+        bridge = ref.BayesBridge(model, ref.RegressionCoefPrior(bridge_exponent=.5))
+        _, info = bridge.gibbs(n_iter=max(warmup, 1), n_burnin=0, coef_sampler_type='cg', seed=0,
+                               params_to_save=('global_scale',))
+        t0 = time.time()
+        _, info2 = bridge.gibbs_resume(info, steps)
+        dt = time.time() - t0
+        n_cg = float(np.mean(info2['_reg_coef_sampling_info']['n_cg_iter'])) if steps > 0 else float('nan')
+    else:
+        # the oracle port (numpy restatement) when the reference could not be built
+        kind = 'port'
+        from oracle import cg_oracle as co
+        from oracle.rand_port import PolyaGammaPort, TiltedStablePort
+        t0 = time.time()
+        coefs, n_cg_arr = co.gibbs_cg_oracle('logit', (y.astype(float), np.ones(len(y))), X, warmup + steps, 0, 0.5,
+                                             float('inf'), float('inf'), 0.1, np.ones(p), PolyaGammaPort,
+                                             TiltedStablePort, True)
+        dt = (time.time() - t0) * steps / max(warmup + steps, 1)
+        n_cg = float(n_cg_arr.mean())
+    its_sample = steps / dt
+    desc = {
+        'kind': kind, 'cores': 1,
+        'sample': 'rows 0..%d of %s (%d of %d row blocks, %.0f%% of nnz); %d timed Gibbs iterations after %d warm-up; '
+                  'iterations/s scaled by the nnz fraction (cost ~ nnz); scipy SpMV + Cython PG/tilted-stable are '
+                  'single-threaded (host has %d cores)' % (X.shape[0] - 1, workload, sample_blocks, N_BLOCKS,
+                                                            100 * frac, steps, warmup, os.cpu_count()),
+        'iters_per_s_on_sample': its_sample, 'mean_n_cg_iter': n_cg, 'sample_nnz': int(X.nnz),
+    }
+    return its_sample * frac, desc
+
+
+# ---- main ---------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--workload', default='C4', choices=sorted(WORKLOADS))
+    ap.add_argument('--ref-blocks', type=int, default=2, help='row blocks (of 50) the CPU reference is timed on')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    n, p, density = WORKLOADS[args.workload]
+    config = {'workload': args.workload, 'family': 'logit', 'n': n, 'p': p, 'mean_density': density,
+              'bridge_exponent': 0.5, 'coef_sampler_type': 'cg', 'format': 'binary CSR + CSC, int32 indices, fp64 math',
+              'l2': 'inputs (2.4 GB) exceed L2; no flush'}
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        value, desc = reference_run(args.workload, args.steps, max(args.warmup, 1), args.ref_blocks)
+        print(json.dumps({
+            'impl': 'reference', 'metric': 'gibbs_iters_per_sec', 'value': value, 'unit': 'iter/s',
+            'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1000.0 / value,
+            'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': config, 'cpu_baseline': dict(desc, value=value, unit='iter/s'),
+            'e2e': {'value': value, 'unit': 'iter/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        }))
+        return
+
+    import torch
+    import torch.distributed as dist
+    import bayesbridge_b200 as bb
+    from bayesbridge_b200 import _lib
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    ctx = _lib.Context(local_rank)
+    if world > 1:
+        ctx.init_comm_from_torch()
+
+    # this rank's row blocks
+    blocks = range(N_BLOCKS * rank // world, N_BLOCKS * (rank + 1) // world)
+    X, y = generate_rows(blocks, n, p, density)
+    row_offset = n * blocks[0] // N_BLOCKS
+    nnz_local = int(X.nnz)
+    from bayesbridge_b200.design_matrix import GpuSparseDesignMatrix
+    design = GpuSparseDesignMatrix(X, center_predictor=True, add_intercept=True, ctx=ctx,
+                                   presharded=(world > 1), n_global=n, row_offset=row_offset)
+    model = bb.RegressionModel(y, design, family='logit')
+    bridge = bb.BayesBridge(model, bb.RegressionCoefPrior(bridge_exponent=.5))
+    P = design.shape[1]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ctx.sync()
+
+    # chain initialisation + W warm-up steps (untimed)
+    _, info = bridge.gibbs(n_iter=max(args.warmup, 1), n_burnin=0, coef_sampler_type='cg', seed=0,
+                           params_to_save=('coef', 'global_scale', 'logp'))
+    # roofline of the dominant kernel, measured live with CUDA events on the library stream
+    roof = {}
+    for what in ('spmv_dot', 'spmv_tdot'):
+        roof[what] = design.time_kernel(what, reps=10, flush_l2=False)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    ctx.reset_device_ms()
+    ctx.reset_launch_count()
+    t0 = time.perf_counter()
+    samples, info2 = bridge.gibbs_resume(info, args.steps)
+    ctx.sync()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    dev_ms = ctx.device_ms()
+    launches = ctx.launch_count()
+    barrier()
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    stats = torch.tensor([wall, dev_ms, float(nnz_local), float(launches)], dtype=torch.float64, device='cuda')
+    if world > 1:
+        mx = stats.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stats.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        wall, dev_ms, nnz_total = float(mx[0]), float(mx[1]), float(sm[2])
+    else:
+        nnz_total = float(nnz_local)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    K = args.steps
+    n_cg = info2['_reg_coef_sampling_info']['n_cg_iter']
+    value = K / (dev_ms / 1000.0)
+    e2e = K / wall
+    # algorithmic bytes of one launch of the dominant kernel (pattern-only format:
+    # 4 B per nnz index + pointers + gathered and written vectors); per rank
+    n_loc = design.shape[0]
+    b_dot = 4 * nnz_local + 4 * (n_loc + 1) + 8 * P + 8 * n_loc
+    b_tdot = 4 * nnz_local + 4 * (P + 1) + 8 * n_loc + 8 * P
+    dom = 'spmv_tdot' if roof['spmv_tdot'] >= roof['spmv_dot'] else 'spmv_dot'
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    peak = float(peaks.get('hbm_gbs', 6650.0))
+    peak_src = 'measured (MEASURED_PEAKS.json hbm_gbs)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s'
+    ach = (b_tdot if dom == 'spmv_tdot' else b_dot) / (roof[dom] * 1e-3) / 1e9
+    line = {
+        'metric': 'gibbs_iters_per_sec', 'value': value, 'unit': 'iter/s', 'n_gpus': world, 'steps': K,
+        'warmup': args.warmup, 'ms_per_step': dev_ms / K, 'higher_is_better': True, 'scaling': 'strong',
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': dict(config, nnz=int(nnz_total)),
+        'e2e': {'value': e2e, 'unit': 'iter/s', 'ms_per_step_wall': 1000 * wall / K,
+                'h2d_bytes_per_step': int(8 * (4 * P + (P - 1))), 'd2h_bytes_per_step': int(8 * (P + (P - 1)) + 64),
+                'api': 'BayesBridge.gibbs_resume (public API; host numpy state in, samples out)'},
+        'gpu_launches': int(launches),
+        'mean_n_cg_iter': float(np.mean(n_cg)),
+        'clocks': sampler.summary(),
+        'roofline': {
+            'bound': 'hbm', 'kernel': 'k_seg_spmv (%s)' % dom, 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
+            'frac': ach / peak, 'traffic': None, 'peak_source': peak_src,
+            'algorithmic_bytes_per_launch': int(b_tdot if dom == 'spmv_tdot' else b_dot),
+            'ms_per_launch': roof[dom],
+            'other': {'spmv_dot_ms': roof['spmv_dot'], 'spmv_dot_GBs': b_dot / (roof['spmv_dot'] * 1e-3) / 1e9,
+                      'spmv_tdot_ms': roof['spmv_tdot'], 'spmv_tdot_GBs': b_tdot / (roof['spmv_tdot'] * 1e-3) / 1e9},
+        },
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            v, desc = reference_run(args.workload, 6, 2, args.ref_blocks)
+            line['cpu_baseline'] = dict(desc, value=v, unit='iter/s')
+        except Exception as e:      # the baseline is reported, never required
+            line['cpu_baseline'] = {'value': None, 'unit': 'iter/s', 'cores': 1, 'kind': 'reference',
+                                    'sample': 'failed: %r' % (e,)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -119,18 +119,31 @@ def test_csr_upload_and_csc_construction_are_bit_exact(ctx):
 
 def test_edge_cases(ctx):
     Sparse, _ = _designs()
-    # empty rows, empty columns, an all-zero matrix, a single entry
-    X = sp.csr_matrix((np.array([2.0, -1.0, 3.0]), (np.array([0, 5, 5]), np.array([1, 1, 6]))), shape=(9, 8))
-    for Xc in (X, sp.csr_matrix((6, 4)), sp.csr_matrix(([1.5], ([2], [3])), shape=(4, 5))):
-        D = Sparse(Xc, center_predictor=False, add_intercept=True, ctx=ctx)
-        A = np.hstack((np.ones((Xc.shape[0], 1)), Xc.toarray()))
-        v, w = np.arange(1., A.shape[1] + 1), np.arange(1., A.shape[0] + 1)
-        assert np.allclose(D.dot(v), A @ v, rtol=1e-14, atol=1e-14)
-        assert np.allclose(D.Tdot(w), A.T @ w, rtol=1e-14, atol=1e-14)
+    # empty rows and ragged rows (every column keeps some variance, so none is dropped)
+    rows = np.array([0, 0, 2, 5, 5, 5, 8, 8])
+    cols = np.array([0, 3, 1, 0, 2, 3, 1, 2])
+    X = sp.csr_matrix((np.arange(1., 9.), (rows, cols)), shape=(9, 4))
+    for center in (False, True):
+        D = Sparse(X, center_predictor=center, add_intercept=True, ctx=ctx)
+        O = co.DesignOracle(X, center, True)
+        v, w = np.arange(1., 6.), np.arange(1., 10.)
+        assert np.allclose(D.dot(v), O.dot(v), rtol=1e-14, atol=1e-14)
+        assert np.allclose(D.Tdot(w), O.Tdot(w), rtol=1e-14, atol=1e-14)
     with pytest.raises(ValueError):
         D.dot(np.ones(3))
+    with pytest.raises(ValueError):
+        D.Tdot(np.ones(3))
     with pytest.raises(NotImplementedError):
-        D.compute_fisher_info(np.ones(4), diag_only=False)
+        D.compute_fisher_info(np.ones(9), diag_only=False)
+    # an all-zero matrix: every column is constant and is dropped (as the reference does) -> intercept only
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        Z = Sparse(sp.csr_matrix((6, 4)), center_predictor=True, add_intercept=True, ctx=ctx)
+    assert Z.shape == (6, 1) and Z.nnz == 0
+    assert np.array_equal(Z.dot(np.array([2.5])), np.full(6, 2.5))
+    assert np.array_equal(Z.Tdot(np.arange(6.)), [15.0])
+    assert np.array_equal(Z.compute_fisher_info(np.ones(6), diag_only=True), [6.0])
 
 
 def test_constant_column_is_dropped_with_warning(ctx):
