@@ -67,8 +67,11 @@ class BayesBridge():
             self.n_pred, self.prior_sd_for_unshrunk, prev_mcmc_info['coef_sampler_type'],
             prev_mcmc_info['options']['hmc_curvature_est_stabilized'], self.prior.slab_size)
         self.reg_coef_sampler.set_internal_state(prev_mcmc_info['_reg_coef_sampler_state'])
+        init = dict(prev_mcmc_info['_markov_chain_state'])
+        if '_markov_chain_state_raw_scales' in prev_mcmc_info:
+            init['_raw_scales'] = prev_mcmc_info['_markov_chain_state_raw_scales']
         new_samples, new_mcmc_info = self.gibbs(
-            n_add_iter, 0, prev_mcmc_info['thin'], init=prev_mcmc_info['_markov_chain_state'],
+            n_add_iter, 0, prev_mcmc_info['thin'], init=init,
             params_to_save=prev_mcmc_info['saved_params'], n_status_update=n_status_update,
             options=prev_mcmc_info['options'], _add_iter_mode=True)
         if merge:
@@ -123,6 +126,7 @@ class BayesBridge():
             self.manager.print_status(n_status_update, mcmc_iter, n_iter)
 
         runtime = time.time() - start_time
+        raw_scales = {'global_scale': gscale, 'local_scale': np.array(lscale, copy=True)}
 
         if self.prior._gscale_paramet == 'coef_magnitude':
             gscale, lscale = self.prior.adjust_scale(gscale, lscale, to='coef_magnitude')
@@ -143,6 +147,9 @@ class BayesBridge():
             '_init_optim_info': initial_optim_info,
             '_reg_coef_sampling_info': sampling_info,
             '_markov_chain_state': self.manager.pack_parameters(coef, obs_prec_host, lscale, gscale),
+            # the sampler's own (raw) parametrisation: tau*u/u is not a floating-point identity, and a one-ulp
+            # change is enough to make a resumed chain differ from an uninterrupted one
+            '_markov_chain_state_raw_scales': raw_scales,
             '_random_gen_state': self.rg.get_state(),
             '_reg_coef_sampler_state': self.reg_coef_sampler.get_internal_state(),
         }
@@ -153,7 +160,7 @@ class BayesBridge():
         """User-specified state where given, heuristics / conditional optimisation elsewhere
         (reference: bayesbridge.py:279-353)."""
         for key in init:
-            if key not in ('coef', 'local_scale', 'global_scale', 'obs_prec', 'logp'):
+            if key not in ('coef', 'local_scale', 'global_scale', 'obs_prec', 'logp', '_raw_scales'):
                 warn("'{:s}' is not a valid parameter name and will be ignored.".format(key))
         n_shrunk = self.n_pred - self.n_unshrunk
         have_coef = 'coef' in init
@@ -185,7 +192,10 @@ class BayesBridge():
             else:
                 lscale = np.ones(n_shrunk)
 
-        if self.prior._gscale_paramet == 'coef_magnitude':
+        if '_raw_scales' in init:
+            gscale = init['_raw_scales']['global_scale']
+            lscale = np.array(init['_raw_scales']['local_scale'], dtype=np.float64)
+        elif self.prior._gscale_paramet == 'coef_magnitude':
             # the sampler itself works in the raw parametrisation
             gscale, lscale = self.prior.adjust_scale(gscale, lscale, to='raw')
 
@@ -234,11 +244,17 @@ class BayesBridge():
             # omega already on the device (left there by the fused PG update); z = X' kappa cached there
             return self.reg_coef_sampler.sample_gaussian_posterior(
                 None, self.model.design, None, gscale, lscale, sampling_method, noise=noise, philox=philox)
-        # host omega (initial / resumed state, or a host-side PG sampler was plugged in): omega is uploaded;
-        # omega * y_gaussian = kappa exactly (bayesbridge.py:380), so z = X'kappa is still formed on the device,
-        # which keeps a resumed chain bit-identical to an uninterrupted one
+        # host omega (initial / resumed state, or a host-side PG sampler was plugged in): omega is uploaded.
+        if noise == 'host':
+            # parity mode: the reference's arithmetic, z = X'(omega * (kappa / omega))  (bayesbridge.py:380-383)
+            y_gaussian = (self.model.n_success - self.model.n_trial / 2) / obs_prec
+        else:
+            # omega * y_gaussian == kappa, so z = X'kappa is formed (once) on the device; using the same z
+            # as the resident path keeps a resumed chain bit-identical to an uninterrupted one
+            y_gaussian = None
         return self.reg_coef_sampler.sample_gaussian_posterior(
-            None, self.model.design, _lib.as_f64(obs_prec), gscale, lscale, sampling_method, noise=noise, philox=philox)
+            y_gaussian, self.model.design, _lib.as_f64(obs_prec), gscale, lscale, sampling_method,
+            noise=noise, philox=philox)
 
     def update_obs_precision(self, coef):
         """omega | beta (reference: bayesbridge.py:397-410)."""

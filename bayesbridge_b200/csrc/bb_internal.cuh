@@ -107,6 +107,7 @@ struct SlabFmt {
     int*  idx;          // [nnz] gather index (global)
     double* val;        // [nnz] or NULL (pattern-only)
     bool  owns_arrays;  // false when aliasing the canonical CSR/CSC (nslab == 1)
+    bool  staged;       // the kernel stages the slab of the gather vector in shared memory
     int   ntiles;
     TileMeta* tiles;    // [ntiles]
     int*  head_seg;     // [ntiles] virtual segment continued from the previous tile, or -1

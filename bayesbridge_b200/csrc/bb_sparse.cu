@@ -444,10 +444,12 @@ static i64 max_stage_width(bb_ctx* ctx) {
 
 // Build a slab format from a canonical compressed matrix (ptr[n_seg+1], idx, val).
 static int build_slab_format(bb_ctx* ctx, const int* cptr, const int* cidx, const double* cval,
-                             i64 n_seg, i64 n_gather, i64 nnz, SlabFmt* f) {
+                             i64 n_seg, i64 n_gather, i64 nnz, bool staged, SlabFmt* f) {
     memset(f, 0, sizeof(*f));
+    f->staged = staged;
     cudaStream_t st = ctx->stream;
     i64 wmax = max_stage_width(ctx);
+    if (!staged) wmax = ((i64)1 << 40);     // gathers go through L2: no slab limit
     if (ctx->opt_slab_width > 0) {
         i64 w = (ctx->opt_slab_width + 31) & ~(i64)31;
         if (w < wmax) wmax = w;
@@ -555,7 +557,8 @@ static int build_slab_format(bb_ctx* ctx, const int* cptr, const int* cidx, cons
 // launch the SpMV + fix-up for one format; gvec has f->n_gather entries
 int bb_launch_spmv(bb_mat* m, SlabFmt* f, const double* gvec, const int* done_flag) {
     bb_ctx* ctx = m->ctx;
-    const bool stage = ctx->opt_spmv_stage != 0;
+    // a format built without staging in mind may have slabs wider than shared memory
+    const bool stage = f->staged && (i64)f->W <= max_stage_width(ctx);
     int wstage = stage ? f->W : 0;
     size_t smem = (size_t)(wstage + SPMV_WARPS * SPMV_TILE) * sizeof(double);
     static bool attr_set = false;
@@ -761,8 +764,11 @@ extern "C" int bb_csr_upload(bb_ctx* ctx, int64_t n, int64_t p, int64_t nnz,
         }
         cudaFree(row_of); cudaFree(iota); cudaFree(perm); cudaFree(col_sorted);
         if (rc != BB_OK) break;
-        CK(build_slab_format(ctx, m->csr_ptr, m->csr_idx, m->csr_val, n, p, nnz, &m->fdot));
-        CK(build_slab_format(ctx, m->csc_ptr, m->csc_idx, m->csc_val, p, n, nnz, &m->ftdot));
+        // spmv_stage: 0 = gather through L2 (one slab), 1 = stage both products' vectors in shared memory,
+        //             2 = stage only dot's (p-vector), 3 = stage only Tdot's (n-vector)
+        const i64 sopt = ctx->opt_spmv_stage;
+        CK(build_slab_format(ctx, m->csr_ptr, m->csr_idx, m->csr_val, n, p, nnz, sopt == 1 || sopt == 2, &m->fdot));
+        CK(build_slab_format(ctx, m->csc_ptr, m->csc_idx, m->csc_val, p, n, nnz, sopt == 1 || sopt == 3, &m->ftdot));
         CK(bb_mat_alloc_work(m));
         CKC(cudaStreamSynchronize(st));
 #undef CK

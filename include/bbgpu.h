@@ -39,8 +39,9 @@ enum { BB_OK = 0, BB_ERR_CUDA = 1, BB_ERR_ARG = 2, BB_ERR_NCCL = 3, BB_ERR_STATE
 enum { BB_NOISE_INJECT = 0,   /* eps1[n_local], eps2[P] supplied by the caller (parity mode)   */
        BB_NOISE_PHILOX = 1 }; /* generated on device, Philox4x32-10 keyed by (seed, offset, global row) */
 
-/* spmv kernel variants (bb_set_option "spmv_stage"): */
-enum { BB_SPMV_STAGE_SMEM = 1, BB_SPMV_STAGE_L2 = 0 };
+/* spmv kernel variants (bb_set_option "spmv_stage", read when a matrix is uploaded):
+ * gather vector staged in shared memory (slab formats) or read through L2 (single slab) */
+enum { BB_SPMV_STAGE_NONE = 0, BB_SPMV_STAGE_BOTH = 1, BB_SPMV_STAGE_DOT = 2, BB_SPMV_STAGE_TDOT = 3 };
 
 /* ---- library ---------------------------------------------------------------------------- */
 const char* bb_last_error(void);

@@ -18,7 +18,7 @@ for (n, p, dens) in sizes:
     X = sp.csr_matrix((np.ones(nnz), (rows, cols)), shape=(n, p)); X.sum_duplicates(); X.data[:] = 1.0
     print("matrix", n, p, X.nnz, flush=True)
     for binary in (True, False):
-        for stage in (1, 0):
+        for stage in (1, 0, 2, 3):
             ctx.set_option('spmv_stage', stage)
             t0 = time.time()
             D = GpuSparseDesignMatrix(X, center_predictor=True, add_intercept=True, ctx=ctx, pattern_only=binary)
