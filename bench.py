@@ -88,34 +88,53 @@ def generate_rows(blocks, n, p, density):
 
 # ---- clocks ------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi during the timed region (B200_PROFILING.md, 'clocks' line)."""
-    QUERY = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
-             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    """Samples SM clocks and throttle reasons during the timed region through NVML (in-process: spawning
+    nvidia-smi every 200 ms was measured to slow the timed Gibbs loop 3x on the shared driver lock)."""
 
-    def __init__(self, device):
+    def __init__(self, device, period=0.25):
         super().__init__(daemon=True)
-        self.device, self.samples, self.stop_flag = device, [], False
+        self.device, self.period, self.samples, self.stop_flag = device, period, [], False
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(device)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nvml = None
 
     def run(self):
+        if self.nvml is None:
+            return
+        nv = self.nvml
         while not self.stop_flag:
             try:
-                out = subprocess.run(['nvidia-smi', '-i', str(self.device), '--query-gpu=' + self.QUERY,
-                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(',')]
-                if len(f) >= 6:
-                    self.samples.append(f)
+                sm = nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.samples.append((sm, reasons))
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(self.period)
 
     def summary(self):
         if not self.samples:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
-        sm = sorted(float(s[0]) for s in self.samples)
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = [nm for i, nm in enumerate(names) if any(s[2 + i].lower().startswith('active') for s in self.samples)]
-        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': float(self.samples[0][1]), 'reasons': reasons,
-                'samples': len(sm)}
+        nv = self.nvml
+        sm = sorted(s[0] for s in self.samples)
+        bits = 0
+        for s_ in self.samples:
+            bits |= s_[1]
+        table = [('hw_slowdown', 'nvmlClocksThrottleReasonHwSlowdown'),
+                 ('hw_thermal_slowdown', 'nvmlClocksThrottleReasonHwThermalSlowdown'),
+                 ('sw_thermal_slowdown', 'nvmlClocksThrottleReasonSwThermalSlowdown'),
+                 ('sw_power_cap', 'nvmlClocksThrottleReasonSwPowerCap')]
+        reasons = [nm for nm, attr in table if bits & getattr(nv, attr, 0)]
+        return {'sm_mhz': float(sm[len(sm) // 2]), 'sm_max_mhz': float(self.max_sm), 'reasons': reasons,
+                'samples': len(sm), 'source': 'nvml'}
 
 
 # ---- reference arm / cpu baseline ---------------------------------------------------------------

@@ -1,0 +1,83 @@
+"""Row-sharded path check, run under torchrun (N >= 2 GPUs):
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 scripts/multi_gpu_check.py
+Every rank builds the same small problem; the sharded design (this rank's row block + NCCL allreduce inside
+libbbgpu) is compared on every rank against an unsharded design living on the same GPU."""
+import os, sys, warnings
+import numpy as np
+import scipy.sparse as sp
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+warnings.simplefilter('ignore')
+import torch, torch.distributed as dist
+import bayesbridge_b200 as bb
+from bayesbridge_b200 import _lib
+from bayesbridge_b200.design_matrix import GpuSparseDesignMatrix, GpuDenseDesignMatrix
+from bayesbridge_b200.reg_coef_sampler import ConjugateGradientSampler
+
+rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])
+torch.cuda.set_device(local)
+dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+ctx = _lib.Context(local); ctx.init_comm_from_torch()
+solo = _lib.Context(local)                      # same GPU, no communicator: the unsharded comparator
+ok = True
+
+def rel(a, b): return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+def check(name, err, tol):
+    global ok
+    good = err <= tol
+    ok &= good
+    print(f"[rank {rank}] {name}: {err:.2e} {'ok' if good else 'FAIL'}", flush=True)
+
+rs = np.random.RandomState(0)
+n, p = 30001, 1200
+X = sp.random(n, p, density=0.01, format='csr', random_state=rs, dtype=np.float64); X.data[:] = 1.0
+Xd = rs.randn(2003, 150)
+for name, Xm, Cls in (('sparse', X, GpuSparseDesignMatrix), ('dense', Xd, GpuDenseDesignMatrix)):
+    nn, pp = Xm.shape
+    Ds = Cls(Xm.copy(), center_predictor=True, add_intercept=True, ctx=ctx)       # sharded
+    Du = Cls(Xm.copy(), center_predictor=True, add_intercept=True, ctx=solo)      # unsharded
+    lo, hi = Ds.row_offset, Ds.row_offset + Ds.shape[0]
+    rng = np.random.default_rng(1)
+    v, w, wt = rng.standard_normal(pp + 1), rng.standard_normal(nn), rng.random(nn)
+    check(name + ' dot', rel(Ds.dot(v), Du.dot(v)[lo:hi]), 1e-13)
+    check(name + ' Tdot', rel(Ds.Tdot(w[lo:hi]), Du.Tdot(w)), 1e-12)
+    check(name + ' fisher', rel(Ds.compute_fisher_info(wt[lo:hi], True), Du.compute_fisher_info(wt, True)), 1e-12)
+    P = pp + 1
+    omega = rng.random(nn) * 0.25 + 0.01
+    pps = np.concatenate(([0.5], 1 / (0.1 * rng.random(pp) + 1e-3)))
+    z, x0, sd = rng.standard_normal(P), 0.01 * rng.standard_normal(P), 0.5 + rng.random(P)
+    S = ConjugateGradientSampler(1)
+    for atol, tol in ((1e-5 * np.sqrt(P), 1e-5), (1e-12 * np.sqrt(P), 1e-8)):
+        np.random.seed(5); e1 = np.random.randn(nn); e2 = np.random.randn(P)
+        # inject the same global noise: the sharded call sees only its block of eps1
+        import ctypes
+        def run(D, om, e1_):
+            coef = np.empty(P); ni, info = ctypes.c_int(), ctypes.c_int()
+            s = S.choose_preconditioner(pps, None, D, 'prior', sd)
+            _lib.check(_lib.load().bb_cg_sample(D._mat, _lib.dptr(om), _lib.dptr(pps), _lib.dptr(z), _lib.dptr(x0), _lib.dptr(s),
+                                                float(atol), 500, 0, _lib.dptr(e1_), _lib.dptr(e2), 0, 0, _lib.dptr(coef),
+                                                ctypes.byref(ni), ctypes.byref(info), None))
+            return coef, ni.value
+        cs, ns = run(Ds, np.ascontiguousarray(omega[lo:hi]), np.ascontiguousarray(e1[lo:hi]))
+        cu, nu = run(Du, omega, e1)
+        check(f'{name} cg atol={atol:.0e} (n_iter {ns}/{nu})', rel(cs, cu), tol)
+        # every rank must hold bit-identical coefficients
+        t = torch.from_numpy(cs.copy()).cuda(); t0 = t.clone(); dist.broadcast(t0, 0)
+        check(f'{name} cg replicas identical', float((t - t0).abs().max()), 0.0)
+    # device noise: sharding-invariant streams -> same draw as unsharded
+    a, _ = S.sample(Ds, np.ascontiguousarray(omega[lo:hi]), pps, z, x0, 'prior', sd, maxiter=500, atol=1e-11, noise='device', philox=(9, 3))
+    b, _ = S.sample(Du, omega, pps, z, x0, 'prior', sd, maxiter=500, atol=1e-11, noise='device', philox=(9, 3))
+    check(name + ' cg device-noise sharded vs unsharded', rel(a, b), 1e-8)
+
+# full chain, sharded vs unsharded, device RNG: identical streams => same chain up to CG tolerance
+y = rs.binomial(1, 1 / (1 + np.exp(-(X @ np.concatenate((np.full(5, 1.5), np.zeros(p - 5))) - 1.0))))
+chains = []
+for c in (ctx, solo):
+    model = bb.RegressionModel(y, X, family='logit', ctx=c)
+    s, info = bb.BayesBridge(model, bb.RegressionCoefPrior(bridge_exponent=.5)).gibbs(30, 10, coef_sampler_type='cg', seed=2)
+    chains.append(s)
+check('chain coef mean sharded vs unsharded', float(np.abs(chains[0]['coef'].mean(1) - chains[1]['coef'].mean(1)).max()), 5e-2)
+check('chain logp sharded vs unsharded', float(abs(chains[0]['logp'].mean() / chains[1]['logp'].mean() - 1)), 1e-2)
+flag = torch.tensor([1.0 if ok else 0.0]).cuda(); dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print('MULTI_GPU_CHECK', 'PASS' if flag.item() == 1.0 else 'FAIL', flush=True)
+dist.destroy_process_group()
