@@ -113,7 +113,8 @@ struct SlabFmt {
     int*  head_seg;     // [ntiles] virtual segment continued from the previous tile, or -1
     int2* tmeta;        // [ntiles] {first owned virtual segment, number owned}
     int*  slab_tile0;   // [nslab+1] first tile of each slab
-    int*  slab_nnz0;    // [nslab+1] first nnz of each slab
+    int*  slab_nnz0;    // [nslab+1] first nnz of each slab (padded to a multiple of 4)
+    int*  slab_nnz1;    // [nslab+1] one past the last nnz of each slab
     double* part;       // [nslab*n_seg] per-slab partial sums (output of the kernel)
     double* head_part;  // [ntiles]
 };

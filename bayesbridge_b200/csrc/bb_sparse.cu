@@ -65,6 +65,25 @@ __global__ void k_lower_bound(const K* __restrict__ key, i64 n, i64 nv, int* __r
     out[v] = (int)lo;
 }
 
+// slab-major copy with every slab start padded to a multiple of 4 nnz (128-bit loads)
+__global__ void k_scatter_padded(const int* __restrict__ cidx, const double* __restrict__ cval,
+                                 const int* __restrict__ perm, const int* __restrict__ slab_sorted,
+                                 const int* __restrict__ delta, i64 n, int* __restrict__ oidx, double* __restrict__ oval) {
+    i64 m = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n) return;
+    i64 dst = m + delta[slab_sorted[m]];
+    int src = perm[m];
+    oidx[dst] = cidx[src];
+    if (cval) oval[dst] = cval[src];
+}
+// ptr[v] (position in the unpadded sorted sequence) -> position in the padded arrays
+__global__ void k_shift_ptr(int* __restrict__ ptr, i64 V, i64 n_seg, const int* __restrict__ delta) {
+    i64 v = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v > V) return;
+    i64 slab = (n_seg > 0) ? (v / n_seg) : 0;             // the sentinel v == V indexes delta[nslab] (= last slab's shift)
+    ptr[v] += delta[slab];
+}
+
 // per-tile ownership: slab/last flags are packed in vlo/vhi on input
 __global__ void k_tile_meta(const int* __restrict__ ptr, i64 V, i64 n_seg, int ntiles,
                             TileMeta* __restrict__ tiles, int* __restrict__ head_seg) {
@@ -117,37 +136,43 @@ struct TileData {
     double rv[BINARY ? 1 : SPMV_ITEMS];
 };
 
-// Loads of one tile.  Elements past `end` are clamped to the last valid nnz: their products are
-// garbage that no piece ever reads (pieces cover [0, end-start) only), so no predication is needed.
+// Loads of one tile in BLOCKED layout: lane l owns the 8 consecutive nnz [start+8l, start+8l+8), fetched
+// with 128-bit loads (tile starts are multiples of 4 nnz from a 256 B-aligned base).  A partial tile (the
+// last of a slab) uses clamped scalar loads: elements past `end` duplicate the last valid nnz, and their
+// products land beyond every piece, where nothing reads them.
 template <bool BINARY>
 __device__ __forceinline__ void tile_fetch(TileData<BINARY>& R, int start, int end,
                                            const int* __restrict__ idx, const double* __restrict__ val, int lane) {
     if (end - start == SPMV_TILE) {
-        const int* ip = idx + start + lane;
-        const double* vp = BINARY ? nullptr : val + start + lane;
+        const int4* ip = reinterpret_cast<const int4*>(idx + start) + lane * 2;
+        int4 a = ip[0], b = ip[1];
+        R.ri[0] = a.x; R.ri[1] = a.y; R.ri[2] = a.z; R.ri[3] = a.w;
+        R.ri[4] = b.x; R.ri[5] = b.y; R.ri[6] = b.z; R.ri[7] = b.w;
+        if (!BINARY) {
+            const double2* vp = reinterpret_cast<const double2*>(val + start) + lane * 4;
 #pragma unroll
-        for (int j = 0; j < SPMV_ITEMS; ++j) {
-            R.ri[j] = ip[j * 32];
-            if (!BINARY) R.rv[j] = vp[j * 32];
+            for (int q = 0; q < 4; ++q) { double2 v = vp[q]; R.rv[BINARY ? 0 : 2 * q] = v.x; R.rv[BINARY ? 0 : 2 * q + 1] = v.y; }
         }
     } else if (end > start) {
 #pragma unroll
         for (int j = 0; j < SPMV_ITEMS; ++j) {
-            int k = min(start + j * 32 + lane, end - 1);
+            int k = min(start + lane * SPMV_ITEMS + j, end - 1);
             R.ri[j] = idx[k];
-            if (!BINARY) R.rv[j] = val[k];
+            if (!BINARY) R.rv[BINARY ? 0 : j] = val[k];
         }
-    } else {
-#pragma unroll
-        for (int j = 0; j < SPMV_ITEMS; ++j) { R.ri[j] = -1; if (!BINARY) R.rv[j] = 0.0; }
     }
 }
 
+// The SpMV kernel.  Per 256-nnz tile a warp computes the products, marks the
+// starts of the tile's pieces in a 256-bit head-flag map (cut points c_k = min(ptr[vlo+k], end) - start),
+// runs a segmented inclusive scan (8 serial steps per lane + 5 shuffle steps across lanes), parks the
+// prefix values in shared memory, and lane k picks the total of piece k at position c_k - 1.
 template <bool BINARY, bool STAGE>
 __global__ void __launch_bounds__(SPMV_THREADS, 1)
 k_seg_spmv(const int* __restrict__ ptr, const int* __restrict__ idx, const double* __restrict__ val,
            const int2* __restrict__ tmeta, const int* __restrict__ slab_tile0, const int* __restrict__ slab_nnz0,
-           int nslab, int ntiles, const double* __restrict__ gvec, int W, i64 n_gather, int wstage,
+           const int* __restrict__ slab_nnz1, int nslab, int ntiles,
+           const double* __restrict__ gvec, int W, i64 n_gather, int wstage,
            double* __restrict__ part, double* __restrict__ head_part, const int* __restrict__ done_flag)
 {
     if (done_flag != nullptr && *done_flag) return;
@@ -155,11 +180,11 @@ k_seg_spmv(const int* __restrict__ ptr, const int* __restrict__ idx, const doubl
     double* sv = smem;
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    double* wprod = smem + wstage + warp * SPMV_TILE;      // per-warp product buffer
+    double* wprod = smem + wstage + warp * SPMV_TILE;                       // per-warp prefix buffer
+    unsigned* fl = reinterpret_cast<unsigned*>(smem + wstage + SPMV_WARPS * SPMV_TILE) + warp * 8;   // head flags
     const int t_lo = (int)((i64)ntiles * blockIdx.x / gridDim.x);
     const int t_hi = (int)((i64)ntiles * (blockIdx.x + 1) / gridDim.x);
     if (t_lo >= t_hi) return;
-    // slab containing tile t_lo: last s with slab_tile0[s] <= t_lo
     int slab;
     {
         int lo = 0, hi = nslab;
@@ -170,7 +195,7 @@ k_seg_spmv(const int* __restrict__ ptr, const int* __restrict__ idx, const doubl
     while (cur < t_hi) {
         const int s_t0 = slab_tile0[slab];
         const int sec_end = min(t_hi, slab_tile0[slab + 1]);
-        const int nnz0 = slab_nnz0[slab], nnz1 = slab_nnz0[slab + 1];
+        const int nnz0 = slab_nnz0[slab], nnz1 = slab_nnz1[slab];
         const i64 gbase = (i64)slab * W;
         if (STAGE) {
             __syncthreads();                               // previous section's readers are done
@@ -184,7 +209,6 @@ k_seg_spmv(const int* __restrict__ ptr, const int* __restrict__ idx, const doubl
             }
             for (; i < wlen; i += SPMV_THREADS) sv[i] = src[i];
         }
-        // gather base: shared (staged slab, rebased so that the global index addresses it) or global
         const double* gsrc = STAGE ? (sv - gbase) : gvec;
         int t = cur + warp;
         TileData<BINARY> R;
@@ -202,17 +226,60 @@ k_seg_spmv(const int* __restrict__ ptr, const int* __restrict__ idx, const doubl
         while (t < sec_end) {
             const int start = nnz0 + (t - s_t0) * SPMV_TILE;
             const int end = min(start + SPMV_TILE, nnz1);
-            // products of the current tile -> per-warp shared buffer
-            __syncwarp();
-            if (end > start) {
+            const int len = end - start;
+            const int vlo = m_cur.x, nown = m_cur.y;
+            const int c = min(cut, end) - start;            // cut point k = lane (valid for lane <= nown)
+            // products (blocked: p[j] is element 8*lane + j)
+            double p[SPMV_ITEMS];
+            if (len > 0) {
 #pragma unroll
                 for (int j = 0; j < SPMV_ITEMS; ++j) {
                     double g = gsrc[R.ri[j]];
-                    wprod[j * 32 + lane] = BINARY ? g : R.rv[BINARY ? 0 : j] * g;
+                    p[j] = BINARY ? g : R.rv[BINARY ? 0 : j] * g;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < SPMV_ITEMS; ++j) p[j] = 0.0;
+            }
+            // head flags: piece k+1 starts at c_k
+            __syncwarp();
+            if (lane < 8) fl[lane] = 0u;
+            __syncwarp();
+            if (lane < nown && c < len) atomicOr(&fl[c >> 5], 1u << (c & 31));
+            if (nown > 32) {
+                for (int k = 32 + lane; k < nown; k += 32) {
+                    int cc = min(ptr[vlo + k], end) - start;
+                    if (cc < len) atomicOr(&fl[cc >> 5], 1u << (cc & 31));
                 }
             }
-            const int vlo = m_cur.x, nown = m_cur.y;
-            int c = min(cut, end) - start;                  // this lane's cut point (lane <= nown)
+            __syncwarp();
+            const unsigned f = (fl[lane >> 2] >> ((lane & 3) * 8)) & 0xffu;
+            // segmented inclusive scan: serial inside the lane ...
+            double run = 0.0;
+#pragma unroll
+            for (int j = 0; j < SPMV_ITEMS; ++j) {
+                if ((f >> j) & 1u) run = 0.0;
+                run += p[j];
+                p[j] = run;
+            }
+            // ... and across lanes (segments start at lanes that contain a head)
+            double x = run;
+            unsigned hf = (f != 0u) ? 1u : 0u;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                double y = __shfl_up_sync(0xffffffffu, x, d);
+                unsigned g = __shfl_up_sync(0xffffffffu, hf, d);
+                if (lane >= d) { if (!hf) x += y; hf |= g; }
+            }
+            double carry = __shfl_up_sync(0xffffffffu, x, 1);
+            if (lane == 0) carry = 0.0;
+            const int nfirst = f ? (__ffs((int)f) - 1) : SPMV_ITEMS;
+#pragma unroll
+            for (int j = 0; j < SPMV_ITEMS; ++j) {
+                double v = p[j];
+                if (j < nfirst) v += carry;
+                wprod[j * 32 + lane] = v;                 // prefix value of element 8*lane + j
+            }
             // prefetch: data and cut points of tile t+32, metadata of tile t+64
             const int tn = t + SPMV_WARPS;
             if (tn < sec_end) {
@@ -223,41 +290,24 @@ k_seg_spmv(const int* __restrict__ ptr, const int* __restrict__ idx, const doubl
                 if (tn + SPMV_WARPS < sec_end) m_next = tmeta[tn + SPMV_WARPS];
             }
             __syncwarp();
-            // segmented reduction, 32 pieces per pass
-            const int npieces = nown + 1;
-            int G = 32;
-            if (npieces > 1) { int lg = 32 - __clz(min(npieces, 32) - 1); G = 32 >> lg; }
-            const int gl = lane & (G - 1), grp = lane / G, ngrp = 32 / G;
-            int prev_last = 0;                              // c_{base-1}
-            for (int base = 0; base < npieces; base += 32) {
-                if (base > 0) {                             // rare: more than 32 pieces in a tile
-                    int k = base + lane;
-                    c = (k <= nown) ? min(ptr[vlo + k], end) - start : end - start;
+            // piece k = [c_{k-1}, c_k): its total is the prefix value at c_k - 1
+            {
+                int prev = __shfl_up_sync(0xffffffffu, c, 1);
+                if (lane == 0) prev = 0;
+                if (lane <= nown) {
+                    double tot = 0.0;
+                    if (c > prev) { int e = c - 1; tot = wprod[(e & 7) * 32 + (e >> 3)]; }
+                    if (lane == 0) head_part[t] = tot; else part[vlo + lane - 1] = tot;
                 }
-                for (int sub = 0; sub < 32; sub += ngrp) {
-                    if (base + sub >= npieces) break;       // warp-uniform
-                    const int pl = sub + grp;               // piece index within this pass
-                    int b = __shfl_sync(0xffffffffu, c, pl);
-                    int a = __shfl_sync(0xffffffffu, c, (pl > 0) ? pl - 1 : 0);
-                    if (pl == 0) a = prev_last;
-                    const bool valid = (base + pl) <= nown;
-                    if (!valid) b = a;
-                    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-                    int e = a + gl;
-                    const double* wp = wprod;
-                    for (; e + 3 * G < b; e += 4 * G) {
-                        double x0 = wp[e], x1 = wp[e + G], x2 = wp[e + 2 * G], x3 = wp[e + 3 * G];
-                        s0 += x0; s1 += x1; s2 += x2; s3 += x3;
-                    }
-                    for (; e < b; e += G) s0 += wp[e];
-                    double sacc = (s0 + s1) + (s2 + s3);
-                    for (int o = G >> 1; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
-                    if (valid && gl == 0) {
-                        const int k = base + pl;
-                        if (k == 0) head_part[t] = sacc; else part[vlo + k - 1] = sacc;
-                    }
+            }
+            if (nown >= 32) {                               // rare: more than 32 pieces in a tile
+                for (int k = 32 + lane; k <= nown; k += 32) {
+                    int ck = min(ptr[vlo + k], end) - start;
+                    int pk = min(ptr[vlo + k - 1], end) - start;
+                    double tot = 0.0;
+                    if (ck > pk) { int e = ck - 1; tot = wprod[(e & 7) * 32 + (e >> 3)]; }
+                    part[vlo + k - 1] = tot;
                 }
-                prev_last = __shfl_sync(0xffffffffu, c, 31);
             }
             t = tn;
         }
@@ -428,6 +478,7 @@ int bb_slab_free(SlabFmt* f) {
     if (f->tmeta) cudaFree(f->tmeta);
     if (f->slab_tile0) cudaFree(f->slab_tile0);
     if (f->slab_nnz0) cudaFree(f->slab_nnz0);
+    if (f->slab_nnz1) cudaFree(f->slab_nnz1);
     if (f->part) cudaFree(f->part);
     if (f->head_part) cudaFree(f->head_part);
     memset(f, 0, sizeof(*f));
@@ -435,7 +486,7 @@ int bb_slab_free(SlabFmt* f) {
 }
 
 static i64 max_stage_width(bb_ctx* ctx) {
-    i64 avail = (i64)ctx->smem_optin - (i64)(SPMV_WARPS * SPMV_TILE) * 8 - 64;
+    i64 avail = (i64)ctx->smem_optin - (i64)(SPMV_WARPS * SPMV_TILE) * 8 - SPMV_WARPS * 8 * 4 - 64;
     i64 w = avail / 8;
     w &= ~(i64)31;
     if (w < 32) w = 32;
@@ -467,14 +518,15 @@ static int build_slab_format(bb_ctx* ctx, const int* cptr, const int* cidx, cons
     f->W = (int)W;
     f->nnz = nnz;
     const int TB = 256;
+    std::vector<int> padded_start((size_t)nslab + 1, 0), padded_end((size_t)nslab + 1, 0);
+    i64 padded_total = nnz;
     if (nslab == 1) {
         f->ptr = (int*)cptr; f->idx = (int*)cidx; f->val = (double*)cval;
         f->owns_arrays = false;
+        padded_start[0] = 0; padded_end[0] = (int)nnz;
     } else {
         f->owns_arrays = true;
         BB_CUDA(cudaMalloc((void**)&f->ptr, (size_t)(V + 1) * sizeof(int)));
-        BB_CUDA(cudaMalloc((void**)&f->idx, (size_t)(nnz > 0 ? nnz : 1) * sizeof(int)));
-        if (cval) BB_CUDA(cudaMalloc((void**)&f->val, (size_t)(nnz > 0 ? nnz : 1) * sizeof(double)));
         int *seg_of = nullptr, *key = nullptr, *key_sorted = nullptr, *iota = nullptr, *perm = nullptr;
         i64* vkey = nullptr;
         size_t nb = (size_t)(nnz > 0 ? nnz : 1);
@@ -485,6 +537,10 @@ static int build_slab_format(bb_ctx* ctx, const int* cptr, const int* cidx, cons
         BB_CUDA(cudaMalloc((void**)&perm, nb * sizeof(int)));
         BB_CUDA(cudaMalloc((void**)&vkey, nb * sizeof(i64)));
         int rc = BB_OK;
+        int* d_delta = nullptr;           // per-slab shift that pads every slab start to a multiple of 4 nnz
+        int* d_old = nullptr;
+        BB_CUDA(cudaMalloc((void**)&d_delta, ((size_t)nslab + 1) * sizeof(int)));
+        BB_CUDA(cudaMalloc((void**)&d_old, ((size_t)nslab + 1) * sizeof(int)));
         if (nnz > 0) {
             int g = (int)((nnz + TB - 1) / TB);
             k_expand_ptr<<<g, TB, 0, st>>>(cptr, n_seg, nnz, seg_of);
@@ -492,33 +548,58 @@ static int build_slab_format(bb_ctx* ctx, const int* cptr, const int* cidx, cons
             k_iota<<<g, TB, 0, st>>>(iota, nnz);
             ctx->launches += 3;
             rc = sort_pairs<int>(ctx, key, key_sorted, iota, perm, nnz, bits_for(nslab - 1));
-            if (rc == BB_OK) {
-                k_gather_i<<<g, TB, 0, st>>>(cidx, perm, nnz, f->idx);
-                if (cval) k_gather_d<<<g, TB, 0, st>>>(cval, perm, nnz, f->val);
-                k_vkey<<<g, TB, 0, st>>>(key_sorted, seg_of, perm, nnz, n_seg, vkey);
-                ctx->launches += 3;
+        }
+        std::vector<int> old_start((size_t)nslab + 1, 0), delta((size_t)nslab + 1, 0);
+        if (rc == BB_OK) {
+            // first position of every slab in the sorted sequence
+            k_lower_bound<int><<<(int)((nslab + 1 + TB - 1) / TB), TB, 0, st>>>(key_sorted, nnz, nslab, d_old);
+            ctx->launches += 1;
+            BB_CUDA(cudaMemcpyAsync(old_start.data(), d_old, ((size_t)nslab + 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
+            BB_CUDA(cudaStreamSynchronize(st));
+            i64 pos = 0;
+            for (i64 sl = 0; sl < nslab; ++sl) {
+                pos = (pos + 3) & ~(i64)3;
+                padded_start[(size_t)sl] = (int)pos;
+                delta[(size_t)sl] = (int)(pos - old_start[(size_t)sl]);
+                pos += old_start[(size_t)sl + 1] - old_start[(size_t)sl];
+                padded_end[(size_t)sl] = (int)pos;
             }
+            delta[(size_t)nslab] = delta[(size_t)nslab - 1];
+            padded_total = pos;
+            if (padded_total + 8 >= ((i64)1 << 31)) { bb_set_error("slab format exceeds int32 nnz range"); rc = BB_ERR_ARG; }
         }
         if (rc == BB_OK) {
+            BB_CUDA(cudaMemcpyAsync(d_delta, delta.data(), ((size_t)nslab + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+            BB_CUDA(cudaMalloc((void**)&f->idx, (size_t)(padded_total + 8) * sizeof(int)));
+            BB_CUDA(cudaMemsetAsync(f->idx, 0, (size_t)(padded_total + 8) * sizeof(int), st));
+            if (cval) {
+                BB_CUDA(cudaMalloc((void**)&f->val, (size_t)(padded_total + 8) * sizeof(double)));
+                BB_CUDA(cudaMemsetAsync(f->val, 0, (size_t)(padded_total + 8) * sizeof(double), st));
+            }
+            if (nnz > 0) {
+                int g = (int)((nnz + TB - 1) / TB);
+                k_scatter_padded<<<g, TB, 0, st>>>(cidx, cval, perm, key_sorted, d_delta, nnz, f->idx, f->val);
+                k_vkey<<<g, TB, 0, st>>>(key_sorted, seg_of, perm, nnz, n_seg, vkey);
+                ctx->launches += 2;
+            }
             int g = (int)((V + 1 + TB - 1) / TB);
             k_lower_bound<i64><<<g, TB, 0, st>>>(vkey, nnz, V, f->ptr);
-            ctx->launches += 1;
+            k_shift_ptr<<<g, TB, 0, st>>>(f->ptr, V, n_seg, d_delta);
+            ctx->launches += 2;
             cudaError_t e = cudaStreamSynchronize(st);
             if (e != cudaSuccess) { bb_set_error("slab build: %s", cudaGetErrorString(e)); rc = BB_ERR_CUDA; }
         }
+        cudaFree(d_delta); cudaFree(d_old);
         cudaFree(seg_of); cudaFree(key); cudaFree(key_sorted); cudaFree(iota); cudaFree(perm); cudaFree(vkey);
         BB_TRY(rc);
     }
     // slab nnz ranges -> tiles (host), ownership (device)
-    std::vector<int> slab_off((size_t)nslab + 1);
-    for (i64 s = 0; s <= nslab; ++s)
-        BB_CUDA(cudaMemcpyAsync(&slab_off[(size_t)s], f->ptr + s * n_seg, sizeof(int), cudaMemcpyDeviceToHost, st));
-    BB_CUDA(cudaStreamSynchronize(st));
+    std::vector<int>& slab_off = padded_start;
     std::vector<TileMeta> tiles;
     std::vector<int> slab_tile0((size_t)nslab + 1);
     for (i64 s = 0; s < nslab; ++s) {
         slab_tile0[(size_t)s] = (int)tiles.size();
-        int a = slab_off[(size_t)s], b = slab_off[(size_t)s + 1];
+        int a = padded_start[(size_t)s], b = padded_end[(size_t)s];
         int nt = (b - a + SPMV_TILE - 1) / SPMV_TILE;
         if (nt < 1) nt = 1;
         for (int t = 0; t < nt; ++t) {
@@ -545,7 +626,9 @@ static int build_slab_format(bb_ctx* ctx, const int* cptr, const int* cidx, cons
     BB_CUDA(cudaMalloc((void**)&f->slab_tile0, ((size_t)nslab + 1) * sizeof(int)));
     BB_CUDA(cudaMalloc((void**)&f->slab_nnz0, ((size_t)nslab + 1) * sizeof(int)));
     BB_CUDA(cudaMemcpyAsync(f->slab_tile0, slab_tile0.data(), ((size_t)nslab + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+    BB_CUDA(cudaMalloc((void**)&f->slab_nnz1, ((size_t)nslab + 1) * sizeof(int)));
     BB_CUDA(cudaMemcpyAsync(f->slab_nnz0, slab_off.data(), ((size_t)nslab + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+    BB_CUDA(cudaMemcpyAsync(f->slab_nnz1, padded_end.data(), ((size_t)nslab + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
     BB_CUDA(cudaMalloc((void**)&f->part, (size_t)(V > 0 ? V : 1) * sizeof(double)));
     BB_CUDA(cudaMalloc((void**)&f->head_part, (size_t)f->ntiles * sizeof(double)));
     BB_CUDA(cudaMemsetAsync(f->part, 0, (size_t)(V > 0 ? V : 1) * sizeof(double), st));
@@ -560,7 +643,7 @@ int bb_launch_spmv(bb_mat* m, SlabFmt* f, const double* gvec, const int* done_fl
     // a format built without staging in mind may have slabs wider than shared memory
     const bool stage = f->staged && (i64)f->W <= max_stage_width(ctx);
     int wstage = stage ? f->W : 0;
-    size_t smem = (size_t)(wstage + SPMV_WARPS * SPMV_TILE) * sizeof(double);
+    size_t smem = (size_t)(wstage + SPMV_WARPS * SPMV_TILE) * sizeof(double) + SPMV_WARPS * 8 * sizeof(unsigned);
     static bool attr_set = false;
     if (!attr_set) {
         int mx = (int)ctx->smem_optin;
@@ -574,7 +657,7 @@ int bb_launch_spmv(bb_mat* m, SlabFmt* f, const double* gvec, const int* done_fl
     const bool binary = (f->val == nullptr);
     int ncta = ctx->sm_count < f->ntiles ? ctx->sm_count : f->ntiles;
     dim3 grid(ncta), block(SPMV_THREADS);
-#define SPMV_ARGS f->ptr, f->idx, f->val, f->tmeta, f->slab_tile0, f->slab_nnz0, f->nslab, f->ntiles, gvec, f->W, f->n_gather, wstage, f->part, f->head_part, done_flag
+#define SPMV_ARGS f->ptr, f->idx, f->val, f->tmeta, f->slab_tile0, f->slab_nnz0, f->slab_nnz1, f->nslab, f->ntiles, gvec, f->W, f->n_gather, wstage, f->part, f->head_part, done_flag
     if (binary && stage) k_seg_spmv<true, true><<<grid, block, smem, ctx->stream>>>(SPMV_ARGS);
     else if (binary && !stage) k_seg_spmv<true, false><<<grid, block, smem, ctx->stream>>>(SPMV_ARGS);
     else if (!binary && stage) k_seg_spmv<false, true><<<grid, block, smem, ctx->stream>>>(SPMV_ARGS);
