@@ -127,6 +127,36 @@ class AbstractDesignMatrix(abc.ABC):
         return X
 
     @staticmethod
+    def remove_intercept_indicator_sharded(X_local, ctx, n_global):
+        """Same rule as remove_intercept_indicator, for a matrix given as per-rank row blocks: the column
+        moments are summed over all ranks first, so that every rank drops the SAME columns (a column that is
+        constant inside one block only must stay, or the ranks would disagree on p and the allreduce would hang)."""
+        if sparse.issparse(X_local):
+            s1 = np.asarray(X_local.sum(axis=0)).ravel()
+            s2 = np.asarray(X_local.power(2).sum(axis=0)).ravel()
+        else:
+            s1, s2 = X_local.sum(axis=0), (X_local ** 2).sum(axis=0)
+        tot = ctx.allreduce_host(np.concatenate((s1, s2)))
+        p = X_local.shape[1]
+        mean, sq_mean = tot[:p] / n_global, tot[p:] / n_global
+        constant = (sq_mean - mean ** 2) < n_global * 2.0 ** -52
+        if np.any(constant):
+            warnings.warn(
+                "Intercept column (or numerically indistinguishable from such) detected. "
+                "Do not add intercept manually. Removing....")
+            X_local = X_local[:, np.logical_not(constant)]
+            mean = mean[np.logical_not(constant)]
+        return X_local, mean
+
+    def _check_shards_agree(self):
+        """Every rank must hold the same number of columns, or the allreduces inside libbbgpu would hang."""
+        if self.ctx.nranks > 1:
+            P = float(self.shape[1])
+            tot = self.ctx.allreduce_host(np.array([P, P * P]))
+            if tot[0] != self.ctx.nranks * P or tot[1] != self.ctx.nranks * P * P:
+                raise ValueError("Row shards disagree on the number of predictors.")
+
+    @staticmethod
     def shard_rows(n, ctx):
         """Contiguous row block of this rank: [lo, hi)."""
         G, r = ctx.nranks, ctx.rank

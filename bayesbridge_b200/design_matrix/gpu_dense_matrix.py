@@ -20,13 +20,13 @@ class GpuDenseDesignMatrix(AbstractDesignMatrix):
         self.ctx = ctx if ctx is not None else _lib.Context.default()
         self.centered = bool(center_predictor)
         self.intercept_added = bool(add_intercept)
-        X = self.remove_intercept_indicator(X)
         sharded = self.ctx.nranks > 1
         if sharded and presharded:
             n_glob = int(n_global)
-            col_mean = self.ctx.allreduce_host(X.sum(axis=0)) / n_glob
+            X, col_mean = self.remove_intercept_indicator_sharded(X, self.ctx, n_glob)
             X_local = X
         else:
+            X = self.remove_intercept_indicator(X)
             n_glob = X.shape[0]
             col_mean = np.mean(X, axis=0)
             if sharded:
@@ -44,6 +44,7 @@ class GpuDenseDesignMatrix(AbstractDesignMatrix):
             self.ctx.handle, self.X_raw.shape[0], self.X_raw.shape[1], _lib.dptr(self.X_raw),
             _lib.dptr(offset), int(self.intercept_added), self.row_offset, n_glob, ctypes.byref(handle)))
         self._mat = handle
+        self._check_shards_agree()
 
     @property
     def shape(self):

@@ -31,15 +31,14 @@ class GpuSparseDesignMatrix(AbstractDesignMatrix):
         self.centered = bool(center_predictor)
         self.intercept_added = bool(add_intercept)
         self.use_mkl = False
-        X = self.remove_intercept_indicator(X)
         sharded = self.ctx.nranks > 1
 
         if sharded and presharded:
             n_glob = int(n_global)
-            col_sum = self.ctx.allreduce_host(np.asarray(X.sum(axis=0)).ravel())
-            col_mean = col_sum / n_glob
+            X, col_mean = self.remove_intercept_indicator_sharded(X, self.ctx, n_glob)
             X_local = X.tocsr()
         else:
+            X = self.remove_intercept_indicator(X)
             n_glob = X.shape[0]
             col_mean = np.squeeze(np.array(X.mean(axis=0))).reshape(-1)
             X_csr = X.tocsr()
@@ -70,6 +69,7 @@ class GpuSparseDesignMatrix(AbstractDesignMatrix):
             _lib.iptr(indptr), _lib.iptr(indices), None if self.is_binary else _lib.dptr(data),
             _lib.dptr(offset), int(self.intercept_added), self.row_offset, n_glob, ctypes.byref(handle)))
         self._mat = handle
+        self._check_shards_agree()
 
     @property
     def shape(self):
