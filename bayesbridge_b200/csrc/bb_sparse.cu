@@ -130,43 +130,46 @@ __global__ void k_compact_meta(const TileMeta* __restrict__ tiles, int ntiles, i
 // by its cut points c_k = min(ptr[vlo+k], end) - start: piece 0 is the head (a segment continued from
 // the previous tile -> head_part), piece k>0 is owned segment vlo+k-1 (-> part).  The reduction shape
 // depends only on static metadata, so results are bit-reproducible.
-template <bool BINARY>
-struct TileData {
-    int ri[SPMV_ITEMS];
-    double rv[BINARY ? 1 : SPMV_ITEMS];
-};
-
 // Loads of one tile in BLOCKED layout: lane l owns the 8 consecutive nnz [start+8l, start+8l+8), fetched
 // with 128-bit loads (tile starts are multiples of 4 nnz from a 256 B-aligned base).  A partial tile (the
 // last of a slab) uses clamped scalar loads: elements past `end` duplicate the last valid nnz, and their
-// products land beyond every piece, where nothing reads them.
-template <bool BINARY>
-__device__ __forceinline__ void tile_fetch(TileData<BINARY>& R, int start, int end,
-                                           const int* __restrict__ idx, const double* __restrict__ val, int lane) {
+// products land beyond every piece, where nothing reads them.  Indices and values are fetched separately so
+// that the index prefetch can be issued early and the value prefetch once the product registers are dead.
+__device__ __forceinline__ void tile_fetch_idx(int (&ri)[SPMV_ITEMS], int start, int end,
+                                               const int* __restrict__ idx, int lane) {
     if (end - start == SPMV_TILE) {
         const int4* ip = reinterpret_cast<const int4*>(idx + start) + lane * 2;
         int4 a = ip[0], b = ip[1];
-        R.ri[0] = a.x; R.ri[1] = a.y; R.ri[2] = a.z; R.ri[3] = a.w;
-        R.ri[4] = b.x; R.ri[5] = b.y; R.ri[6] = b.z; R.ri[7] = b.w;
-        if (!BINARY) {
-            const double2* vp = reinterpret_cast<const double2*>(val + start) + lane * 4;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) { double2 v = vp[q]; R.rv[BINARY ? 0 : 2 * q] = v.x; R.rv[BINARY ? 0 : 2 * q + 1] = v.y; }
-        }
+        ri[0] = a.x; ri[1] = a.y; ri[2] = a.z; ri[3] = a.w;
+        ri[4] = b.x; ri[5] = b.y; ri[6] = b.z; ri[7] = b.w;
     } else if (end > start) {
 #pragma unroll
-        for (int j = 0; j < SPMV_ITEMS; ++j) {
-            int k = min(start + lane * SPMV_ITEMS + j, end - 1);
-            R.ri[j] = idx[k];
-            if (!BINARY) R.rv[BINARY ? 0 : j] = val[k];
-        }
+        for (int j = 0; j < SPMV_ITEMS; ++j) ri[j] = idx[min(start + lane * SPMV_ITEMS + j, end - 1)];
     }
+}
+__device__ __forceinline__ void tile_fetch_val(double (&rv)[SPMV_ITEMS], int start, int end,
+                                               const double* __restrict__ val, int lane) {
+    if (end - start == SPMV_TILE) {
+        const double2* vp = reinterpret_cast<const double2*>(val + start) + lane * 4;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { double2 v = vp[q]; rv[2 * q] = v.x; rv[2 * q + 1] = v.y; }
+    } else if (end > start) {
+#pragma unroll
+        for (int j = 0; j < SPMV_ITEMS; ++j) rv[j] = val[min(start + lane * SPMV_ITEMS + j, end - 1)];
+    }
+}
+
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
 }
 
 // The SpMV kernel.  Per 256-nnz tile a warp computes the products, marks the
 // starts of the tile's pieces in a 256-bit head-flag map (cut points c_k = min(ptr[vlo+k], end) - start),
 // runs a segmented inclusive scan (8 serial steps per lane + 5 shuffle steps across lanes), parks the
-// prefix values in shared memory, and lane k picks the total of piece k at position c_k - 1.
+// lane-local prefix values and the per-lane carries in shared memory, and lane k picks the total of piece k
+// at position c_k - 1 (adding the carry of that lane when no piece starts in the lane at or before it).
 template <bool BINARY, bool STAGE>
 __global__ void __launch_bounds__(SPMV_THREADS, 1)
 k_seg_spmv(const int* __restrict__ ptr, const int* __restrict__ idx, const double* __restrict__ val,
@@ -181,7 +184,8 @@ k_seg_spmv(const int* __restrict__ ptr, const int* __restrict__ idx, const doubl
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     double* wprod = smem + wstage + warp * SPMV_TILE;                       // per-warp prefix buffer
-    unsigned* fl = reinterpret_cast<unsigned*>(smem + wstage + SPMV_WARPS * SPMV_TILE) + warp * 8;   // head flags
+    double* wcarry = smem + wstage + SPMV_WARPS * SPMV_TILE + warp * 32;     // per-lane carries
+    unsigned* fl = reinterpret_cast<unsigned*>(smem + wstage + SPMV_WARPS * (SPMV_TILE + 32)) + warp * 8;   // head flags
     const int t_lo = (int)((i64)ntiles * blockIdx.x / gridDim.x);
     const int t_hi = (int)((i64)ntiles * (blockIdx.x + 1) / gridDim.x);
     if (t_lo >= t_hi) return;
@@ -209,14 +213,17 @@ k_seg_spmv(const int* __restrict__ ptr, const int* __restrict__ idx, const doubl
             }
             for (; i < wlen; i += SPMV_THREADS) sv[i] = src[i];
         }
-        const double* gsrc = STAGE ? (sv - gbase) : gvec;
+        // byte address such that (sbase + 8*global_index) addresses the staged entry
+        const unsigned sbase = (unsigned)__cvta_generic_to_shared(sv) - (unsigned)((unsigned)gbase << 3);
         int t = cur + warp;
-        TileData<BINARY> R;
+        int ri[SPMV_ITEMS];
+        double rv[SPMV_ITEMS];
         int2 m_cur = make_int2(0, 0), m_next = make_int2(0, 0);
         int cut = 0;
         if (t < sec_end) {
             const int st0 = nnz0 + (t - s_t0) * SPMV_TILE;
-            tile_fetch<BINARY>(R, st0, min(st0 + SPMV_TILE, nnz1), idx, val, lane);
+            tile_fetch_idx(ri, st0, min(st0 + SPMV_TILE, nnz1), idx, lane);
+            if (!BINARY) tile_fetch_val(rv, st0, min(st0 + SPMV_TILE, nnz1), val, lane);
             m_cur = tmeta[t];
             if (t + SPMV_WARPS < sec_end) m_next = tmeta[t + SPMV_WARPS];
             cut = (lane <= m_cur.y) ? ptr[m_cur.x + lane] : 0x7fffffff;
@@ -229,84 +236,99 @@ k_seg_spmv(const int* __restrict__ ptr, const int* __restrict__ idx, const doubl
             const int len = end - start;
             const int vlo = m_cur.x, nown = m_cur.y;
             const int c = min(cut, end) - start;            // cut point k = lane (valid for lane <= nown)
-            // products (blocked: p[j] is element 8*lane + j)
+            const int tn = t + SPMV_WARPS;
+            const int st1 = nnz0 + (tn - s_t0) * SPMV_TILE;
+            const int en1 = min(st1 + SPMV_TILE, nnz1);
             double p[SPMV_ITEMS];
             if (len > 0) {
+                // products (blocked: p[j] is element 8*lane + j)
 #pragma unroll
                 for (int j = 0; j < SPMV_ITEMS; ++j) {
-                    double g = gsrc[R.ri[j]];
-                    p[j] = BINARY ? g : R.rv[BINARY ? 0 : j] * g;
+                    double g = STAGE ? lds_f64(sbase + ((unsigned)ri[j] << 3)) : __ldg(gvec + ri[j]);
+                    p[j] = BINARY ? g : rv[j] * g;
+                }
+                // early prefetch (indices, cut points, metadata) of the next tile: `ri` is dead now
+                if (tn < sec_end) {
+                    tile_fetch_idx(ri, st1, en1, idx, lane);
+                    m_cur = m_next;
+                    cut = (lane <= m_cur.y) ? ptr[m_cur.x + lane] : 0x7fffffff;
+                    if (tn + SPMV_WARPS < sec_end) m_next = tmeta[tn + SPMV_WARPS];
+                }
+                // head flags: piece k+1 starts at c_k
+                __syncwarp();
+                if (lane < 8) fl[lane] = 0u;
+                __syncwarp();
+                if (lane < nown && c < len) atomicOr(&fl[c >> 5], 1u << (c & 31));
+                if (nown > 32) {
+                    for (int k = 32 + lane; k < nown; k += 32) {
+                        int cc = min(ptr[vlo + k], end) - start;
+                        if (cc < len) atomicOr(&fl[cc >> 5], 1u << (cc & 31));
+                    }
+                }
+                __syncwarp();
+                const unsigned f = (fl[lane >> 2] >> ((lane & 3) * 8)) & 0xffu;
+                // segmented inclusive scan: serial inside the lane ...
+                double run = 0.0;
+#pragma unroll
+                for (int j = 0; j < SPMV_ITEMS; ++j) {
+                    if ((f >> j) & 1u) run = 0.0;
+                    run += p[j];
+                    wprod[j * 32 + lane] = run;           // lane-local prefix of element 8*lane + j
+                }
+                // late prefetch (values): the product registers are dead now
+                if (!BINARY && tn < sec_end) tile_fetch_val(rv, st1, en1, val, lane);
+                // ... and across lanes (segments start at lanes that contain a head)
+                double x = run;
+                unsigned hf = (f != 0u) ? 1u : 0u;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    double y = __shfl_up_sync(0xffffffffu, x, d);
+                    unsigned g = __shfl_up_sync(0xffffffffu, hf, d);
+                    if (lane >= d) { if (!hf) x += y; hf |= g; }
+                }
+                double carry = __shfl_up_sync(0xffffffffu, x, 1);
+                if (lane == 0) carry = 0.0;
+                wcarry[lane] = carry;                       // sum of the open piece over the previous lanes
+                __syncwarp();
+                // piece k = [c_{k-1}, c_k): total = prefix at e = c_k - 1 (+ carry of e's lane if the piece began before it)
+                {
+                    int prev = __shfl_up_sync(0xffffffffu, c, 1);
+                    if (lane == 0) prev = 0;
+                    if (lane <= nown) {
+                        double tot = 0.0;
+                        if (c > prev) {
+                            int e = c - 1, le = e >> 3, je = e & 7;
+                            unsigned fe = (fl[le >> 2] >> ((le & 3) * 8)) & 0xffu;
+                            tot = wprod[je * 32 + le];
+                            if ((fe & ((2u << je) - 1u)) == 0u) tot += wcarry[le];
+                        }
+                        if (lane == 0) head_part[t] = tot; else part[vlo + lane - 1] = tot;
+                    }
+                }
+                if (nown >= 32) {                           // rare: more than 32 pieces in a tile
+                    for (int k = 32 + lane; k <= nown; k += 32) {
+                        int ck = min(ptr[vlo + k], end) - start;
+                        int pk = min(ptr[vlo + k - 1], end) - start;
+                        double tot = 0.0;
+                        if (ck > pk) {
+                            int e = ck - 1, le = e >> 3, je = e & 7;
+                            unsigned fe = (fl[le >> 2] >> ((le & 3) * 8)) & 0xffu;
+                            tot = wprod[je * 32 + le];
+                            if ((fe & ((2u << je) - 1u)) == 0u) tot += wcarry[le];
+                        }
+                        part[vlo + k - 1] = tot;
+                    }
                 }
             } else {
-#pragma unroll
-                for (int j = 0; j < SPMV_ITEMS; ++j) p[j] = 0.0;
-            }
-            // head flags: piece k+1 starts at c_k
-            __syncwarp();
-            if (lane < 8) fl[lane] = 0u;
-            __syncwarp();
-            if (lane < nown && c < len) atomicOr(&fl[c >> 5], 1u << (c & 31));
-            if (nown > 32) {
-                for (int k = 32 + lane; k < nown; k += 32) {
-                    int cc = min(ptr[vlo + k], end) - start;
-                    if (cc < len) atomicOr(&fl[cc >> 5], 1u << (cc & 31));
-                }
-            }
-            __syncwarp();
-            const unsigned f = (fl[lane >> 2] >> ((lane & 3) * 8)) & 0xffu;
-            // segmented inclusive scan: serial inside the lane ...
-            double run = 0.0;
-#pragma unroll
-            for (int j = 0; j < SPMV_ITEMS; ++j) {
-                if ((f >> j) & 1u) run = 0.0;
-                run += p[j];
-                p[j] = run;
-            }
-            // ... and across lanes (segments start at lanes that contain a head)
-            double x = run;
-            unsigned hf = (f != 0u) ? 1u : 0u;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                double y = __shfl_up_sync(0xffffffffu, x, d);
-                unsigned g = __shfl_up_sync(0xffffffffu, hf, d);
-                if (lane >= d) { if (!hf) x += y; hf |= g; }
-            }
-            double carry = __shfl_up_sync(0xffffffffu, x, 1);
-            if (lane == 0) carry = 0.0;
-            const int nfirst = f ? (__ffs((int)f) - 1) : SPMV_ITEMS;
-#pragma unroll
-            for (int j = 0; j < SPMV_ITEMS; ++j) {
-                double v = p[j];
-                if (j < nfirst) v += carry;
-                wprod[j * 32 + lane] = v;                 // prefix value of element 8*lane + j
-            }
-            // prefetch: data and cut points of tile t+32, metadata of tile t+64
-            const int tn = t + SPMV_WARPS;
-            if (tn < sec_end) {
-                const int st1 = nnz0 + (tn - s_t0) * SPMV_TILE;
-                tile_fetch<BINARY>(R, st1, min(st1 + SPMV_TILE, nnz1), idx, val, lane);
-                m_cur = m_next;
-                cut = (lane <= m_cur.y) ? ptr[m_cur.x + lane] : 0x7fffffff;
-                if (tn + SPMV_WARPS < sec_end) m_next = tmeta[tn + SPMV_WARPS];
-            }
-            __syncwarp();
-            // piece k = [c_{k-1}, c_k): its total is the prefix value at c_k - 1
-            {
-                int prev = __shfl_up_sync(0xffffffffu, c, 1);
-                if (lane == 0) prev = 0;
-                if (lane <= nown) {
-                    double tot = 0.0;
-                    if (c > prev) { int e = c - 1; tot = wprod[(e & 7) * 32 + (e >> 3)]; }
-                    if (lane == 0) head_part[t] = tot; else part[vlo + lane - 1] = tot;
-                }
-            }
-            if (nown >= 32) {                               // rare: more than 32 pieces in a tile
-                for (int k = 32 + lane; k <= nown; k += 32) {
-                    int ck = min(ptr[vlo + k], end) - start;
-                    int pk = min(ptr[vlo + k - 1], end) - start;
-                    double tot = 0.0;
-                    if (ck > pk) { int e = ck - 1; tot = wprod[(e & 7) * 32 + (e >> 3)]; }
-                    part[vlo + k - 1] = tot;
+                // empty tile (a slab without nnz): every owned segment is empty
+                if (lane == 0) head_part[t] = 0.0;
+                for (int k = 1 + lane; k <= nown; k += 32) part[vlo + k - 1] = 0.0;
+                if (tn < sec_end) {
+                    tile_fetch_idx(ri, st1, en1, idx, lane);
+                    if (!BINARY) tile_fetch_val(rv, st1, en1, val, lane);
+                    m_cur = m_next;
+                    cut = (lane <= m_cur.y) ? ptr[m_cur.x + lane] : 0x7fffffff;
+                    if (tn + SPMV_WARPS < sec_end) m_next = tmeta[tn + SPMV_WARPS];
                 }
             }
             t = tn;
@@ -486,7 +508,7 @@ int bb_slab_free(SlabFmt* f) {
 }
 
 static i64 max_stage_width(bb_ctx* ctx) {
-    i64 avail = (i64)ctx->smem_optin - (i64)(SPMV_WARPS * SPMV_TILE) * 8 - SPMV_WARPS * 8 * 4 - 64;
+    i64 avail = (i64)ctx->smem_optin - (i64)(SPMV_WARPS * (SPMV_TILE + 32)) * 8 - SPMV_WARPS * 8 * 4 - 64;
     i64 w = avail / 8;
     w &= ~(i64)31;
     if (w < 32) w = 32;
@@ -643,7 +665,7 @@ int bb_launch_spmv(bb_mat* m, SlabFmt* f, const double* gvec, const int* done_fl
     // a format built without staging in mind may have slabs wider than shared memory
     const bool stage = f->staged && (i64)f->W <= max_stage_width(ctx);
     int wstage = stage ? f->W : 0;
-    size_t smem = (size_t)(wstage + SPMV_WARPS * SPMV_TILE) * sizeof(double) + SPMV_WARPS * 8 * sizeof(unsigned);
+    size_t smem = (size_t)(wstage + SPMV_WARPS * (SPMV_TILE + 32)) * sizeof(double) + SPMV_WARPS * 8 * sizeof(unsigned);
     static bool attr_set = false;
     if (!attr_set) {
         int mx = (int)ctx->smem_optin;

@@ -1,0 +1,22 @@
+"""GPU (>= 2 devices): the row-sharded path, launched as one process per GPU under torchrun.
+scripts/multi_gpu_check.py compares, on every rank, the sharded design / CG sampler / chain (NCCL allreduce inside
+libbbgpu) against an unsharded design on the same GPU, and checks that all ranks hold bit-identical coefficients."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def test_sharded_path_matches_unsharded_two_gpus():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+           '--master-addr', '127.0.0.1', '--master-port', '29533', os.path.join(ROOT, 'scripts', 'multi_gpu_check.py')]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert 'MULTI_GPU_CHECK PASS' in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
