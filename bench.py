@@ -88,12 +88,15 @@ def generate_rows(blocks, n, p, density):
 
 # ---- clocks ------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
-    """Samples SM clocks and throttle reasons during the timed region through NVML (in-process: spawning
-    nvidia-smi every 200 ms was measured to slow the timed Gibbs loop 3x on the shared driver lock)."""
+    """Samples SM clocks and throttle reasons during the timed region through NVML, in-process.
+    On this driver every NVML query costs tens of milliseconds and serialises with kernel launches (spawning
+    nvidia-smi every 200 ms slowed the timed loop 3x, NVML every 250 ms 2x), so the sampler backs off to at
+    most ~5 % duty: it sleeps max(period, 20 x the measured query time) between samples."""
 
-    def __init__(self, device, period=0.25):
+    def __init__(self, device, period=0.4):
         super().__init__(daemon=True)
         self.device, self.period, self.samples, self.stop_flag = device, period, [], False
+        self.query_ms = []
         self.nvml = None
         try:
             import pynvml
@@ -109,6 +112,7 @@ class ClockSampler(threading.Thread):
             return
         nv = self.nvml
         while not self.stop_flag:
+            t0 = time.perf_counter()
             try:
                 sm = nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)
                 try:
@@ -118,7 +122,9 @@ class ClockSampler(threading.Thread):
                 self.samples.append((sm, reasons))
             except Exception:
                 pass
-            time.sleep(self.period)
+            dt = time.perf_counter() - t0
+            self.query_ms.append(1000 * dt)
+            time.sleep(max(self.period, 20 * dt))
 
     def summary(self):
         if not self.samples:
@@ -134,7 +140,8 @@ class ClockSampler(threading.Thread):
                  ('sw_power_cap', 'nvmlClocksThrottleReasonSwPowerCap')]
         reasons = [nm for nm, attr in table if bits & getattr(nv, attr, 0)]
         return {'sm_mhz': float(sm[len(sm) // 2]), 'sm_max_mhz': float(self.max_sm), 'reasons': reasons,
-                'samples': len(sm), 'source': 'nvml'}
+                'samples': len(sm), 'source': 'nvml',
+                'query_ms_mean': float(np.mean(self.query_ms)) if self.query_ms else None}
 
 
 # ---- reference arm / cpu baseline ---------------------------------------------------------------
@@ -213,6 +220,8 @@ def main():
     ap.add_argument('--workload', default='C4', choices=sorted(WORKLOADS))
     ap.add_argument('--ref-blocks', type=int, default=2, help='row blocks (of 50) the CPU reference is timed on')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--clocks', default=os.environ.get('BENCH_CLOCKS', 'nvml'), choices=['nvml', 'none'])
+    ap.add_argument('--profile-host', action='store_true', help='cProfile the timed region (stderr)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -273,15 +282,32 @@ def main():
         roof[what] = design.time_kernel(what, reps=10, flush_l2=False)
 
     sampler = ClockSampler(local_rank)
+    if args.clocks == 'none':
+        sampler.nvml = None
     sampler.start()
+    prof = None
+    if args.profile_host:
+        import cProfile
+        prof = cProfile.Profile()
     barrier()
     ctx.reset_device_ms()
     ctx.reset_launch_count()
+    ncu_range = os.environ.get('BENCH_NCU_RANGE') == '1'      # ncu --profile-from-start off
+    if ncu_range:
+        torch.cuda.profiler.start()
     t0 = time.perf_counter()
+    if prof is not None:
+        prof.enable()
     samples, info2 = bridge.gibbs_resume(info, args.steps)
+    if prof is not None:
+        prof.disable()
+        import pstats
+        pstats.Stats(prof, stream=sys.stderr).sort_stats('cumulative').print_stats(18)
     ctx.sync()
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
+    if ncu_range:
+        torch.cuda.profiler.stop()
     dev_ms = ctx.device_ms()
     launches = ctx.launch_count()
     barrier()
