@@ -58,6 +58,7 @@ extern "C" int bb_destroy(bb_ctx* c) {
         if (f) f(c->nccl_comm);
     }
     if (c->flush_buf) cudaFree(c->flush_buf);
+    for (int i = 0; i < 4; ++i) if (c->scratch[i]) cudaFree(c->scratch[i]);
     if (c->pinned) cudaFreeHost(c->pinned);
     cudaEventDestroy(c->tev0);
     cudaEventDestroy(c->tev1);
@@ -133,6 +134,19 @@ int bb_ctx_pinned(bb_ctx* c, size_t bytes, double** out) {
         c->pinned_bytes = want;
     }
     *out = c->pinned;
+    return BB_OK;
+}
+
+int bb_ctx_scratch(bb_ctx* c, int slot, size_t bytes, void** out) {
+    if (bytes > c->scratch_bytes[slot]) {
+        if (c->scratch[slot]) { cudaStreamSynchronize(c->stream); cudaFree(c->scratch[slot]); }
+        c->scratch[slot] = nullptr;
+        c->scratch_bytes[slot] = 0;
+        size_t want = bytes + bytes / 4 + 4096;
+        BB_CUDA(cudaMalloc(&c->scratch[slot], want));
+        c->scratch_bytes[slot] = want;
+    }
+    *out = c->scratch[slot];
     return BB_OK;
 }
 

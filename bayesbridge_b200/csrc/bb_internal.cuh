@@ -68,6 +68,9 @@ struct bb_ctx {
     // generic host pinned staging
     double* pinned;
     size_t pinned_bytes;
+    // persistent device scratch (grown on demand) so that per-iteration entry points never cudaMalloc/cudaFree
+    void* scratch[4];
+    size_t scratch_bytes[4];
     // device-time accounting of the public entry points (CUDA events on `stream`)
     cudaEvent_t tev0, tev1;
     double dev_ms;
@@ -75,6 +78,7 @@ struct bb_ctx {
 };
 
 int bb_ctx_pinned(bb_ctx* ctx, size_t bytes, double** out);
+int bb_ctx_scratch(bb_ctx* ctx, int slot, size_t bytes, void** out);
 // bracket the device work of one entry point: begin() before the first enqueue, end() after the
 // last enqueue and BEFORE the final stream sync, commit() after that sync.
 struct BBTimer {

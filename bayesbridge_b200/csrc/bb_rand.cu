@@ -282,9 +282,9 @@ extern "C" int bb_pg_sample(bb_ctx* ctx, int64_t n, const int32_t* shape, const 
     BBTimer timer_(ctx);
     cudaStream_t st = ctx->stream;
     int* d_shape = nullptr; double *d_tilt = nullptr, *d_out = nullptr;
-    BB_TRY(scratch_vec(ctx, (void**)&d_shape, (size_t)n * sizeof(int)));
-    BB_TRY(scratch_vec(ctx, (void**)&d_tilt, (size_t)n * sizeof(double)));
-    BB_TRY(scratch_vec(ctx, (void**)&d_out, (size_t)n * sizeof(double)));
+    BB_TRY(bb_ctx_scratch(ctx, 0, (size_t)n * sizeof(int), (void**)&d_shape));
+    BB_TRY(bb_ctx_scratch(ctx, 1, (size_t)n * sizeof(double), (void**)&d_tilt));
+    BB_TRY(bb_ctx_scratch(ctx, 2, (size_t)n * sizeof(double), (void**)&d_out));
     int rc = BB_OK;
     cudaError_t e;
     e = cudaMemcpyAsync(d_shape, shape, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st);
@@ -299,7 +299,6 @@ extern "C" int bb_pg_sample(bb_ctx* ctx, int64_t n, const int32_t* shape, const 
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     timer_.commit();
     if (e != cudaSuccess) { bb_set_error("bb_pg_sample: %s", cudaGetErrorString(e)); rc = BB_ERR_CUDA; }
-    cudaFree(d_shape); cudaFree(d_tilt); cudaFree(d_out);
     return rc;
 }
 
@@ -313,8 +312,8 @@ extern "C" int bb_tilted_stable_sample(bb_ctx* ctx, int64_t n, double char_exp, 
     BBTimer timer_(ctx);
     cudaStream_t st = ctx->stream;
     double *d_tilt = nullptr, *d_out = nullptr;
-    BB_TRY(scratch_vec(ctx, (void**)&d_tilt, (size_t)n * sizeof(double)));
-    BB_TRY(scratch_vec(ctx, (void**)&d_out, (size_t)n * sizeof(double)));
+    BB_TRY(bb_ctx_scratch(ctx, 1, (size_t)n * sizeof(double), (void**)&d_tilt));
+    BB_TRY(bb_ctx_scratch(ctx, 2, (size_t)n * sizeof(double), (void**)&d_out));
     int rc = BB_OK;
     cudaError_t e = cudaMemcpyAsync(d_tilt, tilt, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) {
@@ -327,7 +326,6 @@ extern "C" int bb_tilted_stable_sample(bb_ctx* ctx, int64_t n, double char_exp, 
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     timer_.commit();
     if (e != cudaSuccess) { bb_set_error("bb_tilted_stable_sample: %s", cudaGetErrorString(e)); rc = BB_ERR_CUDA; }
-    cudaFree(d_tilt); cudaFree(d_out);
     return rc;
 }
 
@@ -338,13 +336,12 @@ extern "C" int bb_philox_normal(bb_ctx* ctx, int64_t n, int stream, uint64_t see
     BB_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     double* d_out = nullptr;
-    BB_TRY(scratch_vec(ctx, (void**)&d_out, (size_t)n * sizeof(double)));
+    BB_TRY(bb_ctx_scratch(ctx, 2, (size_t)n * sizeof(double), (void**)&d_out));
     k_philox_normal<<<(int)((n + 255) / 256), 256, 0, st>>>(n, stream, seed, offset, index_offset, d_out);
     ctx->launches++;
     cudaError_t e = cudaPeekAtLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaFree(d_out);
     if (e != cudaSuccess) { bb_set_error("bb_philox_normal: %s", cudaGetErrorString(e)); return BB_ERR_CUDA; }
     return BB_OK;
 }
@@ -423,7 +420,7 @@ extern "C" int bb_pg_from_coef(bb_mat* m, const double* coef, uint64_t seed, uin
     if (nblk < 1) nblk = 1;
     // partial log-likelihoods: one per block; collapse in passes of RED_MAX
     double* red_ll = nullptr;
-    BB_CUDA(cudaMalloc((void**)&red_ll, (size_t)nblk * sizeof(double)));
+    BB_TRY(bb_ctx_scratch(ctx, 3, (size_t)nblk * sizeof(double), (void**)&red_ll));
     k_pg_loglik<<<(int)nblk, TB, 0, st>>>(m->n, m->n_trial, m->n_success, m->eta, seed, offset, m->row_offset, m->omega, red_ll);
     ctx->launches++;
     m->use_omega_scalar = 0;
@@ -437,7 +434,6 @@ extern "C" int bb_pg_from_coef(bb_mat* m, const double* coef, uint64_t seed, uin
     timer_.end();
     cudaError_t e = cudaStreamSynchronize(st);
     timer_.commit();
-    cudaFree(red_ll);
     if (e != cudaSuccess) { bb_set_error("bb_pg_from_coef: %s", cudaGetErrorString(e)); return BB_ERR_CUDA; }
     if (loglik) *loglik = ll;
     return BB_OK;

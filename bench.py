@@ -281,6 +281,15 @@ def main():
     for what in ('spmv_dot', 'spmv_tdot'):
         roof[what] = design.time_kernel(what, reps=10, flush_l2=False)
 
+    # the same kernel on the 12 B/nnz layout (fp64 values + int32 indices) of the same matrix: the format
+    # SURVEY section 8d's byte formulas are written for; measured here so both fractions are on record
+    valued = {}
+    if world == 1:
+        Dv = GpuSparseDesignMatrix(X, center_predictor=True, add_intercept=True, ctx=ctx, pattern_only=False)
+        for what in ('spmv_dot', 'spmv_tdot'):
+            valued[what] = Dv.time_kernel(what, reps=10, flush_l2=False)
+        del Dv
+
     sampler = ClockSampler(local_rank)
     if args.clocks == 'none':
         sampler.nvml = None
@@ -363,6 +372,10 @@ def main():
             'ms_per_launch': roof[dom],
             'other': {'spmv_dot_ms': roof['spmv_dot'], 'spmv_dot_GBs': b_dot / (roof['spmv_dot'] * 1e-3) / 1e9,
                       'spmv_tdot_ms': roof['spmv_tdot'], 'spmv_tdot_GBs': b_tdot / (roof['spmv_tdot'] * 1e-3) / 1e9},
+            'valued_format_12B_per_nnz': {
+                what: {'ms': ms, 'GBs': ((b_dot if what == 'spmv_dot' else b_tdot) + 8 * nnz_local) / (ms * 1e-3) / 1e9,
+                       'frac': ((b_dot if what == 'spmv_dot' else b_tdot) + 8 * nnz_local) / (ms * 1e-3) / 1e9 / peak}
+                for what, ms in valued.items()},
         },
     }
     if world == 1 and not args.no_cpu_baseline:
