@@ -409,18 +409,36 @@ __global__ void k_sum_partials(const double* __restrict__ w, i64 n, double* __re
 }
 
 // traw[0] = sum of the w partials; traw[1+j] = sum_r part[r*p+j]
-__global__ void k_tdot_collect(const double* __restrict__ part, int nslab, i64 p,
-                               const double* __restrict__ red_w, int nred, double* __restrict__ traw,
-                               const int* __restrict__ done_flag) {
+// Block = 32 columns x 8 slab groups: each thread sums slabs r = gy, gy+8, ... (independent loads in flight),
+// then the 8 partial sums of a column are added in fixed order through shared memory.
+__global__ void __launch_bounds__(256)
+k_tdot_collect(const double* __restrict__ part, int nslab, i64 p,
+               const double* __restrict__ red_w, int nred, double* __restrict__ traw,
+               const int* __restrict__ done_flag) {
     if (done_flag != nullptr && *done_flag) return;
+    __shared__ double sm[8][33];
     if (blockIdx.x == 0 && threadIdx.x < 32) {
         double s = warp_sum_partials(red_w, nred);
         if (threadIdx.x == 0) traw[0] = s;
     }
-    for (i64 j = (i64)blockIdx.x * blockDim.x + threadIdx.x; j < p; j += (i64)gridDim.x * blockDim.x) {
-        double t = 0.0;
-        for (int r = 0; r < nslab; ++r) t += part[(i64)r * p + j];
-        traw[1 + j] = t;
+    const int cx = threadIdx.x & 31, gy = threadIdx.x >> 5;
+    for (i64 j0 = (i64)blockIdx.x * 32; j0 < p; j0 += (i64)gridDim.x * 32) {
+        const i64 j = j0 + cx;
+        double t0 = 0.0, t1 = 0.0;
+        if (j < p) {
+            int r = gy;
+            for (; r + 8 < nslab; r += 16) { t0 += part[(i64)r * p + j]; t1 += part[(i64)(r + 8) * p + j]; }
+            if (r < nslab) t0 += part[(i64)r * p + j];
+        }
+        sm[gy][cx] = t0 + t1;
+        __syncthreads();
+        if (gy == 0 && j < p) {
+            double t = sm[0][cx];
+#pragma unroll
+            for (int g = 1; g < 8; ++g) t += sm[g][cx];
+            traw[1 + j] = t;
+        }
+        __syncthreads();
     }
 }
 
@@ -737,12 +755,12 @@ int bb_op_tdot_flag(bb_mat* m, const double* w, bool have_w_partials, const int*
     }
     if (!m->is_sparse) {
         BB_TRY(bb_dense_tdot(m, w, done_flag));
-        k_tdot_collect<<<grid_for(m->p, 1024, RED_MAX), 256, 0, ctx->stream>>>(
+        k_tdot_collect<<<grid_for(m->p, 32, 4096), 256, 0, ctx->stream>>>(
             m->dense_part, m->dense_nblk, m->p, m->red + RED_W * RED_MAX, m->nred_w, m->traw, done_flag);
         BB_LAUNCHED(ctx);
     } else {
         BB_TRY(bb_launch_spmv(m, &m->ftdot, w, done_flag));
-        k_tdot_collect<<<grid_for(m->p, 1024, RED_MAX), 256, 0, ctx->stream>>>(
+        k_tdot_collect<<<grid_for(m->p, 32, 4096), 256, 0, ctx->stream>>>(
             m->ftdot.part, m->ftdot.nslab, m->p, m->red + RED_W * RED_MAX, m->nred_w, m->traw, done_flag);
         BB_LAUNCHED(ctx);
     }
