@@ -34,6 +34,9 @@ SIGNATURES = {
     'bb_comm_unique_id': (c_int, [c_char_p, ctypes.c_char_p]),
     'bb_comm_init': (c_int, [c_void_p, c_char_p, c_int, c_int, c_char_p]),
     'bb_comm_allreduce_host': (c_int, [c_void_p, P_dbl, c_i64]),
+    'bb_comm_p2p_export': (c_int, [c_void_p, c_i64, ctypes.c_char_p]),
+    'bb_comm_p2p_attach': (c_int, [c_void_p, ctypes.c_char_p]),
+    'bb_comm_p2p_status': (c_int, [c_void_p, P_int, P_int]),
     'bb_csr_upload': (c_int, [c_void_p, c_i64, c_i64, c_i64, P_i32, P_i32, P_dbl, P_dbl, c_int, c_i64, c_i64,
                               ctypes.POINTER(c_void_p)]),
     'bb_dense_upload': (c_int, [c_void_p, c_i64, c_i64, P_dbl, P_dbl, c_int, c_i64, c_i64, ctypes.POINTER(c_void_p)]),
@@ -185,6 +188,31 @@ class Context:
         dist.broadcast_object_list(box, src=0)
         check(lib.bb_comm_init(self.handle, path, world, rank, box[0]))
         self.nranks, self.rank = world, rank
+
+    def init_p2p(self, capacity):
+        """Map every rank's exchange buffer into every other rank (CUDA IPC over NVLink) so that the
+        all-reduces of vectors of <= `capacity` doubles run as libbbgpu's own one-shot peer-memory kernels
+        instead of ncclAllReduce. Collective: every rank must call it. torch.distributed only carries the
+        64-byte IPC handles."""
+        import torch.distributed as dist
+        if self.nranks == 1 or getattr(self, 'p2p_capacity', 0) >= capacity:
+            return
+        if getattr(self, 'p2p_capacity', 0) > 0:
+            return      # already attached with a smaller capacity: larger vectors fall back to NCCL
+        if os.environ.get('BB_ALLREDUCE', 'p2p') == 'nccl':
+            return
+        lib = load()
+        buf = ctypes.create_string_buffer(64)
+        check(lib.bb_comm_p2p_export(self.handle, int(capacity), buf))
+        handles = [None] * self.nranks
+        dist.all_gather_object(handles, bytes(buf.raw))
+        check(lib.bb_comm_p2p_attach(self.handle, b''.join(handles)))
+        self.p2p_capacity = int(capacity)
+
+    def p2p_status(self):
+        ready, err = c_int(), c_int()
+        check(load().bb_comm_p2p_status(self.handle, ctypes.byref(ready), ctypes.byref(err)))
+        return bool(ready.value), int(err.value)
 
     def allreduce_host(self, arr):
         arr = as_f64(arr)

@@ -41,6 +41,7 @@ extern "C" int bb_init(int device, bb_ctx** out) {
     c->opt_slab_width = 0;
     c->opt_cg_chunk = 0;
     c->opt_use_graph = 1;
+    c->opt_allreduce_p2p = 1;
     c->nranks = 1;
     c->rank = 0;
     BB_CUDA(cudaEventCreate(&c->tev0));
@@ -52,6 +53,7 @@ extern "C" int bb_init(int device, bb_ctx** out) {
 extern "C" int bb_destroy(bb_ctx* c) {
     if (!c) return BB_OK;
     cudaSetDevice(c->device);
+    bb_p2p_free(c);
     if (c->nccl_comm && c->nccl_handle) {
         typedef int (*destroy_t)(void*);
         destroy_t f = (destroy_t)dlsym(c->nccl_handle, "ncclCommDestroy");
@@ -78,6 +80,7 @@ static i64* option_slot(bb_ctx* c, const char* name) {
     if (!strcmp(name, "slab_width")) return &c->opt_slab_width;
     if (!strcmp(name, "cg_chunk")) return &c->opt_cg_chunk;
     if (!strcmp(name, "use_graph")) return &c->opt_use_graph;
+    if (!strcmp(name, "allreduce_p2p")) return &c->opt_allreduce_p2p;
     return nullptr;
 }
 
@@ -206,6 +209,10 @@ extern "C" int bb_comm_init(bb_ctx* c, const char* nccl_lib_path, int nranks, in
 
 int bb_allreduce_dev(bb_ctx* c, double* dbuf, i64 count) {
     if (c->nranks == 1) return BB_OK;
+    {
+        int rc = BB_OK;
+        if (bb_p2p_allreduce(c, dbuf, count, nullptr, &rc)) return rc;
+    }
     if (!c->nccl_comm) { bb_set_error("communicator not initialised"); return BB_ERR_STATE; }
     static nccl_allreduce_t f = nullptr;
     if (!f) f = (nccl_allreduce_t)dlsym(c->nccl_handle, "ncclAllReduce");

@@ -62,6 +62,10 @@ struct bb_ctx {
     void* nccl_handle;
     void* nccl_comm;
     int nranks, rank;
+    // one-shot all-reduce over NVLink peer memory (bb_p2p.cu)
+    void* p2p;
+    int p2p_ready;
+    i64 opt_allreduce_p2p;   // 1: use it when attached (default), 0: always NCCL
     // L2 flush scratch for bb_time_kernel
     void* flush_buf;
     size_t flush_bytes;
@@ -93,6 +97,8 @@ struct BBTimer {
     ~BBTimer() { c->timer_depth--; }
 };
 int bb_allreduce_dev(bb_ctx* ctx, double* dbuf, i64 count);   // in place, on ctx->stream
+bool bb_p2p_allreduce(bb_ctx* c, double* dbuf, i64 count, const int* done_flag, int* rc_out);
+int bb_p2p_free(bb_ctx* c);
 
 // ------------------------------------------------------------------------------------------
 // Slab format: the nnz of a compressed (CSR or CSC) matrix regrouped so that every contiguous

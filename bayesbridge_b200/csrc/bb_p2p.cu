@@ -1,0 +1,183 @@
+// One-shot all-reduce over NVLink peer memory (no NCCL on the hot path).
+//
+// Every rank owns one cudaMalloc'ed exchange buffer that the other ranks of the box map through CUDA IPC:
+//     [ flags: nranks x u64, padded to 256 B ][ slot 0: cap doubles ][ slot 1: cap doubles ]
+// A reduction of `count` doubles is two kernels on the library stream:
+//   publish : copy the local partial vector into slot (seq & 1); the LAST block to finish makes the data visible
+//             system-wide and stores seq+1 into flags[my_rank] of EVERY peer (st.release.sys over NVLink);
+//   reduce  : one thread per block spins until all nranks flags in the local buffer have reached seq+1
+//             (ld.acquire.sys), then every thread sums the nranks partials in RANK ORDER with uncached peer loads
+//             -> the result is bit-identical on every rank, which is what keeps the replicated CG recurrences
+//             (and the stopping decision) in lock-step without any further exchange.
+// Two slots are enough: a rank can only start publication k+2 after it has consumed publication k+1, which every
+// peer has published only after it finished reading publication k.  The spin has an iteration cap: a lost peer
+// raises an error flag instead of hanging the GPU.
+#include "bb_internal.cuh"
+#include <stdlib.h>
+
+struct P2PState {
+    unsigned long long seq;        // publications completed by this rank
+    unsigned int blocks_done;      // publish: block counter
+    unsigned int error;            // set when a wait timed out
+};
+
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void k_p2p_publish(const double* __restrict__ src, i64 count, i64 cap, int nranks, int rank,
+                              double* const* __restrict__ peer_base, P2PState* st, const int* __restrict__ done_flag) {
+    if (done_flag != nullptr && *done_flag) return;
+    const unsigned long long seq = st->seq;
+    double* slot = peer_base[rank] + 32 + (seq & 1ull) * cap;      // 32 doubles = 256 B of flags
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (i64)gridDim.x * blockDim.x) slot[i] = src[i];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int prev = atomicAdd(&st->blocks_done, 1u);
+        if (prev == gridDim.x - 1) {                                // last block: everything is written
+            st->blocks_done = 0u;
+            __threadfence_system();
+            for (int q = 0; q < nranks; ++q) {
+                unsigned long long* f = reinterpret_cast<unsigned long long*>(peer_base[q]) + rank;
+                st_release_sys_u64(f, seq + 1ull);
+            }
+            st->seq = seq + 1ull;
+        }
+    }
+}
+
+__global__ void k_p2p_reduce(double* __restrict__ dst, i64 count, i64 cap, int nranks, int rank,
+                             double* const* __restrict__ peer_base, P2PState* st, const int* __restrict__ done_flag) {
+    if (done_flag != nullptr && *done_flag) return;
+    __shared__ int ok;
+    const unsigned long long want = st->seq;                        // publish already advanced it
+    if (threadIdx.x == 0) {
+        const unsigned long long* flags = reinterpret_cast<const unsigned long long*>(peer_base[rank]);
+        int good = 1;
+        for (int q = 0; q < nranks && good; ++q) {
+            unsigned long long spins = 0;
+            while (ld_acquire_sys_u64(flags + q) < want) {
+                if (++spins > (1ull << 26)) { good = 0; st->error = 1u; break; }
+                __nanosleep(20);
+            }
+        }
+        ok = good;
+    }
+    __syncthreads();
+    if (!ok) return;
+    const i64 off = 32 + ((want - 1ull) & 1ull) * cap;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (i64)gridDim.x * blockDim.x) {
+        double acc = 0.0;
+        for (int q = 0; q < nranks; ++q) acc += __ldcv(peer_base[q] + off + i);
+        dst[i] = acc;
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+struct bb_p2p {
+    double* own;                 // exchange buffer of this rank
+    double** peers_host;         // mapped base pointers (own for self)
+    double** peers_dev;
+    P2PState* state;
+    i64 cap;
+    int nranks, rank;
+};
+
+extern "C" int bb_comm_p2p_export(bb_ctx* c, int64_t capacity, char* handle_out_64) {
+    BB_ARG(c && handle_out_64 && capacity > 0, "ctx/handle/capacity");
+    BB_ARG(c->nranks > 1, "bb_comm_init first");
+    BB_CUDA(cudaSetDevice(c->device));
+    if (c->p2p) { bb_set_error("p2p exchange already initialised"); return BB_ERR_STATE; }
+    bb_p2p* p = (bb_p2p*)calloc(1, sizeof(bb_p2p));
+    p->cap = (capacity + 31) & ~(i64)31;
+    p->nranks = c->nranks;
+    p->rank = c->rank;
+    size_t bytes = (size_t)(32 + 2 * p->cap) * sizeof(double);
+    BB_CUDA(cudaMalloc((void**)&p->own, bytes));
+    BB_CUDA(cudaMemset(p->own, 0, bytes));
+    BB_CUDA(cudaMalloc((void**)&p->state, sizeof(P2PState)));
+    BB_CUDA(cudaMemset(p->state, 0, sizeof(P2PState)));
+    BB_CUDA(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    BB_CUDA(cudaIpcGetMemHandle(&h, p->own));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    memcpy(handle_out_64, &h, 64);
+    c->p2p = p;
+    return BB_OK;
+}
+
+extern "C" int bb_comm_p2p_attach(bb_ctx* c, const char* handles_nranks_x_64) {
+    BB_ARG(c && handles_nranks_x_64, "ctx/handles");
+    bb_p2p* p = (bb_p2p*)c->p2p;
+    BB_ARG(p != nullptr, "bb_comm_p2p_export first");
+    BB_CUDA(cudaSetDevice(c->device));
+    p->peers_host = (double**)calloc((size_t)p->nranks, sizeof(double*));
+    for (int q = 0; q < p->nranks; ++q) {
+        if (q == p->rank) { p->peers_host[q] = p->own; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles_nranks_x_64 + 64 * q, 64);
+        void* ptr = nullptr;
+        BB_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        p->peers_host[q] = (double*)ptr;
+    }
+    BB_CUDA(cudaMalloc((void**)&p->peers_dev, (size_t)p->nranks * sizeof(double*)));
+    BB_CUDA(cudaMemcpy(p->peers_dev, p->peers_host, (size_t)p->nranks * sizeof(double*), cudaMemcpyHostToDevice));
+    c->p2p_ready = 1;
+    return BB_OK;
+}
+
+int bb_p2p_free(bb_ctx* c) {
+    bb_p2p* p = (bb_p2p*)c->p2p;
+    if (!p) return BB_OK;
+    if (p->peers_host) {
+        for (int q = 0; q < p->nranks; ++q)
+            if (q != p->rank && p->peers_host[q]) cudaIpcCloseMemHandle(p->peers_host[q]);
+        free(p->peers_host);
+    }
+    if (p->peers_dev) cudaFree(p->peers_dev);
+    if (p->state) cudaFree(p->state);
+    if (p->own) cudaFree(p->own);
+    free(p);
+    c->p2p = nullptr;
+    c->p2p_ready = 0;
+    return BB_OK;
+}
+
+// in-place sum over ranks of dbuf[0..count) on ctx->stream; false => caller falls back to NCCL
+bool bb_p2p_allreduce(bb_ctx* c, double* dbuf, i64 count, const int* done_flag, int* rc_out) {
+    bb_p2p* p = (bb_p2p*)c->p2p;
+    *rc_out = BB_OK;
+    if (!p || !c->p2p_ready || c->opt_allreduce_p2p == 0 || count > p->cap) return false;
+    i64 g = (count + 1023) / 1024;
+    if (g < 1) g = 1;
+    if (g > 64) g = 64;
+    k_p2p_publish<<<(int)g, 256, 0, c->stream>>>(dbuf, count, p->cap, p->nranks, p->rank, p->peers_dev, p->state, done_flag);
+    k_p2p_reduce<<<(int)g, 256, 0, c->stream>>>(dbuf, count, p->cap, p->nranks, p->rank, p->peers_dev, p->state, done_flag);
+    c->launches += 2;
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) { bb_set_error("p2p allreduce launch: %s", cudaGetErrorString(e)); *rc_out = BB_ERR_CUDA; }
+    return true;
+}
+
+extern "C" int bb_comm_p2p_status(bb_ctx* c, int* ready, int* error) {
+    BB_ARG(c != nullptr, "ctx");
+    bb_p2p* p = (bb_p2p*)c->p2p;
+    if (ready) *ready = (p && c->p2p_ready) ? 1 : 0;
+    if (error) {
+        *error = 0;
+        if (p && p->state) {
+            P2PState h;
+            BB_CUDA(cudaSetDevice(c->device));
+            BB_CUDA(cudaStreamSynchronize(c->stream));
+            BB_CUDA(cudaMemcpy(&h, p->state, sizeof(P2PState), cudaMemcpyDeviceToHost));
+            *error = (int)h.error;
+        }
+    }
+    return BB_OK;
+}

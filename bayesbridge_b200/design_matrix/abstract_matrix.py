@@ -155,6 +155,8 @@ class AbstractDesignMatrix(abc.ABC):
             tot = self.ctx.allreduce_host(np.array([P, P * P]))
             if tot[0] != self.ctx.nranks * P or tot[1] != self.ctx.nranks * P * P:
                 raise ValueError("Row shards disagree on the number of predictors.")
+            # (p+1)-vectors are the per-CG-iteration exchange: give them the peer-memory all-reduce
+            self.ctx.init_p2p(int(P) + 64)
 
     @staticmethod
     def shard_rows(n, ctx):

@@ -65,6 +65,12 @@ int  bb_sync(bb_ctx* ctx);
 int  bb_comm_unique_id(const char* nccl_lib_path, char* id_out_128);
 int  bb_comm_init(bb_ctx* ctx, const char* nccl_lib_path, int nranks, int rank, const char* id_128);
 int  bb_comm_allreduce_host(bb_ctx* ctx, double* buf, int64_t count);  /* in-place sum, host buffer */
+/* one-shot all-reduce over NVLink peer memory (replaces ncclAllReduce for vectors of <= capacity doubles):
+ * every rank exports its exchange buffer (64-byte CUDA IPC handle), the handles are gathered by the caller
+ * (any transport) and attached; option "allreduce_p2p" = 0 switches back to NCCL. */
+int  bb_comm_p2p_export(bb_ctx* ctx, int64_t capacity, char* handle_out_64);
+int  bb_comm_p2p_attach(bb_ctx* ctx, const char* handles_nranks_x_64);
+int  bb_comm_p2p_status(bb_ctx* ctx, int* ready, int* error);
 
 /* ---- design matrix (seam 1) ------------------------------------------------------------- */
 /* CSR shard [n_local x p]; data==NULL => pattern-only (all stored values are 1.0).
