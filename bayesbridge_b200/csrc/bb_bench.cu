@@ -53,7 +53,7 @@ extern "C" int bb_time_kernel(bb_mat* m, const char* what, int reps, int do_flus
         } else if (kind == 2) {
             BB_TRY(bb_op_prepare(m, m->v_P, nullptr));
             BB_TRY(bb_op_dot(m, 1));
-            BB_TRY(bb_op_tdot_flag(m, m->w_n, true, nullptr));
+            BB_TRY(bb_op_tdot_flag(m, m->w_n, true, nullptr, false));
         } else if (kind == 3) {
             BB_TRY(bb_launch_spmv(m, &m->fdot, m->v_P + m->add_intercept, nullptr));
         } else {

@@ -76,15 +76,31 @@ __global__ void k_cg_scalars(CgScalars* st, const double* __restrict__ red_bb, i
     }
 }
 
-// q = D.p + s.Tdot ; partial p.q ; bumps the iteration counter when count_iter
+// q = D.p + s.Tdot ; partial p.q ; bumps the iteration counter when count_iter.
+// With a peer-memory exchange (pub != nullptr) the all-reduce of [sum w; X'w] is done HERE: the block waits for
+// every rank's publication and each thread sums the ranks' partials in rank order (compute + collective fused).
 __global__ void k_cg_q(CgScalars* st, const double* __restrict__ traw, const double* __restrict__ c, int icpt, i64 P,
                        const double* __restrict__ pvec, const double* __restrict__ s, const double* __restrict__ D,
-                       double* __restrict__ q, double* __restrict__ red_pq, int count_iter) {
+                       double* __restrict__ q, double* __restrict__ red_pq, int count_iter,
+                       const P2PView* __restrict__ pub_ptr) {
     if (st->done) return;
     __shared__ double sm[33];
+    __shared__ int p2p_ok;
+    P2PView pub;
+    double sw = 0.0;
+    if (pub_ptr != nullptr) {
+        pub = *pub_ptr;
+        if (!p2p_wait_all(pub, &p2p_ok)) return;
+        sw = p2p_sum(pub, 0);
+    }
     double acc = 0.0;
     for (i64 j = (i64)blockIdx.x * blockDim.x + threadIdx.x; j < P; j += (i64)gridDim.x * blockDim.x) {
-        double t = tdot_entry(traw, c, j, icpt);
+        double t;
+        if (pub_ptr != nullptr) {
+            t = (j < icpt) ? sw : __dsub_rn(p2p_sum(pub, 1 + (j - icpt)), __dmul_rn(sw, c[j - icpt]));
+        } else {
+            t = tdot_entry(traw, c, j, icpt);
+        }
         double pj = pvec[j];
         double qj = __dadd_rn(__dmul_rn(D[j], pj), __dmul_rn(s[j], t));
         q[j] = qj;
@@ -178,9 +194,12 @@ static int apply_operator(bb_mat* m, const double* vP, int count_iter) {
     bb_ctx* ctx = m->ctx;
     const int* done = &m->cg->done;
     BB_TRY(bb_op_dot_flag(m, 1, done));
-    BB_TRY(bb_op_tdot_flag(m, m->w_n, true, done));
+    P2PView view;
+    const bool p2p = (ctx->nranks > 1) && bb_p2p_view(ctx, m->p + 1, &view);
+    BB_TRY(bb_op_tdot_flag(m, m->w_n, true, done, /*fuse_reduce_into_consumer=*/p2p));
     k_cg_q<<<P_grid(m->P), 256, 0, ctx->stream>>>(m->cg, m->traw, m->col_offset, m->add_intercept, m->P, vP, m->s, m->D,
-                                                  m->q, m->red + RED_PQ * RED_MAX, count_iter);
+                                                  m->q, m->red + RED_PQ * RED_MAX, count_iter,
+                                                  p2p ? m->p2p_view_dev : nullptr);
     BB_LAUNCHED(ctx);
     return BB_OK;
 }

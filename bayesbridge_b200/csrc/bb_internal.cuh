@@ -46,6 +46,19 @@ void bb_set_error(const char* fmt, ...);
         }                                                                                  \
     } while (0)
 
+// peer-memory exchange state (see bb_p2p.cu)
+struct P2PState {
+    unsigned long long seq;        // publications completed by this rank
+    unsigned int blocks_done;      // publish: block counter
+    unsigned int error;            // set when a wait timed out
+};
+struct P2PView {
+    double* const* peer_base;      // [nranks] mapped exchange buffers (device array)
+    P2PState* st;
+    i64 cap;
+    int nranks, rank;
+};
+
 // ------------------------------------------------------------------------------------------
 struct bb_ctx {
     int device;
@@ -99,6 +112,8 @@ struct BBTimer {
 int bb_allreduce_dev(bb_ctx* ctx, double* dbuf, i64 count);   // in place, on ctx->stream
 bool bb_p2p_allreduce(bb_ctx* c, double* dbuf, i64 count, const int* done_flag, int* rc_out);
 int bb_p2p_free(bb_ctx* c);
+bool bb_p2p_view(bb_ctx* c, i64 count, P2PView* out);          // true when the exchange can carry `count` doubles
+int bb_p2p_reduce_into(bb_ctx* c, double* dst, i64 count);      // wait + rank-ordered sum of the last publication
 
 // ------------------------------------------------------------------------------------------
 // Slab format: the nnz of a compressed (CSR or CSC) matrix regrouped so that every contiguous
@@ -157,6 +172,8 @@ struct bb_mat {
     int has_outcome, is_linear;
     double omega_scalar; int use_omega_scalar;   // linear model: omega = scalar * 1_n
     double* omega_scalar_dev;                    // device copy: kernels inside the captured CG graph read it here
+    P2PView* p2p_view_dev;                       // device copy of the exchange view (kernel argument by pointer)
+    int p2p_view_valid;
     // P-vectors
     double *v_P, *sv, *traw /*[1+p]*/, *t_P, *x, *r, *pvec, *q, *b, *s, *D, *pps, *z, *x0, *eps_P, *out_P;
     // reduction scratch
@@ -187,7 +204,8 @@ int bb_op_tdot_finish(bb_mat* m, double* tP);
 
 int bb_op_prepare_flag(bb_mat* m, const double* vP, const double* scale, const int* done_flag);
 int bb_op_dot_flag(bb_mat* m, int mode, const int* done_flag);
-int bb_op_tdot_flag(bb_mat* m, const double* w, bool have_w_partials, const int* done_flag);
+int bb_op_tdot_flag(bb_mat* m, const double* w, bool have_w_partials, const int* done_flag,
+                    bool fuse_reduce_into_consumer = false);
 int bb_mat_alloc_work(bb_mat* m);
 
 int bb_slab_free(SlabFmt* f);
@@ -289,5 +307,60 @@ struct RandStream {
 };
 
 enum { STREAM_EPS1 = 0, STREAM_EPS2 = 1, STREAM_PG = 2, STREAM_TS = 3 };
+
+// ---- peer-memory exchange (bb_p2p.cu): device-side protocol pieces, usable from any kernel ----
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// slot this rank writes its next publication into (call before any thread of the grid can have advanced seq)
+__device__ __forceinline__ double* p2p_publish_slot(const P2PView& v) {
+    return v.peer_base[v.rank] + 32 + (v.st->seq & 1ull) * v.cap;
+}
+// to be called by every block after its last store into the slot: the last block to arrive signals all peers
+__device__ __forceinline__ void p2p_publish_done(const P2PView& v) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned long long seq = v.st->seq;
+        unsigned int prev = atomicAdd(&v.st->blocks_done, 1u);
+        if (prev == gridDim.x * gridDim.y - 1) {
+            v.st->blocks_done = 0u;
+            __threadfence_system();
+            for (int q = 0; q < v.nranks; ++q)
+                st_release_sys_u64(reinterpret_cast<unsigned long long*>(v.peer_base[q]) + v.rank, seq + 1ull);
+            v.st->seq = seq + 1ull;
+        }
+    }
+}
+// block-wide wait until every rank has published number st->seq; returns false after a time-out
+__device__ __forceinline__ bool p2p_wait_all(const P2PView& v, int* sm_flag) {
+    const unsigned long long want = v.st->seq;
+    if (threadIdx.x == 0) {
+        const unsigned long long* flags = reinterpret_cast<const unsigned long long*>(v.peer_base[v.rank]);
+        int good = 1;
+        for (int q = 0; q < v.nranks && good; ++q) {
+            unsigned long long spins = 0;
+            while (ld_acquire_sys_u64(flags + q) < want) {
+                if (++spins > (1ull << 26)) { good = 0; v.st->error = 1u; break; }
+                __nanosleep(20);
+            }
+        }
+        *sm_flag = good;
+    }
+    __syncthreads();
+    return *sm_flag != 0;
+}
+// element i of the published vectors summed over ranks in rank order (identical bits on every rank)
+__device__ __forceinline__ double p2p_sum(const P2PView& v, i64 i) {
+    const i64 off = 32 + ((v.st->seq - 1ull) & 1ull) * v.cap + i;
+    double acc = 0.0;
+    for (int q = 0; q < v.nranks; ++q) acc += __ldcv(v.peer_base[q] + off);
+    return acc;
+}
 
 #endif  // __CUDACC__

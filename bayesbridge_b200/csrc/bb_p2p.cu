@@ -15,68 +15,17 @@
 #include "bb_internal.cuh"
 #include <stdlib.h>
 
-struct P2PState {
-    unsigned long long seq;        // publications completed by this rank
-    unsigned int blocks_done;      // publish: block counter
-    unsigned int error;            // set when a wait timed out
-};
-
-__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-
-__global__ void k_p2p_publish(const double* __restrict__ src, i64 count, i64 cap, int nranks, int rank,
-                              double* const* __restrict__ peer_base, P2PState* st, const int* __restrict__ done_flag) {
-    if (done_flag != nullptr && *done_flag) return;
-    const unsigned long long seq = st->seq;
-    double* slot = peer_base[rank] + 32 + (seq & 1ull) * cap;      // 32 doubles = 256 B of flags
+__global__ void k_p2p_publish(const double* __restrict__ src, i64 count, P2PView v) {
+    double* slot = p2p_publish_slot(v);
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (i64)gridDim.x * blockDim.x) slot[i] = src[i];
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned int prev = atomicAdd(&st->blocks_done, 1u);
-        if (prev == gridDim.x - 1) {                                // last block: everything is written
-            st->blocks_done = 0u;
-            __threadfence_system();
-            for (int q = 0; q < nranks; ++q) {
-                unsigned long long* f = reinterpret_cast<unsigned long long*>(peer_base[q]) + rank;
-                st_release_sys_u64(f, seq + 1ull);
-            }
-            st->seq = seq + 1ull;
-        }
-    }
+    p2p_publish_done(v);
 }
 
-__global__ void k_p2p_reduce(double* __restrict__ dst, i64 count, i64 cap, int nranks, int rank,
-                             double* const* __restrict__ peer_base, P2PState* st, const int* __restrict__ done_flag) {
-    if (done_flag != nullptr && *done_flag) return;
+__global__ void k_p2p_reduce(double* __restrict__ dst, i64 count, P2PView v) {
     __shared__ int ok;
-    const unsigned long long want = st->seq;                        // publish already advanced it
-    if (threadIdx.x == 0) {
-        const unsigned long long* flags = reinterpret_cast<const unsigned long long*>(peer_base[rank]);
-        int good = 1;
-        for (int q = 0; q < nranks && good; ++q) {
-            unsigned long long spins = 0;
-            while (ld_acquire_sys_u64(flags + q) < want) {
-                if (++spins > (1ull << 26)) { good = 0; st->error = 1u; break; }
-                __nanosleep(20);
-            }
-        }
-        ok = good;
-    }
-    __syncthreads();
-    if (!ok) return;
-    const i64 off = 32 + ((want - 1ull) & 1ull) * cap;
-    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (i64)gridDim.x * blockDim.x) {
-        double acc = 0.0;
-        for (int q = 0; q < nranks; ++q) acc += __ldcv(peer_base[q] + off + i);
-        dst[i] = acc;
-    }
+    if (!p2p_wait_all(v, &ok)) return;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (i64)gridDim.x * blockDim.x)
+        dst[i] = p2p_sum(v, i);
 }
 
 // ---- host side ------------------------------------------------------------------------------------
@@ -149,16 +98,40 @@ int bb_p2p_free(bb_ctx* c) {
     return BB_OK;
 }
 
-// in-place sum over ranks of dbuf[0..count) on ctx->stream; false => caller falls back to NCCL
-bool bb_p2p_allreduce(bb_ctx* c, double* dbuf, i64 count, const int* done_flag, int* rc_out) {
+bool bb_p2p_view(bb_ctx* c, i64 count, P2PView* out) {
     bb_p2p* p = (bb_p2p*)c->p2p;
-    *rc_out = BB_OK;
     if (!p || !c->p2p_ready || c->opt_allreduce_p2p == 0 || count > p->cap) return false;
+    out->peer_base = p->peers_dev;
+    out->st = p->state;
+    out->cap = p->cap;
+    out->nranks = p->nranks;
+    out->rank = p->rank;
+    return true;
+}
+
+static int reduce_grid(i64 count) {
     i64 g = (count + 1023) / 1024;
     if (g < 1) g = 1;
     if (g > 64) g = 64;
-    k_p2p_publish<<<(int)g, 256, 0, c->stream>>>(dbuf, count, p->cap, p->nranks, p->rank, p->peers_dev, p->state, done_flag);
-    k_p2p_reduce<<<(int)g, 256, 0, c->stream>>>(dbuf, count, p->cap, p->nranks, p->rank, p->peers_dev, p->state, done_flag);
+    return (int)g;
+}
+
+int bb_p2p_reduce_into(bb_ctx* c, double* dst, i64 count) {
+    P2PView v;
+    if (!bb_p2p_view(c, count, &v)) { bb_set_error("p2p exchange not available"); return BB_ERR_STATE; }
+    k_p2p_reduce<<<reduce_grid(count), 256, 0, c->stream>>>(dst, count, v);
+    BB_LAUNCHED(c);
+    return BB_OK;
+}
+
+// in-place sum over ranks of dbuf[0..count) on ctx->stream; false => caller falls back to NCCL
+bool bb_p2p_allreduce(bb_ctx* c, double* dbuf, i64 count, const int* done_flag, int* rc_out) {
+    (void)done_flag;
+    P2PView v;
+    *rc_out = BB_OK;
+    if (!bb_p2p_view(c, count, &v)) return false;
+    k_p2p_publish<<<reduce_grid(count), 256, 0, c->stream>>>(dbuf, count, v);
+    k_p2p_reduce<<<reduce_grid(count), 256, 0, c->stream>>>(dbuf, count, v);
     c->launches += 2;
     cudaError_t e = cudaPeekAtLastError();
     if (e != cudaSuccess) { bb_set_error("p2p allreduce launch: %s", cudaGetErrorString(e)); *rc_out = BB_ERR_CUDA; }

@@ -411,12 +411,16 @@ __global__ void k_sum_partials(const double* __restrict__ w, i64 n, double* __re
 // traw[0] = sum of the w partials; traw[1+j] = sum_r part[r*p+j]
 // Block = 32 columns x 8 slab groups: each thread sums slabs r = gy, gy+8, ... (independent loads in flight),
 // then the 8 partial sums of a column are added in fixed order through shared memory.
+// With a peer-memory exchange attached (pub != nullptr) the result goes straight into this rank's exchange
+// slot and the last block signals every peer: the local reduction and the publication are one kernel.
 __global__ void __launch_bounds__(256)
 k_tdot_collect(const double* __restrict__ part, int nslab, i64 p,
                const double* __restrict__ red_w, int nred, double* __restrict__ traw,
-               const int* __restrict__ done_flag) {
+               const int* __restrict__ done_flag, const P2PView* __restrict__ pub_ptr) {
     if (done_flag != nullptr && *done_flag) return;
     __shared__ double sm[8][33];
+    P2PView pub;
+    if (pub_ptr != nullptr) { pub = *pub_ptr; traw = p2p_publish_slot(pub); }
     if (blockIdx.x == 0 && threadIdx.x < 32) {
         double s = warp_sum_partials(red_w, nred);
         if (threadIdx.x == 0) traw[0] = s;
@@ -440,6 +444,7 @@ k_tdot_collect(const double* __restrict__ part, int nslab, i64 p,
         }
         __syncthreads();
     }
+    if (pub_ptr != nullptr) p2p_publish_done(pub);
 }
 
 // t_P from the (allreduced) traw: t[0] = sum w (intercept); t[icpt+j] = traw[1+j] - sum_w * c[j]
@@ -746,28 +751,45 @@ int bb_op_dot_flag(bb_mat* m, int mode, const int* done_flag) {
 int bb_op_dot(bb_mat* m, int mode) { return bb_op_dot_flag(m, mode, nullptr); }
 
 // traw = [sum w; X' w], allreduced.  have_w_partials: red[RED_W] already holds N_grid(n) partial sums of w
-int bb_op_tdot_flag(bb_mat* m, const double* w, bool have_w_partials, const int* done_flag) {
+int bb_op_tdot_flag(bb_mat* m, const double* w, bool have_w_partials, const int* done_flag,
+                    bool fuse_reduce_into_consumer) {
     bb_ctx* ctx = m->ctx;
     if (!have_w_partials) {
         k_sum_partials<<<N_grid(m->n), 256, 0, ctx->stream>>>(w, m->n, m->red + RED_W * RED_MAX);
         BB_LAUNCHED(ctx);
         m->nred_w = N_grid(m->n);
     }
+    // exchange: peer-memory one-shot (publication fused into the collect kernel) or NCCL
+    P2PView view;
+    const bool p2p = (ctx->nranks > 1) && bb_p2p_view(ctx, m->p + 1, &view);
+    const P2PView* pub = nullptr;
+    if (p2p) {
+        if (!m->p2p_view_valid) {      // first use is never inside a graph capture (the RHS product precedes the loop)
+            BB_CUDA(cudaStreamSynchronize(ctx->stream));
+            BB_CUDA(cudaMemcpy(m->p2p_view_dev, &view, sizeof(P2PView), cudaMemcpyHostToDevice));
+            m->p2p_view_valid = 1;
+        }
+        pub = m->p2p_view_dev;
+    }
     if (!m->is_sparse) {
         BB_TRY(bb_dense_tdot(m, w, done_flag));
         k_tdot_collect<<<grid_for(m->p, 32, 4096), 256, 0, ctx->stream>>>(
-            m->dense_part, m->dense_nblk, m->p, m->red + RED_W * RED_MAX, m->nred_w, m->traw, done_flag);
+            m->dense_part, m->dense_nblk, m->p, m->red + RED_W * RED_MAX, m->nred_w, m->traw, done_flag, pub);
         BB_LAUNCHED(ctx);
     } else {
         BB_TRY(bb_launch_spmv(m, &m->ftdot, w, done_flag));
         k_tdot_collect<<<grid_for(m->p, 32, 4096), 256, 0, ctx->stream>>>(
-            m->ftdot.part, m->ftdot.nslab, m->p, m->red + RED_W * RED_MAX, m->nred_w, m->traw, done_flag);
+            m->ftdot.part, m->ftdot.nslab, m->p, m->red + RED_W * RED_MAX, m->nred_w, m->traw, done_flag, pub);
         BB_LAUNCHED(ctx);
     }
-    BB_TRY(bb_allreduce_dev(ctx, m->traw, m->p + 1));
+    if (p2p) {
+        if (!fuse_reduce_into_consumer) BB_TRY(bb_p2p_reduce_into(ctx, m->traw, m->p + 1));
+    } else {
+        BB_TRY(bb_allreduce_dev(ctx, m->traw, m->p + 1));
+    }
     return BB_OK;
 }
-int bb_op_tdot(bb_mat* m, const double* w) { return bb_op_tdot_flag(m, w, false, nullptr); }
+int bb_op_tdot(bb_mat* m, const double* w) { return bb_op_tdot_flag(m, w, false, nullptr, false); }
 
 int bb_op_tdot_finish(bb_mat* m, double* tP) {
     bb_ctx* ctx = m->ctx;
@@ -795,6 +817,7 @@ int bb_mat_alloc_work(bb_mat* m) {
     BB_TRY(alloc_d(m->ctx->stream, &m->traw, m->p + 1));
     BB_TRY(alloc_d(m->ctx->stream, &m->zk, m->P + 1));
     BB_TRY(alloc_d(m->ctx->stream, &m->omega_scalar_dev, 1));
+    BB_CUDA(cudaMalloc((void**)&m->p2p_view_dev, sizeof(P2PView)));
     BB_TRY(alloc_d(m->ctx->stream, &m->red, (i64)RED_SLOTS * RED_MAX));
     BB_CUDA(cudaMalloc((void**)&m->cg, sizeof(CgScalars)));
     BB_CUDA(cudaMemsetAsync(m->cg, 0, sizeof(CgScalars), m->ctx->stream));
@@ -813,7 +836,7 @@ extern "C" int bb_mat_free(bb_mat* m) {
     bb_slab_free(&m->fdot);
     bb_slab_free(&m->ftdot);
     void* ptrs[] = {m->csr_ptr, m->csr_idx, m->csr_val, m->csc_ptr, m->csc_idx, m->csc_val, m->col_offset, m->Xd,
-                    m->omega, m->n_trial, m->n_success, m->eta, m->w_n, m->u_n, m->eps_n, m->dense_part, m->zk, m->omega_scalar_dev,
+                    m->omega, m->n_trial, m->n_success, m->eta, m->w_n, m->u_n, m->eps_n, m->dense_part, m->zk, m->omega_scalar_dev, m->p2p_view_dev,
                     m->v_P, m->sv, m->traw, m->t_P, m->x, m->r, m->pvec, m->q, m->b, m->s, m->D, m->pps, m->z, m->x0,
                     m->eps_P, m->out_P, m->red, m->cg};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -1004,7 +1027,7 @@ extern "C" int bb_fisher_diag(bb_mat* m, const double* weight, double* out) {
     }
     k_sum_partials<<<N_grid(m->n), 256, 0, st>>>(m->eps_n, m->n, m->red + RED_MISC * RED_MAX);
     BB_LAUNCHED(ctx);
-    k_tdot_collect<<<1, 256, 0, st>>>(nullptr, 0, 0, m->red + RED_MISC * RED_MAX, N_grid(m->n), m->traw, nullptr);
+    k_tdot_collect<<<1, 256, 0, st>>>(nullptr, 0, 0, m->red + RED_MISC * RED_MAX, N_grid(m->n), m->traw, nullptr, nullptr);
     BB_LAUNCHED(ctx);
     BB_CUDA(cudaMemcpyAsync(d2, m->traw, sizeof(double), cudaMemcpyDeviceToDevice, st));
     BB_TRY(bb_allreduce_dev(ctx, d2, m->p + 1));

@@ -41,6 +41,7 @@ WORKLOADS = {
     'C4': (1_000_000, 100_000, 0.001),
     'C3': (100_000, 20_000, 0.005),
     'C1': (10_000, 1_000, 0.01),
+    'C4shard8': (125_000, 100_000, 0.001),     # one rank's share of C4 at N = 8 (profiling aid)
 }
 
 
