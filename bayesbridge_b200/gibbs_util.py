@@ -80,7 +80,8 @@ class MarkovChainManager():
         }
         for key in ('coef', 'local_scale', 'global_scale', 'obs_prec', 'logp'):
             if key in params_to_save:
-                samples[key] = np.zeros(shapes[key])
+                # column k is written once per saved iteration: Fortran order makes that write contiguous
+                samples[key] = np.zeros(shapes[key], order='F')
         for key in self.sampling_info_keys(sampling_method):
             sampling_info[key] = np.zeros(n_sample)
 
