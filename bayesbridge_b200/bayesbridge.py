@@ -332,7 +332,8 @@ class BayesBridge():
             loglik, _ = self.model.compute_loglik_and_gradient(coef, obs_prec, loglik_only=True)
         else:
             loglik, _ = self.model.compute_loglik_and_gradient(coef, loglik_only=True)
-        loglik += - .5 * np.sum((coef / self.prior.slab_size) ** 2)
+        if not np.isinf(self.prior.slab_size):
+            loglik += - .5 * np.sum((coef / self.prior.slab_size) ** 2)
 
         n_shrunk = len(coef) - self.n_unshrunk
         prior_logp = - n_shrunk * math.log(gscale) \

@@ -30,8 +30,27 @@ extern "C" int bb_time_kernel(bb_mat* m, const char* what, int reps, int do_flus
     else if (!strcmp(what, "op")) kind = 2;
     else if (!strcmp(what, "spmv_dot")) kind = 3;     // the SpMV kernel alone (+ its fix-up)
     else if (!strcmp(what, "spmv_tdot")) kind = 4;
-    BB_ARG(kind >= 0, "what must be dot | tdot | op | spmv_dot | spmv_tdot");
-    BB_ARG(kind < 3 || m->is_sparse, "spmv_* needs a sparse matrix");
+    else if (!strcmp(what, "exchange")) kind = 5;     // all-reduce of the (p+1)-vector (every rank must call)
+    BB_ARG(kind >= 0, "what must be dot | tdot | op | spmv_dot | spmv_tdot | exchange");
+    BB_ARG(kind < 3 || kind == 5 || m->is_sparse, "spmv_* needs a sparse matrix");
+    if (kind == 5) {
+        // back-to-back exchanges, timed as one region (the per-exchange latency is what matters in the CG loop)
+        cudaEvent_t a, b;
+        BB_CUDA(cudaEventCreate(&a));
+        BB_CUDA(cudaEventCreate(&b));
+        for (int r = 0; r < 3; ++r) BB_TRY(bb_allreduce_dev(ctx, m->traw, m->p + 1));
+        BB_CUDA(cudaStreamSynchronize(st));
+        BB_CUDA(cudaEventRecord(a, st));
+        for (int r = 0; r < reps; ++r) BB_TRY(bb_allreduce_dev(ctx, m->traw, m->p + 1));
+        BB_CUDA(cudaEventRecord(b, st));
+        BB_CUDA(cudaEventSynchronize(b));
+        float ms = 0.f;
+        BB_CUDA(cudaEventElapsedTime(&ms, a, b));
+        cudaEventDestroy(a);
+        cudaEventDestroy(b);
+        *ms_out = ms / reps;
+        return BB_OK;
+    }
     // deterministic, non-trivial inputs
     k_fill_test<<<256, 256, 0, st>>>(m->v_P, m->P, 1e-3);
     k_fill_test<<<256, 256, 0, st>>>(m->eps_n, m->n, 1e-3);

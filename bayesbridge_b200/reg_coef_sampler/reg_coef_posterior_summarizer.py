@@ -13,9 +13,16 @@ class OntheflySummarizer():
         self.stats = {'mean': np.zeros(n_param), 'square': np.ones(n_param)}
 
     def update_stats(self, theta):
+        """mean <- w*theta + (1-w)*mean, square <- w*theta^2 + (1-w)*square (same rounding as the plain
+        expressions; written with out= so that no P-length temporaries are allocated per iteration)."""
         w = 1 / (1 + self.n_averaged)
-        self.stats['mean'] = w * theta + (1 - w) * self.stats['mean']
-        self.stats['square'] = w * theta ** 2 + (1 - w) * self.stats['square']
+        a = np.multiply(theta, w)
+        np.multiply(self.stats['mean'], 1 - w, out=self.stats['mean'])
+        np.add(a, self.stats['mean'], out=self.stats['mean'])
+        np.multiply(theta, theta, out=a)
+        np.multiply(a, w, out=a)
+        np.multiply(self.stats['square'], 1 - w, out=self.stats['square'])
+        np.add(a, self.stats['square'], out=self.stats['square'])
         self.n_averaged += 1
 
     def estimate_post_sd(self):
@@ -36,12 +43,20 @@ class RegressionCoeffficientPosteriorSummarizer():
         self.slab_size = regularizing_slab_size
 
     def compute_prior_scale(self, gscale, lscale):
+        """tau*lambda damped by the slab; cached for the (gscale, lscale) pair of the current Gibbs iteration,
+        which asks for it three times. Without a slab the damping factor is exactly 1."""
+        key = (float(gscale), id(lscale))
+        if getattr(self, '_scale_key', None) == key and self._scale_ref is lscale:
+            return self._scale_val
         raw = gscale * lscale
-        return raw / np.sqrt(1 + (raw / self.slab_size) ** 2)
+        if not np.isinf(self.slab_size):
+            raw /= np.sqrt(1 + (raw / self.slab_size) ** 2)
+        self._scale_key, self._scale_ref, self._scale_val = key, lscale, raw
+        return raw
 
     def scale_coef(self, coef, gscale, lscale):
         scaled = coef.copy()
-        scaled[self.n_unshrunk:] /= self.compute_prior_scale(gscale, lscale)
+        np.divide(scaled[self.n_unshrunk:], self.compute_prior_scale(gscale, lscale), out=scaled[self.n_unshrunk:])
         return scaled
 
     def update(self, coef, gscale, lscale):

@@ -37,7 +37,8 @@ class SparseRegressionCoefficientSampler():
     def compute_prior_shrunk_scale(self, gscale, lscale):
         """tau*lambda damped by the slab (reg_coef_sampler.py:194-201)."""
         scale = gscale * lscale
-        scale /= np.sqrt(1 + (scale / self.regularizing_slab_size) ** 2)
+        if not np.isinf(self.regularizing_slab_size):       # without a slab the damping factor is exactly 1
+            scale /= np.sqrt(1 + (scale / self.regularizing_slab_size) ** 2)
         return scale
 
     def sample_gaussian_posterior(self, y, design, obs_prec, gscale, lscale, method='cg',
@@ -53,9 +54,10 @@ class SparseRegressionCoefficientSampler():
             raise NotImplementedError("Only method='cg' is available on the device.")
         if z is None and y is not None:
             z = design.Tdot(obs_prec * y)
-        prior_sd = np.concatenate((
-            self.prior_sd_for_unshrunk, self.compute_prior_shrunk_scale(gscale, lscale)))
-        prior_prec_sqrt = 1 / prior_sd
+        k = self.n_unshrunk
+        prior_prec_sqrt = np.empty(k + len(lscale))
+        prior_prec_sqrt[:k] = 1 / np.asarray(self.prior_sd_for_unshrunk, dtype=np.float64)
+        np.divide(1., self.regcoef_summarizer.compute_prior_scale(gscale, lscale), out=prior_prec_sqrt[k:])
         x0 = self.regcoef_summarizer.extrapolate_coef_condmean(gscale, lscale)
         scaled_sd = self.regcoef_summarizer.estimate_coef_precond_scale_sd()
         coef, cg_info = self.cg_sampler.sample(
