@@ -198,8 +198,7 @@ static int apply_operator(bb_mat* m, const double* vP, int count_iter) {
     const bool p2p = (ctx->nranks > 1) && bb_p2p_view(ctx, m->p + 1, &view);
     BB_TRY(bb_op_tdot_flag(m, m->w_n, true, done, /*fuse_reduce_into_consumer=*/p2p));
     // red_pq holds one partial per block and k_cg_update sums P_grid(P) of them: keep that grid (<= RED_MAX);
-    // with the fused exchange the block is 1024 wide: one element per thread, one NVLink round trip in total
-    k_cg_q<<<P_grid(m->P), p2p ? 1024 : 256, 0, ctx->stream>>>(m->cg, m->traw, m->col_offset, m->add_intercept, m->P, vP,
+    k_cg_q<<<P_grid(m->P), 256, 0, ctx->stream>>>(m->cg, m->traw, m->col_offset, m->add_intercept, m->P, vP,
                                                   m->s, m->D, m->q, m->red + RED_PQ * RED_MAX, count_iter,
                                                   p2p ? m->p2p_view_dev : nullptr);
     BB_LAUNCHED(ctx);

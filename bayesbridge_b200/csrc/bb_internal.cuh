@@ -321,59 +321,46 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned 
 __device__ __forceinline__ double* p2p_publish_slot(const P2PView& v) {
     return v.peer_base[v.rank] + 32 + (v.st->seq & 1ull) * v.cap;
 }
-// to be called by every block after its last store into the slot: the last block to arrive signals all peers.
-// Ordering: writers fence + relaxed counter RMW; the last block's thread 0 fences after its RMW (fence-fence
-// synchronisation => it observes every block's stores), the block barrier hands that to threads q < nranks, each
-// of which issues a system-scope fence and ONE remote flag store -- the nranks stores fly in parallel.
+// to be called by every block after its last store into the slot: the last block to arrive signals all peers
 __device__ __forceinline__ void p2p_publish_done(const P2PView& v) {
-    __shared__ int p2p_is_last;
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
-        unsigned int prev = atomicAdd(&v.st->blocks_done, 1u);
-        p2p_is_last = (prev == gridDim.x * gridDim.y - 1) ? 1 : 0;
-        if (p2p_is_last) __threadfence();
-    }
-    __syncthreads();
-    if (p2p_is_last) {
         const unsigned long long seq = v.st->seq;
-        if ((int)threadIdx.x < v.nranks) {
+        unsigned int prev = atomicAdd(&v.st->blocks_done, 1u);
+        if (prev == gridDim.x * gridDim.y - 1) {
+            v.st->blocks_done = 0u;
             __threadfence_system();
-            st_release_sys_u64(reinterpret_cast<unsigned long long*>(v.peer_base[threadIdx.x]) + v.rank, seq + 1ull);
+            for (int q = 0; q < v.nranks; ++q)
+                st_release_sys_u64(reinterpret_cast<unsigned long long*>(v.peer_base[q]) + v.rank, seq + 1ull);
+            v.st->seq = seq + 1ull;
         }
-        __syncthreads();
-        if (threadIdx.x == 0) { v.st->blocks_done = 0u; v.st->seq = seq + 1ull; }
     }
 }
-// block-wide wait until every rank has published number st->seq (thread q polls rank q's flag, in parallel);
-// returns false after a time-out
+// block-wide wait until every rank has published number st->seq; returns false after a time-out
 __device__ __forceinline__ bool p2p_wait_all(const P2PView& v, int* sm_flag) {
     const unsigned long long want = v.st->seq;
-    if (threadIdx.x == 0) *sm_flag = 1;
-    __syncthreads();
-    if ((int)threadIdx.x < v.nranks) {
-        const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(v.peer_base[v.rank]) + threadIdx.x;
-        unsigned long long spins = 0;
-        while (ld_acquire_sys_u64(flag) < want) {
-            if (++spins > (1ull << 26)) { *sm_flag = 0; v.st->error = 1u; break; }
-            __nanosleep(20);
+    if (threadIdx.x == 0) {
+        const unsigned long long* flags = reinterpret_cast<const unsigned long long*>(v.peer_base[v.rank]);
+        int good = 1;
+        for (int q = 0; q < v.nranks && good; ++q) {
+            unsigned long long spins = 0;
+            while (ld_acquire_sys_u64(flags + q) < want) {
+                if (++spins > (1ull << 26)) { good = 0; v.st->error = 1u; break; }
+                __nanosleep(20);
+            }
         }
+        *sm_flag = good;
     }
     __syncthreads();
     return *sm_flag != 0;
 }
-// element i of the published vectors summed over ranks in rank order (identical bits on every rank); the peer
-// loads are issued together (one NVLink round trip), then added in order
+// element i of the published vectors summed over ranks in rank order (identical bits on every rank)
 __device__ __forceinline__ double p2p_sum(const P2PView& v, i64 i) {
     const i64 off = 32 + ((v.st->seq - 1ull) & 1ull) * v.cap + i;
     double acc = 0.0;
-    for (int q0 = 0; q0 < v.nranks; q0 += 8) {
-        double x[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) x[k] = (q0 + k < v.nranks) ? __ldcv(v.peer_base[q0 + k] + off) : 0.0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) if (q0 + k < v.nranks) acc += x[k];
-    }
+    for (int q = 0; q < v.nranks; ++q) acc += __ldcv(v.peer_base[q] + off);
     return acc;
 }
+
 #endif  // __CUDACC__
