@@ -42,6 +42,7 @@ WORKLOADS = {
     'C3': (100_000, 20_000, 0.005),
     'C1': (10_000, 1_000, 0.01),
     'C4shard8': (125_000, 100_000, 0.001),     # one rank's share of C4 at N = 8 (profiling aid)
+    'C4quarter': (250_000, 100_000, 0.001),    # two such shares (N = 2 reproduces the N = 8 per-rank load)
 }
 
 
