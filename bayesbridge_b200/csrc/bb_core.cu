@@ -81,6 +81,7 @@ static i64* option_slot(bb_ctx* c, const char* name) {
     if (!strcmp(name, "cg_chunk")) return &c->opt_cg_chunk;
     if (!strcmp(name, "use_graph")) return &c->opt_use_graph;
     if (!strcmp(name, "allreduce_p2p")) return &c->opt_allreduce_p2p;
+    if (!strcmp(name, "p2p_variant")) return &c->opt_p2p_variant;
     return nullptr;
 }
 

@@ -57,6 +57,7 @@ struct P2PView {
     P2PState* st;
     i64 cap;
     int nranks, rank;
+    int variant;                   // protocol variant bits (option "p2p_variant"), see bb_internal.cuh
 };
 
 // ------------------------------------------------------------------------------------------
@@ -79,6 +80,8 @@ struct bb_ctx {
     void* p2p;
     int p2p_ready;
     i64 opt_allreduce_p2p;   // 1: use it when attached (default), 0: always NCCL
+    i64 opt_p2p_variant;     // bit0: one system fence + relaxed flag stores; bit1: parallel flag polls;
+                             // bit2: batched peer loads; bit3: flag stores issued by nranks threads
     // L2 flush scratch for bb_time_kernel
     void* flush_buf;
     size_t flush_bytes;
@@ -321,27 +324,57 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned 
 __device__ __forceinline__ double* p2p_publish_slot(const P2PView& v) {
     return v.peer_base[v.rank] + 32 + (v.st->seq & 1ull) * v.cap;
 }
-// to be called by every block after its last store into the slot: the last block to arrive signals all peers
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// to be called by every block after its last store into the slot: the last block to arrive signals all peers.
+// Ordering: writers fence + relaxed counter RMW; the last block's thread 0 fences after its RMW (fence-fence
+// synchronisation => it observes every block's stores) and then releases the flags at system scope.
 __device__ __forceinline__ void p2p_publish_done(const P2PView& v) {
+    __shared__ int p2p_is_last;
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
-        const unsigned long long seq = v.st->seq;
         unsigned int prev = atomicAdd(&v.st->blocks_done, 1u);
-        if (prev == gridDim.x * gridDim.y - 1) {
-            v.st->blocks_done = 0u;
+        p2p_is_last = (prev == gridDim.x * gridDim.y - 1) ? 1 : 0;
+        if (p2p_is_last) __threadfence();
+    }
+    __syncthreads();
+    if (!p2p_is_last) return;
+    const unsigned long long seq = v.st->seq;
+    if (v.variant & 8) {                       // nranks threads, one remote store each
+        if ((int)threadIdx.x < v.nranks) {
             __threadfence_system();
-            for (int q = 0; q < v.nranks; ++q)
-                st_release_sys_u64(reinterpret_cast<unsigned long long*>(v.peer_base[q]) + v.rank, seq + 1ull);
-            v.st->seq = seq + 1ull;
+            unsigned long long* f = reinterpret_cast<unsigned long long*>(v.peer_base[threadIdx.x]) + v.rank;
+            if (v.variant & 1) st_relaxed_sys_u64(f, seq + 1ull); else st_release_sys_u64(f, seq + 1ull);
         }
+        __syncthreads();
+        if (threadIdx.x == 0) { v.st->blocks_done = 0u; v.st->seq = seq + 1ull; }
+    } else if (threadIdx.x == 0) {
+        v.st->blocks_done = 0u;
+        __threadfence_system();
+        for (int q = 0; q < v.nranks; ++q) {
+            unsigned long long* f = reinterpret_cast<unsigned long long*>(v.peer_base[q]) + v.rank;
+            if (v.variant & 1) st_relaxed_sys_u64(f, seq + 1ull); else st_release_sys_u64(f, seq + 1ull);
+        }
+        v.st->seq = seq + 1ull;
     }
 }
 // block-wide wait until every rank has published number st->seq; returns false after a time-out
 __device__ __forceinline__ bool p2p_wait_all(const P2PView& v, int* sm_flag) {
     const unsigned long long want = v.st->seq;
-    if (threadIdx.x == 0) {
-        const unsigned long long* flags = reinterpret_cast<const unsigned long long*>(v.peer_base[v.rank]);
+    const unsigned long long* flags = reinterpret_cast<const unsigned long long*>(v.peer_base[v.rank]);
+    if (v.variant & 2) {                       // thread q polls rank q's flag
+        if (threadIdx.x == 0) *sm_flag = 1;
+        __syncthreads();
+        if ((int)threadIdx.x < v.nranks) {
+            unsigned long long spins = 0;
+            while (ld_acquire_sys_u64(flags + threadIdx.x) < want) {
+                if (++spins > (1ull << 26)) { *sm_flag = 0; v.st->error = 1u; break; }
+                __nanosleep(20);
+            }
+        }
+    } else if (threadIdx.x == 0) {
         int good = 1;
         for (int q = 0; q < v.nranks && good; ++q) {
             unsigned long long spins = 0;
@@ -359,8 +392,17 @@ __device__ __forceinline__ bool p2p_wait_all(const P2PView& v, int* sm_flag) {
 __device__ __forceinline__ double p2p_sum(const P2PView& v, i64 i) {
     const i64 off = 32 + ((v.st->seq - 1ull) & 1ull) * v.cap + i;
     double acc = 0.0;
-    for (int q = 0; q < v.nranks; ++q) acc += __ldcv(v.peer_base[q] + off);
+    if (v.variant & 4) {                       // issue the peer loads together, then add in order
+        for (int q0 = 0; q0 < v.nranks; q0 += 8) {
+            double x[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) x[k] = (q0 + k < v.nranks) ? __ldcv(v.peer_base[q0 + k] + off) : 0.0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) if (q0 + k < v.nranks) acc += x[k];
+        }
+    } else {
+        for (int q = 0; q < v.nranks; ++q) acc += __ldcv(v.peer_base[q] + off);
+    }
     return acc;
 }
-
 #endif  // __CUDACC__

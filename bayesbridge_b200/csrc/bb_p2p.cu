@@ -106,6 +106,7 @@ bool bb_p2p_view(bb_ctx* c, i64 count, P2PView* out) {
     out->cap = p->cap;
     out->nranks = p->nranks;
     out->rank = p->rank;
+    out->variant = (int)c->opt_p2p_variant;
     return true;
 }
 

@@ -764,10 +764,10 @@ int bb_op_tdot_flag(bb_mat* m, const double* w, bool have_w_partials, const int*
     const bool p2p = (ctx->nranks > 1) && bb_p2p_view(ctx, m->p + 1, &view);
     const P2PView* pub = nullptr;
     if (p2p) {
-        if (!m->p2p_view_valid) {      // first use is never inside a graph capture (the RHS product precedes the loop)
+        if (m->p2p_view_valid != 1 + view.variant) {      // first use is never inside a graph capture (the RHS product precedes the loop)
             BB_CUDA(cudaStreamSynchronize(ctx->stream));
             BB_CUDA(cudaMemcpy(m->p2p_view_dev, &view, sizeof(P2PView), cudaMemcpyHostToDevice));
-            m->p2p_view_valid = 1;
+            m->p2p_view_valid = 1 + view.variant;
         }
         pub = m->p2p_view_dev;
     }

@@ -10,18 +10,19 @@ rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int
 torch.cuda.set_device(local)
 dist.init_process_group('nccl', device_id=torch.device('cuda', local))
 ctx = _lib.Context(local); ctx.init_comm_from_torch()
-for p in (20000, 100000):
+for p in (100000,):
     rs = np.random.RandomState(rank)
     X = sp.random(2000, p, density=0.002, format='csr', random_state=rs, dtype=np.float64); X.data[:] = 1.0
     X = sp.vstack([X, sp.csr_matrix(np.ones((1, p)))]).tocsr()       # keep every column non-constant globally
     D = GpuSparseDesignMatrix(X, center_predictor=True, add_intercept=True, ctx=ctx, presharded=True,
                               n_global=2001 * world, row_offset=2001 * rank)
-    for mode in (1, 0, 1, 0):
+    for mode, variant in ((0, 0), (1, 0), (1, 1), (1, 2), (1, 4), (1, 5), (1, 7), (1, 15), (1, 0), (0, 0)):
         ctx.set_option('allreduce_p2p', mode)
+        ctx.set_option('p2p_variant', variant)
         dist.barrier(); torch.cuda.synchronize()
-        us = D.time_kernel('exchange', reps=200, flush_l2=False) * 1e3
+        us = D.time_kernel('exchange', reps=300, flush_l2=False) * 1e3
         t = torch.tensor([us], device='cuda'); dist.all_reduce(t, op=dist.ReduceOp.MAX)
         if rank == 0:
-            print(f"N={world} p={D.shape[1]} exchange {'p2p ' if mode else 'nccl'}: {t.item():.1f} us", flush=True)
+            print(f"N={world} p={D.shape[1]} exchange {'p2p variant %2d' % variant if mode else 'nccl          '}: {t.item():.1f} us", flush=True)
 print(f"[rank {rank}] p2p status {ctx.p2p_status()}", flush=True)
 dist.destroy_process_group()
