@@ -126,6 +126,11 @@ class BayesBridge():
             self.manager.print_status(n_status_update, mcmc_iter, n_iter)
 
         runtime = time.time() - start_time
+        ctx = self.model.design.ctx
+        if ctx.nranks > 1:
+            ready, err = ctx.p2p_status()
+            if err:
+                raise RuntimeError("peer-memory exchange timed out waiting for another rank; results are invalid")
         raw_scales = {'global_scale': gscale, 'local_scale': np.array(lscale, copy=True)}
 
         if self.prior._gscale_paramet == 'coef_magnitude':

@@ -290,9 +290,11 @@ extern "C" int bb_cg_sample(bb_mat* m, const double* omega, const double* prior_
     k_cg_resid<<<gP, 256, 0, st>>>(m->cg, m->b, m->q, m->P, m->r, m->red + RED_RR * RED_MAX);
     BB_LAUNCHED(ctx);
 
-    // iterations, enqueued in chunks; the device skips work once done != 0
+    // iterations, enqueued in chunks; the device skips work once done != 0.  One CUDA graph holds
+    // CG_GRAPH_ITERS iterations (fewer graph launches; surplus iterations are early-exit kernels).
+    const int CG_GRAPH_ITERS = 4;
     int total = 0;
-    int first = (ctx->opt_cg_chunk > 0) ? (int)ctx->opt_cg_chunk : (m->last_n_iter > 0 ? m->last_n_iter : 8);
+    int first = (ctx->opt_cg_chunk > 0) ? (int)ctx->opt_cg_chunk : (m->last_n_iter > 0 ? m->last_n_iter + 1 : 8);
     int chunk = first;
     const bool use_graph = ctx->opt_use_graph != 0;
     for (;;) {
@@ -300,34 +302,35 @@ extern "C" int bb_cg_sample(bb_mat* m, const double* omega, const double* prior_
         int todo = chunk;
         if (total + todo > maxiter + 1) todo = maxiter + 1 - total;
         if (todo < 1) todo = 1;
-        for (int k = 0; k < todo; ++k) {
-            if (use_graph) {
-                if (!m->cg_graph) {
-                    cudaGraph_t g = nullptr;
-                    const i64 l0 = ctx->launches;
-                    BB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-                    int rc = cg_iteration(m);
-                    cudaError_t e = cudaStreamEndCapture(st, &g);
-                    m->cg_graph_launches = (int)(ctx->launches - l0);
-                    ctx->launches = l0;
-                    if (rc != BB_OK) { if (g) cudaGraphDestroy(g); return rc; }
-                    if (e != cudaSuccess) { bb_set_error("graph capture: %s", cudaGetErrorString(e)); return BB_ERR_CUDA; }
-                    e = cudaGraphInstantiate(&m->cg_graph, g, 0);
-                    cudaGraphDestroy(g);
-                    if (e != cudaSuccess) { bb_set_error("graph instantiate: %s", cudaGetErrorString(e)); return BB_ERR_CUDA; }
-                }
-                BB_CUDA(cudaGraphLaunch(m->cg_graph, st));
-                ctx->launches += m->cg_graph_launches;
-            } else {
-                BB_TRY(cg_iteration(m));
+        if (use_graph) {
+            if (!m->cg_graph) {
+                cudaGraph_t g = nullptr;
+                const i64 l0 = ctx->launches;
+                BB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+                int rc = BB_OK;
+                for (int k = 0; k < CG_GRAPH_ITERS && rc == BB_OK; ++k) rc = cg_iteration(m);
+                cudaError_t e = cudaStreamEndCapture(st, &g);
+                m->cg_graph_launches = (int)(ctx->launches - l0);
+                ctx->launches = l0;
+                if (rc != BB_OK) { if (g) cudaGraphDestroy(g); return rc; }
+                if (e != cudaSuccess) { bb_set_error("graph capture: %s", cudaGetErrorString(e)); return BB_ERR_CUDA; }
+                e = cudaGraphInstantiate(&m->cg_graph, g, 0);
+                cudaGraphDestroy(g);
+                if (e != cudaSuccess) { bb_set_error("graph instantiate: %s", cudaGetErrorString(e)); return BB_ERR_CUDA; }
             }
+            const int ngraphs = (todo + CG_GRAPH_ITERS - 1) / CG_GRAPH_ITERS;
+            for (int k = 0; k < ngraphs; ++k) BB_CUDA(cudaGraphLaunch(m->cg_graph, st));
+            ctx->launches += (i64)ngraphs * m->cg_graph_launches;
+            todo = ngraphs * CG_GRAPH_ITERS;
+        } else {
+            for (int k = 0; k < todo; ++k) BB_TRY(cg_iteration(m));
         }
         total += todo;
         BB_CUDA(cudaMemcpyAsync(m->cg_host, m->cg, sizeof(CgScalars), cudaMemcpyDeviceToHost, st));
         BB_CUDA(cudaStreamSynchronize(st));
         if (m->cg_host->done != 0) break;
         if (total >= maxiter + 1) break;   // cannot happen: launch maxiter+1 sets done=2
-        chunk = (ctx->opt_cg_chunk > 0) ? (int)ctx->opt_cg_chunk : 2;
+        chunk = (ctx->opt_cg_chunk > 0) ? (int)ctx->opt_cg_chunk : CG_GRAPH_ITERS;
     }
     k_cg_final<<<gP, 256, 0, st>>>(m->cg, m->s, m->x, m->P, m->out_P);
     BB_LAUNCHED(ctx);
