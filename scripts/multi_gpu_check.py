@@ -78,8 +78,8 @@ for c in (ctx, solo):
 check('chain coef mean sharded vs unsharded', float(np.abs(chains[0]['coef'].mean(1) - chains[1]['coef'].mean(1)).max()), 5e-2)
 check('chain logp sharded vs unsharded', float(abs(chains[0]['logp'].mean() / chains[1]['logp'].mean() - 1)), 1e-2)
 ready, err = ctx.p2p_status()
-print(f'[rank {rank}] p2p ready={ready} error={err} (BB_ALLREDUCE={os.environ.get("BB_ALLREDUCE", "p2p")})', flush=True)
-ok &= (err == 0)
+print(f'[rank {rank}] p2p ready={ready} error={err} (BB_ALLREDUCE={os.environ.get("BB_ALLREDUCE", "nccl")})', flush=True)
+ok &= (err == 0) and (ready == (os.environ.get('BB_ALLREDUCE', 'nccl') == 'p2p'))
 flag = torch.tensor([1.0 if ok else 0.0]).cuda(); dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
     print('MULTI_GPU_CHECK', 'PASS' if flag.item() == 1.0 else 'FAIL', flush=True)

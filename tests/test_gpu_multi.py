@@ -12,11 +12,15 @@ from conftest import ROOT
 pytestmark = pytest.mark.gpu
 
 
-def test_sharded_path_matches_unsharded_two_gpus():
+@pytest.mark.parametrize('exchange', ['nccl', 'p2p'])
+def test_sharded_path_matches_unsharded_two_gpus(exchange):
+    """exchange = 'nccl': ncclAllReduce on the library stream; 'p2p': the fused peer-memory exchange (bb_p2p.cu)."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip('needs 2 GPUs')
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
-           '--master-addr', '127.0.0.1', '--master-port', '29533', os.path.join(ROOT, 'scripts', 'multi_gpu_check.py')]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+           '--master-addr', '127.0.0.1', '--master-port', '29533' if exchange == 'nccl' else '29534',
+           os.path.join(ROOT, 'scripts', 'multi_gpu_check.py')]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT,
+                         env=dict(os.environ, BB_ALLREDUCE=exchange))
     assert 'MULTI_GPU_CHECK PASS' in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
