@@ -123,7 +123,6 @@ int bb_p2p_reduce_into(bb_ctx* c, double* dst, i64 count);      // wait + rank-o
 // run of nnz gathers from one <=W-wide window of the input vector (a "slab"), which one CTA
 // stages in shared memory.  Virtual segment v = slab * n_seg + seg.
 struct TileMeta { int start, end, vlo, vhi; };   // nnz range; owns virtual segments [vlo, vhi)
-struct WorkUnit { int slab, tile_lo, tile_hi, pad; };
 
 struct SlabFmt {
     int   nslab;

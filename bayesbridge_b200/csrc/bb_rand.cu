@@ -267,10 +267,6 @@ __global__ void k_finish_scalar(const double* __restrict__ red, int nred, double
 }
 
 // ---- host entry points -------------------------------------------------------------------------
-static int scratch_vec(bb_ctx* ctx, void** d, size_t bytes) {
-    BB_CUDA(cudaMalloc(d, bytes ? bytes : 1));
-    return BB_OK;
-}
 
 extern "C" int bb_pg_sample(bb_ctx* ctx, int64_t n, const int32_t* shape, const double* tilt,
                             uint64_t seed, uint64_t offset, int64_t index_offset, double* out) {

@@ -14,7 +14,6 @@ constexpr int SPMV_THREADS = 1024;                      // one CTA per SM, 32 in
 constexpr int SPMV_WARPS = SPMV_THREADS / 32;
 constexpr int SPMV_ITEMS = 8;                           // nnz per lane per tile
 constexpr int SPMV_TILE = 32 * SPMV_ITEMS;              // nnz per (warp) tile
-constexpr int SPMV_REG_ITEMS = 8;                       // <= this many segments in a tile: register path
 
 // ------------------------------------------------------------------------------------------
 // setup kernels (run once per matrix)

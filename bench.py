@@ -357,6 +357,22 @@ def main():
     peak = float(peaks.get('hbm_gbs', 6650.0))
     peak_src = 'measured (MEASURED_PEAKS.json hbm_gbs)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s'
     ach = (b_tdot if dom == 'spmv_tdot' else b_dot) / (roof[dom] * 1e-3) / 1e9
+    # DRAM traffic of the same kernel from the committed `ncu --set full` capture (C4, one GPU): row 0 = dot, row 1 = Tdot
+    traffic, traffic_src = None, None
+    try:
+        if args.workload == 'C4' and world == 1:
+            import csv
+            rows = list(csv.reader(open(os.path.join(ROOT, 'profiles', 'r01_ncu_spmv_v5_c4.csv'))))
+            hdr, units = rows[0], rows[1]
+            row = rows[2 + (1 if dom == 'spmv_tdot' else 0)]
+            scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+            traffic = 0.0
+            for name in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
+                i = hdr.index(name)
+                traffic += float(row[i].replace(',', '')) * scale[units[i]]
+            traffic_src = 'profiles/r01_ncu_spmv_v5_c4.csv (ncu --set full, same kernel and matrix)'
+    except Exception:
+        traffic, traffic_src = None, None
     line = {
         'metric': 'gibbs_iters_per_sec', 'value': value, 'unit': 'iter/s', 'n_gpus': world, 'steps': K,
         'warmup': args.warmup, 'ms_per_step': dev_ms / K, 'higher_is_better': True, 'scaling': 'strong',
@@ -369,7 +385,7 @@ def main():
         'clocks': sampler.summary(),
         'roofline': {
             'bound': 'hbm', 'kernel': 'k_seg_spmv (%s)' % dom, 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
-            'frac': ach / peak, 'traffic': None, 'peak_source': peak_src,
+            'frac': ach / peak, 'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peak_src,
             'algorithmic_bytes_per_launch': int(b_tdot if dom == 'spmv_tdot' else b_dot),
             'ms_per_launch': roof[dom],
             'other': {'spmv_dot_ms': roof['spmv_dot'], 'spmv_dot_GBs': b_dot / (roof['spmv_dot'] * 1e-3) / 1e9,
