@@ -144,3 +144,52 @@ def test_device_noise_is_reproducible_and_gaussian(ctx):
                                       shape=tuple(g['sparse_bin_shape'])), True, True)
     ref, _ = co.cg_sample(O, omega, pps, z, x0, s, 500, 1e-9, e1, e2)
     assert relerr(a, ref) <= TOL
+
+
+def test_dense_cg_draw_is_the_exact_gaussian_draw(ctx):
+    """BASELINE config 2 in miniature (dense X, 'cg' vs the Cholesky answer): with the noise fixed, a tightly converged
+    CG draw equals the dense solve Phi^-1 (z + X' sqrt(omega) eps1 + pps eps2) that the Cholesky sampler computes."""
+    from bayesbridge_b200.design_matrix import GpuDenseDesignMatrix
+    from bayesbridge_b200.reg_coef_sampler import ConjugateGradientSampler
+    rng = np.random.default_rng(3)
+    n, p = 4000, 350
+    X = rng.standard_normal((n, p))
+    D = GpuDenseDesignMatrix(X.copy(), center_predictor=True, add_intercept=True, ctx=ctx)
+    O = co.DesignOracle(X, True, True)
+    P = p + 1
+    omega = np.full(n, 0.8)                                  # linear model: omega = sigma^-2 * 1
+    pps = np.concatenate(([0.5], 1 / (0.05 + rng.random(p))))
+    z, sd = O.Tdot(omega * rng.standard_normal(n)), np.ones(P)
+    np.random.seed(21)
+    e1, e2 = np.random.randn(n), np.random.randn(P)
+    coef, info = ConjugateGradientSampler(1).sample(D, omega, pps, z, np.zeros(P), 'prior', sd, maxiter=2000,
+                                                    atol=1e-12 * np.sqrt(P), seed=21)
+    exact = co.exact_gaussian_mean(O, omega, pps, z + O.Tdot(np.sqrt(omega) * e1) + pps * e2)
+    assert info['converged'] and relerr(coef, exact) <= TOL
+
+
+def test_full_size_cg_solves_the_system_c3(ctx):
+    """BASELINE config 3 at full size: the CG draw must satisfy the linear system it was asked to solve; the residual is
+    re-computed with independent device products (bb_dot / bb_tdot), and the iteration count must be stable."""
+    import bench
+    from bayesbridge_b200.design_matrix import GpuSparseDesignMatrix
+    from bayesbridge_b200.reg_coef_sampler import ConjugateGradientSampler
+    n, p, dens = bench.WORKLOADS['C3']
+    X, _ = bench.generate_rows(range(bench.N_BLOCKS), n, p, dens)
+    D = GpuSparseDesignMatrix(X, center_predictor=True, add_intercept=True, ctx=ctx)
+    P = D.shape[1]
+    rng = np.random.default_rng(1)
+    omega = 0.05 + 0.2 * rng.random(n)
+    pps = np.concatenate(([0.5], 1 / (0.02 + 0.1 * rng.random(P - 1))))
+    z, sd = rng.standard_normal(P), np.ones(P)
+    S = ConjugateGradientSampler(1)
+    np.random.seed(5)
+    e1, e2 = np.random.randn(n), np.random.randn(P)
+    coef, info = S.sample(D, omega, pps, z, np.zeros(P), 'prior', sd, maxiter=2000, atol=1e-10 * np.sqrt(P), seed=5)
+    assert info['converged']
+    rhs = z + D.Tdot(np.sqrt(omega) * e1) + pps * e2
+    resid = D.Tdot(omega * D.dot(coef)) + pps ** 2 * coef - rhs
+    s = S.choose_preconditioner(pps, None, D, 'prior', sd)
+    assert np.linalg.norm(s * resid) <= 2e-10 * np.sqrt(P)       # the stopping rule acts on the preconditioned residual
+    again, info2 = S.sample(D, omega, pps, z, np.zeros(P), 'prior', sd, maxiter=2000, atol=1e-10 * np.sqrt(P), seed=5)
+    assert np.array_equal(again, coef) and info2['n_iter'] == info['n_iter']          # bit-reproducible

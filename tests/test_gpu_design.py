@@ -173,3 +173,36 @@ def test_memoised_dot_and_counters(ctx):
     assert D.n_matvec == 2
     D.reset_matvec_count()
     assert D.n_matvec == 0
+
+
+def test_full_size_properties_c3(ctx):
+    """BASELINE config 3 (OHDSI-scale: binary sparse 100k x 20k, ~0.5 %, bench.py's generator) -- too large for the
+    numpy oracle to be the checker of every entry, so size-independent properties are asserted instead:
+    linearity of dot / Tdot, adjointness <Xv, w> = <v, X'w>, agreement with scipy on a row / column sample,
+    and fisher-diag == Tdot of the weights for a 0/1 matrix."""
+    import bench
+    Sparse, _ = _designs()
+    n, p, dens = bench.WORKLOADS['C3']
+    X, _ = bench.generate_rows(range(bench.N_BLOCKS), n, p, dens)
+    D = Sparse(X, center_predictor=True, add_intercept=True, ctx=ctx)
+    assert D.is_binary and D.shape == (n, X.shape[1] + 1)
+    P = D.shape[1]
+    rng = np.random.default_rng(0)
+    v1, v2, w1, w2 = rng.standard_normal(P), rng.standard_normal(P), rng.standard_normal(n), rng.standard_normal(n)
+    a, b = 0.7, -1.9
+    assert relerr(D.dot(a * v1 + b * v2), a * D.dot(v1) + b * D.dot(v2)) < 1e-13
+    assert relerr(D.Tdot(a * w1 + b * w2), a * D.Tdot(w1) + b * D.Tdot(w2)) < 1e-13
+    lhs, rhs = np.dot(D.dot(v1), w1), np.dot(v1, D.Tdot(w1))
+    assert abs(lhs - rhs) <= 1e-11 * max(abs(lhs), np.linalg.norm(D.dot(v1)) * np.linalg.norm(w1))
+    # spot check against scipy on the un-centred, intercept-free part
+    c = np.asarray(X.mean(axis=0)).ravel()
+    rows = rng.choice(n, 2000, replace=False)
+    ref_rows = v1[0] + X[rows] @ v1[1:] - c @ v1[1:]
+    assert relerr(D.dot(v1)[rows], ref_rows) < 1e-12
+    cols = rng.choice(X.shape[1], 2000, replace=False)
+    ref_cols = X[:, cols].T @ w1 - w1.sum() * c[cols]
+    assert relerr(D.Tdot(w1)[1 + cols], ref_cols) < 1e-12
+    # 0/1 entries: sum_i w_i x_ij^2 == sum_i w_i x_ij
+    wt = rng.random(n)
+    uncentred = Sparse(X, center_predictor=False, add_intercept=True, ctx=ctx)
+    assert relerr(uncentred.compute_fisher_info(wt, diag_only=True), uncentred.Tdot(wt)) < 1e-13
