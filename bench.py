@@ -203,7 +203,8 @@ def reference_run(workload, steps, warmup, sample_blocks):
         'kind': kind, 'cores': 1,
         'sample': 'rows 0..%d of %s (%d of %d row blocks, %.0f%% of nnz); %d timed Gibbs iterations after %d warm-up; '
                   'full-size iteration time = (t_sample - t_pside)/fraction + t_pside, t_pside = the p tilted-stable '
-                  'draws (measured separately); scipy SpMV + Cython PG/tilted-stable are single-threaded '
+                  'draws (measured separately); NB the sample needs fewer CG iterations per Gibbs step than the full '
+                  'problem (see mean_n_cg_iter), so this estimate flatters the reference; scipy SpMV + Cython PG/tilted-stable are single-threaded '
                   '(host has %d cores)' % (X.shape[0] - 1, workload, sample_blocks, N_BLOCKS,
                                            100 * frac, steps, warmup, os.cpu_count()),
         'iters_per_s_on_sample': its_sample, 'p_side_seconds': p_side, 'mean_n_cg_iter': n_cg,
