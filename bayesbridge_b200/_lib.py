@@ -59,6 +59,11 @@ SIGNATURES = {
     'bb_linear_rss': (c_int, [c_void_p, P_dbl, P_dbl]),
     'bb_tilted_stable_sample': (c_int, [c_void_p, c_i64, c_dbl, P_dbl, c_u64, c_u64, c_i64, P_dbl]),
     'bb_philox_normal': (c_int, [c_void_p, c_i64, c_int, c_u64, c_u64, c_i64, P_dbl]),
+    'bb_state_init': (c_int, [c_void_p, c_int, P_dbl, c_dbl]),
+    'bb_state_set': (c_int, [c_void_p, P_dbl, P_dbl, P_dbl, c_i64]),
+    'bb_state_get': (c_int, [c_void_p, P_dbl, P_dbl, P_dbl, P_i64]),
+    'bb_cg_sample_resident': (c_int, [c_void_p, P_dbl, c_dbl, c_dbl, c_dbl, c_int, c_u64, c_u64, P_dbl, P_int, P_int, P_dbl]),
+    'bb_local_scale_resident': (c_int, [c_void_p, c_dbl, c_dbl, c_u64, c_u64, P_int, P_dbl]),
     'bb_time_kernel': (c_int, [c_void_p, c_char_p, c_int, c_int, P_dbl]),
 }
 

@@ -55,6 +55,100 @@ class BayesBridge():
     def _pg_on_device(self):
         return isinstance(self.rg.pg, DevicePolyaGamma)
 
+    # ---- device-resident P-side state (lambda, running summaries): SURVEY section 8f-2 -----------------------------
+    def _resident_mode(self, options):
+        """The P-side Gibbs state can stay on the device when every sampler involved is the device one."""
+        import os
+        from .random import DeviceTiltedStable
+        return (options.noise == 'device' and options.coef_sampler_type == 'cg'
+                and self._pg_on_device and isinstance(self.rg.ts, DeviceTiltedStable)
+                and self.prior.bridge_exp != 2 and (self.n_pred - self.n_unshrunk) > 0
+                and os.environ.get('BB_RESIDENT_STATE', '1') != '0')
+
+    def _state_push(self, lscale):
+        lib, mat = _lib.load(), self.model.design._mat
+        summ = self.reg_coef_sampler.regcoef_summarizer.coef_scaled_summarizer
+        _lib.check(lib.bb_state_init(mat, int(self.n_unshrunk), _lib.dptr(_lib.as_f64(self.prior_sd_for_unshrunk)),
+                                     float(self.prior.slab_size)))
+        _lib.check(lib.bb_state_set(mat, _lib.dptr(_lib.as_f64(lscale)), _lib.dptr(_lib.as_f64(summ.stats['mean'])),
+                                    _lib.dptr(_lib.as_f64(summ.stats['square'])), int(summ.n_averaged)))
+
+    def _state_pull(self, want_lscale=True):
+        """Copy lambda and the summaries back into the host objects (end of a run, or when lambda is saved)."""
+        lib, mat = _lib.load(), self.model.design._mat
+        summ = self.reg_coef_sampler.regcoef_summarizer.coef_scaled_summarizer
+        lscale = np.empty(self.n_pred - self.n_unshrunk) if want_lscale else None
+        mean, square = np.empty(self.n_pred), np.empty(self.n_pred)
+        n_avg = ctypes.c_int64()
+        _lib.check(lib.bb_state_get(mat, _lib.dptr(lscale), _lib.dptr(mean), _lib.dptr(square), ctypes.byref(n_avg)))
+        summ.stats['mean'], summ.stats['square'], summ.n_averaged = mean, square, int(n_avg.value)
+        return lscale
+
+    def _resident_iteration(self, obs_prec, gscale, options, need_lscale):
+        """One Gibbs iteration with lambda / summaries on the device. Returns coef, obs_prec, gscale, lscale, logp, info."""
+        lib, design = _lib.load(), self.model.design
+        mat, bridge_exp = design._mat, self.prior.bridge_exp
+        P, k = self.n_pred, self.n_unshrunk
+        if self.model.name == 'linear':
+            _lib.check(lib.bb_set_obs_prec_scalar(mat, float(obs_prec)))
+            omega = None
+        else:
+            omega = None if obs_prec is _RESIDENT else _lib.as_f64(obs_prec)
+        coef, sums = np.empty(P), np.empty(4)
+        n_iter, info = ctypes.c_int(), ctypes.c_int()
+        _lib.check(lib.bb_cg_sample_resident(
+            mat, _lib.dptr(omega), float(gscale), float(bridge_exp), 10e-6 * np.sqrt(P), 500,
+            self.rg.cg.seed, self.rg.cg._next_offset(), _lib.dptr(coef), ctypes.byref(n_iter), ctypes.byref(info),
+            _lib.dptr(sums)))
+        design.dot_count += n_iter.value + 1
+        design.Tdot_count += n_iter.value + 2
+        if info.value != 0:
+            warn("The conjugate gradient algorithm did not achieve the requested tolerance level. You may "
+                 "increase the maxiter or use the dense linear algebra instead.")
+        obs_prec = self.update_obs_precision(coef)
+        # tau | beta from the device-side sums (bayesbridge.py:412-448)
+        abs_pow_sum, n_nonzero, slab_sq_sum, unshrunk_sq_sum = sums
+        lower_bd = .001 / self.prior.compute_power_exp_ave_magnitude(bridge_exp)
+        if options.gscale_update == 'sample':
+            if n_nonzero == 0:
+                gscale = 0
+            else:
+                hyper = self.prior.param['gscale_neg_power']
+                shape = hyper['shape'] + (P - k) / bridge_exp
+                rate = hyper['rate'] + abs_pow_sum
+                phi = self.rg.np_random.gamma(shape, scale=1 / rate)
+                gscale = 1 / phi ** (1 / bridge_exp)
+        elif options.gscale_update == 'optimize':
+            gscale = ((P - k) / bridge_exp / abs_pow_sum) ** - (1 / bridge_exp)
+        if (options.gscale_update is not None) and gscale < lower_bd:
+            gscale = lower_bd
+            warn("The global shrinkage parameter update returned an unreasonably "
+                 "small value. Returning a specified lower bound value instead.")
+        # lambda | tau, beta on the device
+        counts = (ctypes.c_int * 3)()
+        lscale = np.empty(P - k) if need_lscale else None
+        _lib.check(lib.bb_local_scale_resident(mat, float(gscale), bridge_exp / 2, self.rg.ts.seed,
+                                               self.rg.ts._next_offset(), counts, _lib.dptr(lscale)))
+        if counts[0] > 0:
+            raise ValueError('Tilting parameter must be positive.')
+        if counts[1] > 0:
+            warn("Local scale parameter under-flowed. Replacing with a small number.")
+        elif counts[2] > 0:
+            warn("Local scale parameter over-flowed. Replacing with a large number.")
+        # log posterior (bayesbridge.py:480-511) from the same sums; sum|b/tau|^a = sum|b|^a / tau^a
+        if self.model.name == 'logit':
+            loglik = self._loglik_cache[1]
+        else:
+            loglik, _ = self.model.compute_loglik_and_gradient(coef, obs_prec, loglik_only=True)
+        if not np.isinf(self.prior.slab_size):
+            loglik += - .5 * slab_sq_sum
+        prior_logp = - (P - k) * math.log(gscale) - abs_pow_sum / gscale ** bridge_exp
+        prior_logp += - 1 / 2 * unshrunk_sq_sum
+        prior_logp += - np.sum(np.log(self.prior_sd_for_unshrunk[self.prior_sd_for_unshrunk < float('inf')]))
+        hyper = self.prior.param['gscale_neg_power']
+        prior_logp += (hyper['shape'] - 1.) * math.log(gscale) - hyper['rate'] * gscale
+        return coef, obs_prec, gscale, lscale, loglik + prior_logp, {'n_cg_iter': n_iter.value}
+
     # ---- public API ---------------------------------------------------------------------------
     def gibbs_resume(self, prev_mcmc_info, n_add_iter, n_status_update=0, merge=False, prev_samples=None):
         """Continue a chain from the state stored in `prev_mcmc_info` (reference: bayesbridge.py:43-107)."""
@@ -109,7 +203,23 @@ class BayesBridge():
         self.manager.pre_allocate(
             samples, sampling_info, n_iter - n_burnin, thin, params_to_save, options.coef_sampler_type)
 
+        resident = self._resident_mode(options) and n_iter > 0
+        if resident:
+            self._state_push(lscale)
+        save_lscale = 'local_scale' in params_to_save
         for mcmc_iter in range(1, n_iter + 1):
+            if resident:
+                coef, obs_prec, gscale, lscale_new, logp, info = self._resident_iteration(
+                    obs_prec, gscale, options, need_lscale=save_lscale)
+                if lscale_new is not None:
+                    lscale = lscale_new
+                self.manager.store_current_state(
+                    samples, mcmc_iter, n_burnin, thin, coef, lscale, gscale,
+                    self._host_obs_prec_getter(obs_prec), logp, params_to_save)
+                self.manager.store_sampling_info(
+                    sampling_info, info, mcmc_iter, n_burnin, thin, options.coef_sampler_type)
+                self.manager.print_status(n_status_update, mcmc_iter, n_iter)
+                continue
             coef, info = self.update_regress_coef(
                 coef, obs_prec, gscale, lscale, options.coef_sampler_type, noise=options.noise)
             obs_prec = self.update_obs_precision(coef)
@@ -125,6 +235,8 @@ class BayesBridge():
                 sampling_info, info, mcmc_iter, n_burnin, thin, options.coef_sampler_type)
             self.manager.print_status(n_status_update, mcmc_iter, n_iter)
 
+        if resident:
+            lscale = self._state_pull(want_lscale=True)      # lambda and the summaries back into the host objects
         runtime = time.time() - start_time
         ctx = self.model.design.ctx
         if ctx.nranks > 1:

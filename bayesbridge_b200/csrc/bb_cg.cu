@@ -238,33 +238,12 @@ static int compute_z(bb_mat* m) {
     return BB_OK;
 }
 
-extern "C" int bb_cg_sample(bb_mat* m, const double* omega, const double* prior_prec_sqrt,
-                            const double* z, const double* x0, const double* precond_scale,
-                            double atol, int maxiter, int noise_mode,
-                            const double* eps1, const double* eps2, uint64_t seed, uint64_t offset,
-                            double* coef_out, int* n_iter, int* info, double* stats) {
-    BB_ARG(m && prior_prec_sqrt && x0 && precond_scale && coef_out, "null pointer");
-    BB_ARG(noise_mode == BB_NOISE_PHILOX || (eps1 && eps2), "BB_NOISE_INJECT needs eps1 and eps2");
-    BB_ARG(maxiter >= 0, "maxiter");
+// The solver proper: everything between "inputs are on the device" and "coef is in m->out_P".
+// Inputs in device memory: m->pps, m->x0, m->s, m->z, the observation precisions (vector or scalar), and -- for
+// injected noise -- m->eps_n / m->eps_P.  No host synchronisation except the {iter, done} polls.
+static int cg_core(bb_mat* m, double atol, int maxiter, int philox, uint64_t seed, uint64_t offset) {
     bb_ctx* ctx = m->ctx;
     cudaStream_t st = ctx->stream;
-    BB_CUDA(cudaSetDevice(ctx->device));
-    BBTimer timer_(ctx);
-    const size_t Pb = (size_t)m->P * sizeof(double), nb = (size_t)m->n * sizeof(double);
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    if (stats) { BB_CUDA(cudaEventCreate(&ev0)); BB_CUDA(cudaEventCreate(&ev1)); BB_CUDA(cudaEventRecord(ev0, st)); }
-
-    if (omega) { BB_CUDA(cudaMemcpyAsync(m->omega, omega, nb, cudaMemcpyHostToDevice, st)); m->use_omega_scalar = 0; }
-    BB_CUDA(cudaMemcpyAsync(m->pps, prior_prec_sqrt, Pb, cudaMemcpyHostToDevice, st));
-    BB_CUDA(cudaMemcpyAsync(m->x0, x0, Pb, cudaMemcpyHostToDevice, st));
-    BB_CUDA(cudaMemcpyAsync(m->s, precond_scale, Pb, cudaMemcpyHostToDevice, st));
-    if (z) BB_CUDA(cudaMemcpyAsync(m->z, z, Pb, cudaMemcpyHostToDevice, st));
-    else BB_TRY(compute_z(m));
-    const int philox = (noise_mode == BB_NOISE_PHILOX);
-    if (!philox) {
-        BB_CUDA(cudaMemcpyAsync(m->eps_n, eps1, nb, cudaMemcpyHostToDevice, st));
-        BB_CUDA(cudaMemcpyAsync(m->eps_P, eps2, Pb, cudaMemcpyHostToDevice, st));
-    }
     const double* om = m->use_omega_scalar ? nullptr : m->omega;
     // the captured iteration graph bakes pointer arguments: rebuild it when omega switches between
     // the vector and the scalar representation; the scalar VALUE travels through device memory
@@ -334,6 +313,37 @@ extern "C" int bb_cg_sample(bb_mat* m, const double* omega, const double* prior_
     }
     k_cg_final<<<gP, 256, 0, st>>>(m->cg, m->s, m->x, m->P, m->out_P);
     BB_LAUNCHED(ctx);
+    return BB_OK;
+}
+
+extern "C" int bb_cg_sample(bb_mat* m, const double* omega, const double* prior_prec_sqrt,
+                            const double* z, const double* x0, const double* precond_scale,
+                            double atol, int maxiter, int noise_mode,
+                            const double* eps1, const double* eps2, uint64_t seed, uint64_t offset,
+                            double* coef_out, int* n_iter, int* info, double* stats) {
+    BB_ARG(m && prior_prec_sqrt && x0 && precond_scale && coef_out, "null pointer");
+    BB_ARG(noise_mode == BB_NOISE_PHILOX || (eps1 && eps2), "BB_NOISE_INJECT needs eps1 and eps2");
+    BB_ARG(maxiter >= 0, "maxiter");
+    bb_ctx* ctx = m->ctx;
+    cudaStream_t st = ctx->stream;
+    BB_CUDA(cudaSetDevice(ctx->device));
+    BBTimer timer_(ctx);
+    const size_t Pb = (size_t)m->P * sizeof(double), nb = (size_t)m->n * sizeof(double);
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (stats) { BB_CUDA(cudaEventCreate(&ev0)); BB_CUDA(cudaEventCreate(&ev1)); BB_CUDA(cudaEventRecord(ev0, st)); }
+
+    if (omega) { BB_CUDA(cudaMemcpyAsync(m->omega, omega, nb, cudaMemcpyHostToDevice, st)); m->use_omega_scalar = 0; }
+    BB_CUDA(cudaMemcpyAsync(m->pps, prior_prec_sqrt, Pb, cudaMemcpyHostToDevice, st));
+    BB_CUDA(cudaMemcpyAsync(m->x0, x0, Pb, cudaMemcpyHostToDevice, st));
+    BB_CUDA(cudaMemcpyAsync(m->s, precond_scale, Pb, cudaMemcpyHostToDevice, st));
+    if (z) BB_CUDA(cudaMemcpyAsync(m->z, z, Pb, cudaMemcpyHostToDevice, st));
+    else BB_TRY(compute_z(m));
+    const int philox = (noise_mode == BB_NOISE_PHILOX);
+    if (!philox) {
+        BB_CUDA(cudaMemcpyAsync(m->eps_n, eps1, nb, cudaMemcpyHostToDevice, st));
+        BB_CUDA(cudaMemcpyAsync(m->eps_P, eps2, Pb, cudaMemcpyHostToDevice, st));
+    }
+    BB_TRY(cg_core(m, atol, maxiter, philox, seed, offset));
     BB_CUDA(cudaMemcpyAsync(coef_out, m->out_P, Pb, cudaMemcpyDeviceToHost, st));
     if (stats) BB_CUDA(cudaEventRecord(ev1, st));
     timer_.end();
@@ -349,5 +359,180 @@ extern "C" int bb_cg_sample(bb_mat* m, const double* omega, const double* prior_
         stats[0] = m->cg_host->bnorm; stats[1] = m->cg_host->rnorm; stats[2] = (double)ms;
         cudaEventDestroy(ev0); cudaEventDestroy(ev1);
     }
+    return BB_OK;
+}
+
+
+// =====================================================================================================
+// Device-resident P-side Gibbs state.  The local scales lambda and the running summaries
+// (mean, second moment) of the prior-scaled coefficients live on the device; the vectors the CG sampler needs
+// (prior_prec_sqrt, initial guess, preconditioner scale) are formed there, and after the draw the summaries are
+// updated and the few sums the host needs (for tau and the log-posterior) are reduced there.  Every element-wise
+// expression mirrors the host code's rounding (reg_coef_sampler.py:75-96,194-201; cg_sampler.py:123-138;
+// reg_coef_posterior_summarizer.py:12-41,93-124), so the first draw of a chain is bit-identical to the host path.
+__device__ __forceinline__ double prior_scale_dev(double gscale, double lscale, double slab) {
+    double raw = __dmul_rn(gscale, lscale);
+    if (!isinf(slab)) {
+        double r = raw / slab;
+        raw = raw / sqrt(__dadd_rn(1.0, __dmul_rn(r, r)));
+    }
+    return raw;
+}
+
+__global__ void k_state_pre(i64 P, int k, double gscale, double slab, long long n_avg,
+                            const double* __restrict__ prior_sd, const double* __restrict__ lscale,
+                            const double* __restrict__ mean, const double* __restrict__ square,
+                            double* __restrict__ pps, double* __restrict__ x0, double* __restrict__ s) {
+    for (i64 j = (i64)blockIdx.x * blockDim.x + threadIdx.x; j < P; j += (i64)gridDim.x * blockDim.x) {
+        if (j < k) {
+            pps[j] = 1.0 / prior_sd[j];
+            x0[j] = mean[j];
+            double sd = 1.0;
+            if (n_avg > 1) {                       // reg_coef_posterior_summarizer.py:105-124
+                double nn = (double)n_avg;
+                double var = __dmul_rn(nn / (nn - 1.0), __dsub_rn(square[j], __dmul_rn(mean[j], mean[j])));
+                double w = (nn - 1.0) / (nn - 1.0 + 5.0);
+                sd = sqrt(__dadd_rn(__dmul_rn(w, var), __dmul_rn(1.0 - w, 1.0)));
+            }
+            s[j] = __dmul_rn(2.0, sd);
+        } else {
+            double sc = prior_scale_dev(gscale, lscale[j - k], slab);
+            double pj = 1.0 / sc;
+            pps[j] = pj;
+            x0[j] = __dmul_rn(mean[j], sc);
+            s[j] = 1.0 / pj;                       // cg_sampler.py:129  prior_prec_sqrt ** -1
+        }
+    }
+}
+
+// summaries <- new draw; partial sums: [0] sum_{j>=k} |b_j|^alpha, [1] #nonzero among j>=k, [2] sum (b_j/slab)^2,
+// [3] sum_{j<k} (b_j/prior_sd_j)^2
+__global__ void k_state_post(i64 P, int k, double gscale, double slab, double w, double alpha,
+                             const double* __restrict__ prior_sd, const double* __restrict__ lscale,
+                             const double* __restrict__ coef, double* __restrict__ mean, double* __restrict__ square,
+                             double* __restrict__ red /* [4][RED_MAX] */) {
+    __shared__ double sm[33];
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    const bool use_slab = !isinf(slab);
+    for (i64 j = (i64)blockIdx.x * blockDim.x + threadIdx.x; j < P; j += (i64)gridDim.x * blockDim.x) {
+        const double b = coef[j];
+        double theta = b;
+        if (j >= k) {
+            theta = b / prior_scale_dev(gscale, lscale[j - k], slab);
+            double ab = fabs(b);
+            a0 += (alpha == 0.5) ? sqrt(ab) : pow(ab, alpha);
+            a1 += (b != 0.0) ? 1.0 : 0.0;
+        } else {
+            double r = b / prior_sd[j];
+            a3 += r * r;
+        }
+        if (use_slab) { double r = b / slab; a2 += r * r; }
+        // mean <- w*theta + (1-w)*mean ; square <- w*theta^2 + (1-w)*square
+        mean[j] = __dadd_rn(__dmul_rn(theta, w), __dmul_rn(mean[j], 1.0 - w));
+        square[j] = __dadd_rn(__dmul_rn(__dmul_rn(theta, theta), w), __dmul_rn(square[j], 1.0 - w));
+    }
+    a0 = block_sum(a0, sm); a1 = block_sum(a1, sm); a2 = block_sum(a2, sm); a3 = block_sum(a3, sm);
+    if (threadIdx.x == 0) {
+        red[0 * RED_MAX + blockIdx.x] = a0; red[1 * RED_MAX + blockIdx.x] = a1;
+        red[2 * RED_MAX + blockIdx.x] = a2; red[3 * RED_MAX + blockIdx.x] = a3;
+    }
+}
+
+__global__ void k_state_sums(const double* __restrict__ red, int nred, double* __restrict__ sums) {
+    for (int q = 0; q < 4; ++q) {
+        double t = warp_sum_partials(red + q * RED_MAX, nred);
+        if (threadIdx.x == 0) sums[q] = t;
+    }
+}
+
+extern "C" int bb_state_init(bb_mat* m, int n_unshrunk, const double* prior_sd_unshrunk, double slab_size) {
+    BB_ARG(m && n_unshrunk >= 0 && n_unshrunk <= m->P && (n_unshrunk == 0 || prior_sd_unshrunk), "mat/n_unshrunk/prior_sd");
+    bb_ctx* ctx = m->ctx;
+    cudaStream_t st = ctx->stream;
+    BB_CUDA(cudaSetDevice(ctx->device));
+    if (!m->st_lscale) {
+        const size_t Pb = (size_t)(m->P + 1) * sizeof(double);
+        BB_CUDA(cudaMalloc((void**)&m->st_lscale, Pb));
+        BB_CUDA(cudaMalloc((void**)&m->st_mean, Pb));
+        BB_CUDA(cudaMalloc((void**)&m->st_square, Pb));
+        BB_CUDA(cudaMalloc((void**)&m->st_prior_sd, Pb));
+        BB_CUDA(cudaMalloc((void**)&m->st_sums, 8 * sizeof(double)));
+    }
+    m->st_k = n_unshrunk;
+    m->st_slab = slab_size;
+    m->st_n_avg = 0;
+    if (n_unshrunk > 0)
+        BB_CUDA(cudaMemcpyAsync(m->st_prior_sd, prior_sd_unshrunk, (size_t)n_unshrunk * sizeof(double), cudaMemcpyHostToDevice, st));
+    BB_CUDA(cudaStreamSynchronize(st));
+    m->st_ready = 0;
+    return BB_OK;
+}
+
+extern "C" int bb_state_set(bb_mat* m, const double* lscale, const double* mean, const double* square, int64_t n_averaged) {
+    BB_ARG(m && lscale && mean && square && n_averaged >= 0, "null pointer");
+    if (!m->st_lscale) { bb_set_error("bb_state_init first"); return BB_ERR_STATE; }
+    bb_ctx* ctx = m->ctx;
+    cudaStream_t st = ctx->stream;
+    BB_CUDA(cudaSetDevice(ctx->device));
+    const size_t Pb = (size_t)m->P * sizeof(double);
+    BB_CUDA(cudaMemcpyAsync(m->st_lscale, lscale, (size_t)(m->P - m->st_k) * sizeof(double), cudaMemcpyHostToDevice, st));
+    BB_CUDA(cudaMemcpyAsync(m->st_mean, mean, Pb, cudaMemcpyHostToDevice, st));
+    BB_CUDA(cudaMemcpyAsync(m->st_square, square, Pb, cudaMemcpyHostToDevice, st));
+    BB_CUDA(cudaStreamSynchronize(st));
+    m->st_n_avg = n_averaged;
+    m->st_ready = 1;
+    return BB_OK;
+}
+
+extern "C" int bb_state_get(bb_mat* m, double* lscale, double* mean, double* square, int64_t* n_averaged) {
+    BB_ARG(m != nullptr, "mat");
+    if (!m->st_ready) { bb_set_error("device state not set"); return BB_ERR_STATE; }
+    bb_ctx* ctx = m->ctx;
+    cudaStream_t st = ctx->stream;
+    BB_CUDA(cudaSetDevice(ctx->device));
+    const size_t Pb = (size_t)m->P * sizeof(double);
+    if (lscale) BB_CUDA(cudaMemcpyAsync(lscale, m->st_lscale, (size_t)(m->P - m->st_k) * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (mean) BB_CUDA(cudaMemcpyAsync(mean, m->st_mean, Pb, cudaMemcpyDeviceToHost, st));
+    if (square) BB_CUDA(cudaMemcpyAsync(square, m->st_square, Pb, cudaMemcpyDeviceToHost, st));
+    BB_CUDA(cudaStreamSynchronize(st));
+    if (n_averaged) *n_averaged = m->st_n_avg;
+    return BB_OK;
+}
+
+// One coefficient update with the P-side inputs formed on the device (device Philox noise only).
+//   omega: host pointer, or NULL to use the resident precisions;  sums_out[4]: see k_state_post.
+extern "C" int bb_cg_sample_resident(bb_mat* m, const double* omega, double gscale, double bridge_exp,
+                                     double atol, int maxiter, uint64_t seed, uint64_t offset,
+                                     double* coef_out, int* n_iter, int* info, double* sums_out) {
+    BB_ARG(m && coef_out && sums_out && maxiter >= 0 && gscale > 0.0, "null pointer / maxiter / gscale");
+    if (!m->st_ready) { bb_set_error("device state not set (bb_state_init / bb_state_set)"); return BB_ERR_STATE; }
+    bb_ctx* ctx = m->ctx;
+    cudaStream_t st = ctx->stream;
+    BB_CUDA(cudaSetDevice(ctx->device));
+    BBTimer timer_(ctx);
+    const size_t Pb = (size_t)m->P * sizeof(double), nb = (size_t)m->n * sizeof(double);
+    if (omega) { BB_CUDA(cudaMemcpyAsync(m->omega, omega, nb, cudaMemcpyHostToDevice, st)); m->use_omega_scalar = 0; }
+    const int gP = P_grid(m->P);
+    k_state_pre<<<gP, 256, 0, st>>>(m->P, m->st_k, gscale, m->st_slab, m->st_n_avg, m->st_prior_sd, m->st_lscale,
+                                    m->st_mean, m->st_square, m->pps, m->x0, m->s);
+    BB_LAUNCHED(ctx);
+    BB_TRY(compute_z(m));
+    BB_TRY(cg_core(m, atol, maxiter, 1, seed, offset));
+    const double w = 1.0 / (1.0 + (double)m->st_n_avg);
+    k_state_post<<<gP, 256, 0, st>>>(m->P, m->st_k, gscale, m->st_slab, w, bridge_exp, m->st_prior_sd, m->st_lscale,
+                                     m->out_P, m->st_mean, m->st_square, m->red + RED_STATE * RED_MAX);
+    BB_LAUNCHED(ctx);
+    k_state_sums<<<1, 32, 0, st>>>(m->red + RED_STATE * RED_MAX, gP, m->st_sums);
+    BB_LAUNCHED(ctx);
+    BB_CUDA(cudaMemcpyAsync(coef_out, m->out_P, Pb, cudaMemcpyDeviceToHost, st));
+    BB_CUDA(cudaMemcpyAsync(sums_out, m->st_sums, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    timer_.end();
+    BB_CUDA(cudaStreamSynchronize(st));
+    timer_.commit();
+    m->st_n_avg += 1;
+    const int done = m->cg_host->done;
+    m->last_n_iter = m->cg_host->iter;
+    if (n_iter) *n_iter = m->cg_host->iter;
+    if (info) *info = (done == 1 || done == 3) ? 0 : maxiter;
     return BB_OK;
 }

@@ -187,12 +187,15 @@ struct bb_mat {
     int nred_w;                 // number of valid partials in red[RED_W]
     // dense Tdot partials [dense_nblk x p]
     double* dense_part; int dense_nblk;
+    // device-resident P-side Gibbs state (bb_state_*): local scales, running summaries of the scaled coefficients
+    double *st_lscale, *st_mean, *st_square, *st_prior_sd, *st_sums;
+    int st_k, st_ready; double st_slab; long long st_n_avg;
     // cached z = X' kappa for the logit model (kappa = n_success - n_trial/2 is constant)
     double* zk; int zk_valid;
 };
 
-enum { RED_MAX = 1024, RED_SLOTS = 8 };
-enum { RED_SHIFT = 0, RED_W = 1, RED_PQ = 2, RED_RR = 3, RED_BB = 4, RED_MISC = 5, RED_X0 = 6, RED_LL = 7 };
+enum { RED_MAX = 1024, RED_SLOTS = 12 };
+enum { RED_SHIFT = 0, RED_W = 1, RED_PQ = 2, RED_RR = 3, RED_BB = 4, RED_MISC = 5, RED_X0 = 6, RED_LL = 7, RED_STATE = 8 /* ..11 */ };
 
 // device-side op pipeline (all on ctx->stream, no sync)
 //   sv_shift: computes mat->sv (gather vector, p entries) and the shift partials from a P-vector

@@ -455,3 +455,62 @@ extern "C" int bb_linear_rss(bb_mat* m, const double* coef, double* rss) {
     timer_.commit();
     return BB_OK;
 }
+
+
+// ---- local scales on the device (bayesbridge.py:458-478 with the state of bb_state_*) --------------------------
+// lambda_j = sqrt(0.5 / TS(alpha/2, (beta_j / tau)^2)); counts[0] = #(tilt <= 0), [1] = #(lambda == 0), [2] = #(lambda == inf)
+__global__ void k_local_scale(i64 nshrunk, int k, double char_exp, double gscale, const double* __restrict__ coef,
+                              uint64_t seed, uint64_t offset, double* __restrict__ lscale, int* __restrict__ counts) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nshrunk) return;
+    double r = coef[k + i] / gscale;
+    double tilt = __dmul_rn(r, r);
+    if (!(tilt > 0.0)) { atomicAdd(&counts[0], 1); return; }
+    RandStream rs;
+    rs.init(seed, offset, (uint64_t)i, STREAM_TS);
+    double ts = (pow(tilt, char_exp) < 2.0) ? ts_divide_conquer(rs, char_exp, tilt) : ts_double_rejection(rs, char_exp, tilt);
+    double l = sqrt(0.5 / ts);
+    if (l == 0.0) atomicAdd(&counts[1], 1);
+    else if (isinf(l)) atomicAdd(&counts[2], 1);
+    lscale[i] = l;
+}
+// the reference's repair: zeros -> 10e-16 if any zero, else infinities -> 2/tau
+__global__ void k_local_scale_fix(i64 nshrunk, int mode, double gscale, double* __restrict__ lscale) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nshrunk) return;
+    double l = lscale[i];
+    if (mode == 1 && l == 0.0) lscale[i] = 10e-16;
+    if (mode == 2 && isinf(l)) lscale[i] = 2.0 / gscale;
+}
+
+extern "C" int bb_local_scale_resident(bb_mat* m, double gscale, double char_exp, uint64_t seed, uint64_t offset,
+                                       int* counts_out /*[3]*/, double* lscale_out) {
+    BB_ARG(m && counts_out && gscale > 0.0 && char_exp > 0.0 && char_exp < 1.0, "mat/counts/gscale/char_exp");
+    if (!m->st_ready) { bb_set_error("device state not set"); return BB_ERR_STATE; }
+    bb_ctx* ctx = m->ctx;
+    cudaStream_t st = ctx->stream;
+    BB_CUDA(cudaSetDevice(ctx->device));
+    BBTimer timer_(ctx);
+    const i64 ns = m->P - m->st_k;
+    int* d_counts = nullptr;
+    BB_TRY(bb_ctx_scratch(ctx, 0, 4 * sizeof(int), (void**)&d_counts));
+    BB_CUDA(cudaMemsetAsync(d_counts, 0, 4 * sizeof(int), st));
+    if (ns > 0) {
+        k_local_scale<<<(int)((ns + 127) / 128), 128, 0, st>>>(ns, m->st_k, char_exp, gscale, m->out_P, seed, offset,
+                                                              m->st_lscale, d_counts);
+        ctx->launches++;
+    }
+    BB_CUDA(cudaMemcpyAsync(counts_out, d_counts, 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    timer_.end();
+    BB_CUDA(cudaStreamSynchronize(st));
+    timer_.commit();
+    if (counts_out[0] == 0 && (counts_out[1] > 0 || counts_out[2] > 0) && ns > 0) {
+        k_local_scale_fix<<<(int)((ns + 127) / 128), 128, 0, st>>>(ns, counts_out[1] > 0 ? 1 : 2, gscale, m->st_lscale);
+        ctx->launches++;
+    }
+    if (lscale_out) {
+        BB_CUDA(cudaMemcpyAsync(lscale_out, m->st_lscale, (size_t)ns * sizeof(double), cudaMemcpyDeviceToHost, st));
+        BB_CUDA(cudaStreamSynchronize(st));
+    }
+    return BB_OK;
+}

@@ -836,6 +836,7 @@ extern "C" int bb_mat_free(bb_mat* m) {
     bb_slab_free(&m->ftdot);
     void* ptrs[] = {m->csr_ptr, m->csr_idx, m->csr_val, m->csc_ptr, m->csc_idx, m->csc_val, m->col_offset, m->Xd,
                     m->omega, m->n_trial, m->n_success, m->eta, m->w_n, m->u_n, m->eps_n, m->dense_part, m->zk, m->omega_scalar_dev, m->p2p_view_dev,
+                    m->st_lscale, m->st_mean, m->st_square, m->st_prior_sd, m->st_sums,
                     m->v_P, m->sv, m->traw, m->t_P, m->x, m->r, m->pvec, m->q, m->b, m->s, m->D, m->pps, m->z, m->x0,
                     m->eps_P, m->out_P, m->red, m->cg};
     for (void* p : ptrs) if (p) cudaFree(p);

@@ -138,6 +138,23 @@ int  bb_tilted_stable_sample(bb_ctx* ctx, int64_t n, double char_exp, const doub
 int  bb_philox_normal(bb_ctx* ctx, int64_t n, int stream, uint64_t seed, uint64_t offset,
                       int64_t index_offset, double* out);
 
+/* ---- device-resident P-side Gibbs state (reference: reg_coef_sampler.py:60-103,
+ * reg_coef_posterior_summarizer.py:12-124, bayesbridge.py:458-478) -------------------------------------------
+ * The local scales and the running summaries of the prior-scaled coefficients live on the device; the vectors the
+ * CG sampler needs are formed there, so that per Gibbs iteration only coef (out) and a few scalars cross PCIe. */
+int  bb_state_init(bb_mat* mat, int n_unshrunk, const double* prior_sd_unshrunk, double slab_size);
+int  bb_state_set(bb_mat* mat, const double* lscale, const double* mean, const double* square, int64_t n_averaged);
+int  bb_state_get(bb_mat* mat, double* lscale, double* mean, double* square, int64_t* n_averaged);
+/* beta | omega, tau, lambda with device noise; sums_out = {sum|beta_shrunk|^bridge_exp, #nonzero shrunk,
+ * sum (beta/slab)^2, sum (beta_unshrunk/prior_sd)^2}; the summaries are updated with the new draw */
+int  bb_cg_sample_resident(bb_mat* mat, const double* omega, double gscale, double bridge_exp,
+                           double atol, int maxiter, uint64_t seed, uint64_t offset,
+                           double* coef_out, int* n_iter, int* info, double* sums_out);
+/* lambda | tau, beta from the coefficients of the last bb_cg_sample_resident; counts_out = {#tilt<=0, #zeros, #inf};
+ * lscale_out may be NULL */
+int  bb_local_scale_resident(bb_mat* mat, double gscale, double char_exp, uint64_t seed, uint64_t offset,
+                             int* counts_out, double* lscale_out);
+
 /* ---- timing ----------------------------------------------------------------------------- */
 /* runs `reps` launches of one kernel class on resident data and returns mean device ms:
  * what = "dot" | "tdot" | "op" (one application of X' Omega X v) | "pg" | "fisher_diag" */

@@ -147,3 +147,49 @@ def test_api_contract(ctx):
         bb.RegressionModel((y, y), X, family='cox', ctx=ctx)
     with pytest.raises(ValueError):
         bb.RegressionModel(y[:-1], X, family='logit', ctx=ctx)
+
+
+def test_resident_state_path_equals_host_path(ctx, monkeypatch):
+    """The P-side Gibbs state on the device (bb_state_* / bb_cg_sample_resident / bb_local_scale_resident) mirrors the
+    host arithmetic: with the same seeds the first coefficient draw is bit-identical to the host path and the first
+    few iterations agree to CG-amplified round-off (the only difference is the summation order of sum|beta|^alpha,
+    which enters through the Gamma draw of tau); the saved local scales and the summaries are equal too."""
+    bb = _bb()
+    y, X, _ = _c1_like(3000, 200, seed=4)
+    prior = bb.RegressionCoefPrior(bridge_exponent=.5, sd_for_intercept=2., regularizing_slab_size=3.)
+    runs = {}
+    for flag in ('0', '1'):
+        monkeypatch.setenv('BB_RESIDENT_STATE', flag)
+        bridge = bb.BayesBridge(bb.RegressionModel(y, X, 'logit', ctx=ctx), prior)
+        s, info = bridge.gibbs(6, 0, coef_sampler_type='cg', seed=11, params_to_save='all')
+        runs[flag] = (s, info)
+    host, dev = runs['0'][0], runs['1'][0]
+    assert np.array_equal(dev['coef'][:, 0], host['coef'][:, 0])
+    assert np.array_equal(dev['obs_prec'][:, 0], host['obs_prec'][:, 0])
+    assert dev['global_scale'][0] == pytest.approx(host['global_scale'][0], rel=1e-12)
+    assert np.allclose(dev['local_scale'][:, 0], host['local_scale'][:, 0], rtol=1e-10)
+    assert dev['logp'][0] == pytest.approx(host['logp'][0], rel=1e-10)
+    assert np.allclose(dev['coef'][:, 1], host['coef'][:, 1], rtol=0, atol=1e-6)
+    sh = runs['0'][1]['_reg_coef_sampler_state']['regcoef_summarizer'].coef_scaled_summarizer
+    sd = runs['1'][1]['_reg_coef_sampler_state']['regcoef_summarizer'].coef_scaled_summarizer
+    assert sd.n_averaged == sh.n_averaged == 6
+    assert np.allclose(sd.stats['mean'], sh.stats['mean'], rtol=0, atol=1e-4)
+    n_cg_h = runs['0'][1]['_reg_coef_sampling_info']['n_cg_iter']
+    n_cg_d = runs['1'][1]['_reg_coef_sampling_info']['n_cg_iter']
+    assert n_cg_h[0] == n_cg_d[0] and np.max(np.abs(n_cg_h - n_cg_d)) <= 3
+
+
+def test_resident_state_linear_model(ctx, monkeypatch):
+    bb = _bb()
+    rng = np.random.default_rng(2)
+    n, p = 1500, 60
+    X = rng.standard_normal((n, p))
+    y = 0.5 + X[:, :3] @ np.array([1.5, -1., .5]) + rng.standard_normal(n)
+    out = {}
+    for flag in ('0', '1'):
+        monkeypatch.setenv('BB_RESIDENT_STATE', flag)
+        bridge = bb.BayesBridge(bb.RegressionModel(y, X, 'linear', ctx=ctx), bb.RegressionCoefPrior(bridge_exponent=.5))
+        out[flag], _ = bridge.gibbs(4, 0, coef_sampler_type='cg', seed=5, params_to_save='all')
+    assert np.array_equal(out['1']['coef'][:, 0], out['0']['coef'][:, 0])
+    assert np.allclose(out['1']['coef'][:, 1], out['0']['coef'][:, 1], atol=1e-6)
+    assert out['1']['obs_prec'][0] == pytest.approx(out['0']['obs_prec'][0], rel=1e-12)
