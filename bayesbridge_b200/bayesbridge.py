@@ -105,7 +105,7 @@ class BayesBridge():
         if info.value != 0:
             warn("The conjugate gradient algorithm did not achieve the requested tolerance level. You may "
                  "increase the maxiter or use the dense linear algebra instead.")
-        obs_prec = self.update_obs_precision(coef)
+        obs_prec = self.update_obs_precision(coef, coef_is_resident=True)
         # tau | beta from the device-side sums (bayesbridge.py:412-448)
         abs_pow_sum, n_nonzero, slab_sq_sum, unshrunk_sq_sum = sums
         lower_bd = .001 / self.prior.compute_power_exp_ave_magnitude(bridge_exp)
@@ -373,26 +373,28 @@ class BayesBridge():
             y_gaussian, self.model.design, _lib.as_f64(obs_prec), gscale, lscale, sampling_method,
             noise=noise, philox=philox)
 
-    def update_obs_precision(self, coef):
-        """omega | beta (reference: bayesbridge.py:397-410)."""
+    def update_obs_precision(self, coef, coef_is_resident=False):
+        """omega | beta (reference: bayesbridge.py:397-410). coef_is_resident: the device still holds these very
+        coefficients from the CG draw, so they are not uploaded again."""
         if self.model.name == 'linear':
-            scale = self._linear_rss(coef) / 2
+            scale = self._linear_rss(coef, coef_is_resident) / 2
             obs_var = scale / self.rg.np_random.gamma(self.model.n_obs_global / 2, 1)
             return 1 / obs_var
         if self._pg_on_device:
             # fused on the device: eta = X beta, omega ~ PG(n_trial, eta), log-likelihood; omega stays there
             loglik = ctypes.c_double()
             _lib.check(_lib.load().bb_pg_from_coef(
-                self.model.design._mat, _lib.dptr(_lib.as_f64(coef)),
+                self.model.design._mat, None if coef_is_resident else _lib.dptr(_lib.as_f64(coef)),
                 self.rg.pg.seed, self.rg.pg._next_offset(), None, ctypes.byref(loglik)))
             self.model.design.dot_count += 1
             self._loglik_cache = (coef, loglik.value)
             return _RESIDENT
         return self.rg.polya_gamma(self.model.n_trial.astype(np.intc), self.model.design.dot(coef))
 
-    def _linear_rss(self, coef):
+    def _linear_rss(self, coef, coef_is_resident=False):
         rss = ctypes.c_double()
-        _lib.check(_lib.load().bb_linear_rss(self.model.design._mat, _lib.dptr(_lib.as_f64(coef)), ctypes.byref(rss)))
+        _lib.check(_lib.load().bb_linear_rss(
+            self.model.design._mat, None if coef_is_resident else _lib.dptr(_lib.as_f64(coef)), ctypes.byref(rss)))
         self.model.design.dot_count += 1
         return rss.value
 

@@ -395,7 +395,9 @@ static int N_grid(i64 n) { i64 g = (n + 1023) / 1024; if (g < 1) g = 1; if (g > 
 // eta = X coef into m->eta (device)
 static int linear_predictor(bb_mat* m, const double* coef) {
     bb_ctx* ctx = m->ctx;
-    BB_CUDA(cudaMemcpyAsync(m->v_P, coef, (size_t)m->P * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    // coef == NULL: the coefficients of the last CG draw, still resident in m->out_P
+    if (coef) BB_CUDA(cudaMemcpyAsync(m->v_P, coef, (size_t)m->P * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    else BB_CUDA(cudaMemcpyAsync(m->v_P, m->out_P, (size_t)m->P * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     BB_TRY(bb_op_prepare(m, m->v_P, nullptr));
     BB_TRY(bb_op_dot(m, 0));
     BB_CUDA(cudaMemcpyAsync(m->eta, m->u_n, (size_t)m->n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -404,7 +406,7 @@ static int linear_predictor(bb_mat* m, const double* coef) {
 
 extern "C" int bb_pg_from_coef(bb_mat* m, const double* coef, uint64_t seed, uint64_t offset,
                                double* omega_out, double* loglik) {
-    BB_ARG(m && coef, "mat/coef");
+    BB_ARG(m != nullptr, "mat");      // coef == NULL: use the coefficients of the last CG draw (resident)
     if (!m->has_outcome || m->is_linear) { bb_set_error("bb_pg_from_coef needs a logit outcome (bb_set_outcome)"); return BB_ERR_STATE; }
     bb_ctx* ctx = m->ctx;
     cudaStream_t st = ctx->stream;
@@ -436,7 +438,7 @@ extern "C" int bb_pg_from_coef(bb_mat* m, const double* coef, uint64_t seed, uin
 }
 
 extern "C" int bb_linear_rss(bb_mat* m, const double* coef, double* rss) {
-    BB_ARG(m && coef && rss, "mat/coef/rss");
+    BB_ARG(m && rss, "mat/rss");          // coef == NULL: resident coefficients of the last CG draw
     if (!m->has_outcome) { bb_set_error("bb_linear_rss needs bb_set_outcome"); return BB_ERR_STATE; }
     bb_ctx* ctx = m->ctx;
     cudaStream_t st = ctx->stream;

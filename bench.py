@@ -379,7 +379,10 @@ def main():
         'warmup': args.warmup, 'ms_per_step': dev_ms / K, 'higher_is_better': True, 'scaling': 'strong',
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': dict(config, nnz=int(nnz_total)),
         'e2e': {'value': e2e, 'unit': 'iter/s', 'ms_per_step_wall': 1000 * wall / K,
-                'h2d_bytes_per_step': int(8 * (4 * P + (P - 1))), 'd2h_bytes_per_step': int(8 * (P + (P - 1)) + 64),
+                # device-resident P-side state: per step only the coefficient draw (P doubles) and a few scalars
+                # come back; nothing P-length goes up (BB_RESIDENT_STATE=0: 4P+(P-1) doubles up, 2P-1 down)
+                'h2d_bytes_per_step': 64 if os.environ.get('BB_RESIDENT_STATE', '1') != '0' else int(8 * (4 * P + (P - 1))),
+                'd2h_bytes_per_step': int(8 * P + 128) if os.environ.get('BB_RESIDENT_STATE', '1') != '0' else int(8 * (P + (P - 1)) + 64),
                 'api': 'BayesBridge.gibbs_resume (public API; host numpy state in, samples out)'},
         'gpu_launches': int(launches),
         'mean_n_cg_iter': float(np.mean(n_cg)),

@@ -126,7 +126,8 @@ int  bb_cg_sample(bb_mat* mat, const double* omega, const double* prior_prec_sqr
 int  bb_pg_sample(bb_ctx* ctx, int64_t n, const int32_t* shape, const double* tilt,
                   uint64_t seed, uint64_t offset, int64_t index_offset, double* out);
 /* fused Gibbs step: eta = X coef; omega ~ PG(n_trial, eta) kept resident; loglik = sum(n_success*eta
- * - n_trial*log(1+e^eta)) over all shards.  omega_out may be NULL. */
+ * - n_trial*log(1+e^eta)) over all shards.  omega_out may be NULL; coef may be NULL = the coefficients of the last
+ * CG draw, still resident on the device. */
 int  bb_pg_from_coef(bb_mat* mat, const double* coef, uint64_t seed, uint64_t offset,
                      double* omega_out, double* loglik);
 /* linear model: sum of squared residuals ||y - X coef||^2 over all shards */
