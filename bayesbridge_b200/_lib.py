@@ -140,6 +140,10 @@ class Context:
         self.handle = handle
         self.device = int(device)
         self.nranks, self.rank = 1, 0
+        # tuning knobs of the library can be preset from the environment, e.g. BB_OPT_SPMV_STAGE=2
+        for key, val in os.environ.items():
+            if key.startswith('BB_OPT_'):
+                check(lib.bb_set_option(handle, key[len('BB_OPT_'):].lower().encode(), int(val)))
 
     @classmethod
     def default(cls):
