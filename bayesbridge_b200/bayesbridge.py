@@ -185,6 +185,11 @@ class BayesBridge():
             options = SamplerOptions.pick_default_and_create(
                 coef_sampler_type, options, self.model.name, self.model.design)
         if not _add_iter_mode:
+            ctx = self.model.design.ctx
+            if seed is None and ctx.nranks > 1:
+                # the P-side state is replicated: every rank must draw the same tau, so they must share a seed
+                mine = float(np.random.SeedSequence().generate_state(1)[0]) if ctx.rank == 0 else 0.0
+                seed = int(ctx.allreduce_host(np.array([mine]))[0])
             self.rg.set_seed(seed)
             self.reg_coef_sampler = SparseRegressionCoefficientSampler(
                 self.n_pred, self.prior_sd_for_unshrunk, options.coef_sampler_type,
@@ -389,7 +394,8 @@ class BayesBridge():
             self.model.design.dot_count += 1
             self._loglik_cache = (coef, loglik.value)
             return _RESIDENT
-        return self.rg.polya_gamma(self.model.n_trial.astype(np.intc), self.model.design.dot(coef))
+        return self.rg.polya_gamma(self.model.n_trial.astype(np.intc), self.model.design.dot(coef),
+                                   index_offset=getattr(self.model.design, 'row_offset', 0))
 
     def _linear_rss(self, coef, coef_is_resident=False):
         rss = ctypes.c_double()
