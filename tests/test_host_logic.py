@@ -147,3 +147,33 @@ def test_sharded_operator_algebra_gloo_world2():
         pr.join(timeout=60)
     assert sorted(r for r, _ in res) == [0, 1]
     assert all(err < 1e-13 for _, err in res)
+
+
+def test_bench_generator_is_block_deterministic():
+    """bench.py builds C4 from 50 seeded row blocks so that every N sees the same matrix: a rank's rows must not
+    depend on which other blocks the process generated."""
+    import bench
+    n, p, dens = 5000, 400, 0.01
+    full, y_full = bench.generate_rows(range(bench.N_BLOCKS), n, p, dens)
+    part, y_part = bench.generate_rows(range(10, 20), n, p, dens)
+    lo, hi = n * 10 // bench.N_BLOCKS, n * 20 // bench.N_BLOCKS
+    assert (full[lo:hi] != part).nnz == 0 and np.array_equal(y_full[lo:hi], y_part)
+    assert full.indices.dtype == np.int32 and np.all(full.data == 1.0)
+    assert abs(full.nnz / (n * p) - dens) < 0.5 * dens
+
+
+def test_reference_arm_line_has_the_contract_keys():
+    """`bench.py --impl reference` (the reference's own CPU sampler from oracle/_ref, or the oracle port) prints one JSON
+    line with the keys the driver expects; run on the smallest workload so that it takes seconds."""
+    import json
+    import subprocess
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--workload', 'C1',
+                          '--steps', '3', '--warmup', '1', '--ref-blocks', '10'],
+                         capture_output=True, text=True, timeout=300, cwd=ROOT)
+    line = [l for l in out.stdout.splitlines() if l.startswith('{')][-1]
+    d = json.loads(line)
+    assert d['impl'] == 'reference' and d['metric'] == 'gibbs_iters_per_sec' and d['value'] > 0
+    for key in ('unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling', 'config',
+                'cpu_baseline', 'e2e'):
+        assert key in d
+    assert d['cpu_baseline']['kind'] in ('reference', 'port') and d['e2e']['h2d_bytes_per_step'] == 0
