@@ -39,6 +39,7 @@ extern "C" int bb_init(int device, bb_ctx** out) {
     c->smem_optin = prop.sharedMemPerBlockOptin;
     c->opt_spmv_stage = 1;
     c->opt_slab_width = 0;
+    c->opt_bank_permute = 1;
     c->opt_cg_chunk = 0;
     c->opt_use_graph = 1;
     c->opt_allreduce_p2p = 1;
@@ -79,6 +80,7 @@ extern "C" int bb_sync(bb_ctx* c) {
 static i64* option_slot(bb_ctx* c, const char* name) {
     if (!strcmp(name, "spmv_stage")) return &c->opt_spmv_stage;
     if (!strcmp(name, "slab_width")) return &c->opt_slab_width;
+    if (!strcmp(name, "bank_permute")) return &c->opt_bank_permute;
     if (!strcmp(name, "cg_chunk")) return &c->opt_cg_chunk;
     if (!strcmp(name, "use_graph")) return &c->opt_use_graph;
     if (!strcmp(name, "allreduce_p2p")) return &c->opt_allreduce_p2p;

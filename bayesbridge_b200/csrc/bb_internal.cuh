@@ -70,6 +70,7 @@ struct bb_ctx {
     // options
     i64 opt_spmv_stage;    // 1: stage the gather vector in shared memory; 0: gather through L2
     i64 opt_slab_width;    // max doubles of the gather vector staged per CTA (0 = auto)
+    i64 opt_bank_permute;  // 1: reorder nnz inside (segment x tile) pieces so that staged gathers avoid bank conflicts
     i64 opt_cg_chunk;      // CG iterations enqueued between host checks (0 = adaptive)
     i64 opt_use_graph;     // capture the CG iteration chunk into a CUDA graph
     // communicator (NCCL via dlopen)

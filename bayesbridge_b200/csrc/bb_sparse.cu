@@ -118,6 +118,59 @@ __global__ void k_compact_meta(const TileMeta* __restrict__ tiles, int ntiles, i
     if (t < ntiles) tmeta[t] = make_int2(tiles[t].vlo, tiles[t].vhi - tiles[t].vlo);
 }
 
+// Bank-aware ordering of the nnz (build time, one thread per tile).  The SpMV kernel gathers the staged vector
+// with one 8-byte shared-memory load per nnz: load j of lane l reads element 8l + j of the tile, and the 16
+// lanes of a half-warp are served together, one wavefront per distinct address that falls into the same
+// 8-byte bank (index mod 16).  With the nnz in canonical order the gather indices of those 16 lanes are
+// random, so a load needs ~3 wavefronts per half-warp instead of 1, and the gathers are what saturates the
+// shared-memory pipe.  A sum does not depend (beyond rounding) on the order of its terms, so the nnz of a
+// piece (one segment inside one tile) may be stored in any order: for every position, in order, pick among
+// the piece's remaining nnz one whose bank is least used so far by the (load j, half-warp) group of that
+// position.  Pieces, cut points and tile boundaries do not move; the canonical CSR/CSC images are separate
+// arrays and stay bit-exact.
+__global__ void __launch_bounds__(64)
+k_bank_permute(const TileMeta* __restrict__ tiles, int ntiles, const int* __restrict__ ptr, i64 V,
+               const int* __restrict__ idx_in, const double* __restrict__ val_in,
+               int* __restrict__ idx_out, double* __restrict__ val_out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntiles) return;
+    const int start = tiles[t].start, len = tiles[t].end - tiles[t].start;
+    if (len <= 1) return;
+    int e[SPMV_TILE];
+    unsigned char src[SPMV_TILE];
+    unsigned char occ[2 * SPMV_ITEMS * 16];
+    for (int k = 0; k < len; ++k) { e[k] = idx_in[start + k]; src[k] = (unsigned char)k; }
+    for (int k = 0; k < 2 * SPMV_ITEMS * 16; ++k) occ[k] = 0;
+    // virtual segment that contains nnz `start`: the largest v < V with ptr[v] <= start
+    i64 v = 0;
+    {
+        i64 lo = 0, hi = V;
+        while (hi - lo > 1) { i64 mid = (lo + hi) >> 1; if (ptr[mid] <= start) lo = mid; else hi = mid; }
+        v = lo;
+    }
+    int a = 0;
+    while (a < len) {
+        while (v + 1 < V && ptr[v + 1] <= start + a) ++v;
+        int b = min(ptr[v + 1] - start, len);
+        if (b <= a) b = len;                                  // defensive: never loop on an empty piece
+        for (int k = a; k < b; ++k) {
+            unsigned char* og = occ + ((((k & (SPMV_ITEMS - 1)) << 1) | (k >> 7)) << 4);
+            int best = k, bo = og[e[k] & 15];
+            for (int m = k + 1; bo > 0 && m < b; ++m) {
+                int o = og[e[m] & 15];
+                if (o < bo) { bo = o; best = m; }
+            }
+            int te = e[k]; e[k] = e[best]; e[best] = te;
+            unsigned char ts = src[k]; src[k] = src[best]; src[best] = ts;
+            og[e[k] & 15] = (unsigned char)(bo + 1);
+        }
+        a = b;
+    }
+    for (int k = 0; k < len; ++k) idx_out[start + k] = e[k];
+    if (val_in != nullptr)
+        for (int k = 0; k < len; ++k) val_out[start + k] = val_in[start + src[k]];
+}
+
 // ------------------------------------------------------------------------------------------
 // The SpMV kernel.  The tile sequence (all slabs concatenated) is cut into gridDim.x equal contiguous
 // ranges, one per CTA (grid = #SMs, one CTA per SM): perfectly balanced in nnz.  A CTA walks its
@@ -277,13 +330,14 @@ k_seg_spmv(const int* __restrict__ ptr, const int* __restrict__ idx, const doubl
                 // late prefetch (values): the product registers are dead now
                 if (!BINARY && tn < sec_end) tile_fetch_val(rv, st1, en1, val, lane);
                 // ... and across lanes (segments start at lanes that contain a head)
+                // (lane l takes the partial sum of lane l-d unless a head lies in lanes (l-d, l]: one ballot
+                //  replaces a shuffled flag per step)
                 double x = run;
-                unsigned hf = (f != 0u) ? 1u : 0u;
+                const unsigned hm = __ballot_sync(0xffffffffu, f != 0u);
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
                     double y = __shfl_up_sync(0xffffffffu, x, d);
-                    unsigned g = __shfl_up_sync(0xffffffffu, hf, d);
-                    if (lane >= d) { if (!hf) x += y; hf |= g; }
+                    if (lane >= d && ((hm >> (lane - d + 1)) & ((1u << d) - 1u)) == 0u) x += y;
                 }
                 double carry = __shfl_up_sync(0xffffffffu, x, 1);
                 if (lane == 0) carry = 0.0;
@@ -667,6 +721,26 @@ static int build_slab_format(bb_ctx* ctx, const int* cptr, const int* cidx, cons
     BB_CUDA(cudaMalloc((void**)&f->tmeta, tiles.size() * sizeof(int2)));
     k_compact_meta<<<(f->ntiles + TB - 1) / TB, TB, 0, st>>>(f->tiles, f->ntiles, f->tmeta);
     ctx->launches += 1;
+    if (f->owns_arrays && staged && ctx->opt_bank_permute != 0 && nnz > 0) {
+        // reorder the nnz inside every (segment x tile) piece for conflict-free staged gathers
+        static_assert(SPMV_TILE == 256 && SPMV_ITEMS == 8, "k_bank_permute assumes 32 lanes x 8 nnz per tile");
+        int* idx_tmp = nullptr;
+        double* val_tmp = nullptr;
+        size_t cnt = (size_t)(padded_total + 8);
+        BB_CUDA(cudaMalloc((void**)&idx_tmp, cnt * sizeof(int)));
+        BB_CUDA(cudaMemcpyAsync(idx_tmp, f->idx, cnt * sizeof(int), cudaMemcpyDeviceToDevice, st));
+        if (f->val) {
+            cudaError_t e = cudaMalloc((void**)&val_tmp, cnt * sizeof(double));
+            if (e != cudaSuccess) { cudaFree(idx_tmp); bb_set_error("slab build: %s", cudaGetErrorString(e)); return BB_ERR_CUDA; }
+            BB_CUDA(cudaMemcpyAsync(val_tmp, f->val, cnt * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        }
+        k_bank_permute<<<(f->ntiles + 63) / 64, 64, 0, st>>>(f->tiles, f->ntiles, f->ptr, V, idx_tmp, val_tmp, f->idx, f->val);
+        ctx->launches += 1;
+        cudaError_t e = cudaStreamSynchronize(st);
+        cudaFree(idx_tmp);
+        if (val_tmp) cudaFree(val_tmp);
+        if (e != cudaSuccess) { bb_set_error("bank permute: %s", cudaGetErrorString(e)); return BB_ERR_CUDA; }
+    }
     BB_CUDA(cudaMalloc((void**)&f->slab_tile0, ((size_t)nslab + 1) * sizeof(int)));
     BB_CUDA(cudaMalloc((void**)&f->slab_nnz0, ((size_t)nslab + 1) * sizeof(int)));
     BB_CUDA(cudaMemcpyAsync(f->slab_tile0, slab_tile0.data(), ((size_t)nslab + 1) * sizeof(int), cudaMemcpyHostToDevice, st));

@@ -363,7 +363,7 @@ def main():
     try:
         if args.workload == 'C4' and world == 1:
             import csv
-            rows = list(csv.reader(open(os.path.join(ROOT, 'profiles', 'r01_ncu_spmv_v5_c4.csv'))))
+            rows = list(csv.reader(open(os.path.join(ROOT, 'profiles', 'r01_ncu_spmv_v6_c4.csv'))))
             hdr, units = rows[0], rows[1]
             row = rows[2 + (1 if dom == 'spmv_tdot' else 0)]
             scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
@@ -371,7 +371,7 @@ def main():
             for name in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
                 i = hdr.index(name)
                 traffic += float(row[i].replace(',', '')) * scale[units[i]]
-            traffic_src = 'profiles/r01_ncu_spmv_v5_c4.csv (ncu --set full, same kernel and matrix)'
+            traffic_src = 'profiles/r01_ncu_spmv_v6_c4.csv (ncu --set full, same kernel and matrix)'
     except Exception:
         traffic, traffic_src = None, None
     line = {
