@@ -78,6 +78,30 @@ def test_products_are_bit_reproducible(ctx):
     assert np.array_equal(D.Tdot(w), D.Tdot(w))
 
 
+def test_bank_aware_order_changes_rounding_only(ctx):
+    """The nnz order inside the slab copies (option bank_permute) is a storage detail: the canonical
+    CSR / CSC images stay bit-exact and the products move by rounding only."""
+    Sparse, _ = _designs()
+    X = random_sparse(60000, 3000, 0.004, seed=11)
+    w = np.random.default_rng(2).standard_normal(60000)
+    out = {}
+    ctx.set_option('slab_width', 1024)
+    try:
+        for perm in (1, 0):
+            ctx.set_option('bank_permute', perm)
+            D = Sparse(X, center_predictor=True, add_intercept=True, ctx=ctx, pattern_only=False)
+            v = np.random.default_rng(3).standard_normal(D.shape[1])
+            out[perm] = (D.dot(v), D.Tdot(w), D.export_csr() + D.export_csc())
+    finally:
+        ctx.set_option('bank_permute', 1)
+        ctx.set_option('slab_width', 0)
+    assert relerr(out[1][0], out[0][0]) < 1e-14 and relerr(out[1][1], out[0][1]) < 1e-14
+    for a, b in zip(out[1][2], out[0][2]):
+        assert np.array_equal(a, b)
+    C = X.tocsc()
+    assert np.array_equal(out[1][2][4], C.indices) and np.array_equal(out[1][2][5], C.data)
+
+
 @pytest.mark.parametrize('n,p', [(200, 30), (5000, 1300)])
 def test_dense_products_vs_oracle(ctx, n, p):
     _, Dense = _designs()
