@@ -1,0 +1,520 @@
+// PROTOTYPE of the next SpMV kernel ("v7") + a standalone self-test / micro-benchmark.
+//
+// STATUS: compiles for sm_100a; HAS NOT RUN ON A GPU YET.  Not built into libbbgpu.so, not used by the product.
+// The algorithm is pinned on the CPU by experimental/emulate_spmv_v7.py (tests/test_spmv_v7_emulator.py); this file
+// is its CUDA translation, kept standalone so that the first GPU minutes of the next round can go into
+//     nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -o /tmp/spmv_v7 experimental/spmv_v7.cu
+//     /tmp/spmv_v7 1000000 100000 0.001 1        (rows, columns, density, pattern-only [, bank order, --host, W])
+// `--host` as the 6th argument runs a CPU transliteration of the kernel on the same format instead (no GPU needed).
+// which builds the format on the host, checks the kernel against a CPU segmented sum and times it.
+//
+// What changes against k_seg_spmv (v6, bb_sparse.cu) and why (profiles/r01_spmv_history.md, "instruction budget"):
+//   * 512-nnz tiles, 16 nnz per lane: the cross-lane scan, the prefetch and the loop control are paid per tile.
+//   * Head flags are static metadata (one u32 per lane and tile: 16 flag bits + the number of heads in the lower
+//     lanes) instead of a shared-memory bitmap rebuilt from the cut points with atomics for every tile.
+//   * Piece sums leave from registers: a lane stores the sum that ends at each of its heads straight to the output
+//     (the first head of a lane waits for the carry of the lower lanes), so the 2 KB per-warp prefix buffer, its 16
+//     STS.64 and the cut-point gather are gone -- the shared-memory pipe only serves the gathers of the staged vector.
+//   * The output is COMPACT: tile t owns the consecutive slots [tile_out[t], tile_out[t] + n_heads[t]]: slot 0 is the
+//     piece continued from the previous tile, slot o the segment started by the tile's o-th head.  No segment ids in
+//     the hot loop, and empty virtual segments (a rare column has no entry in most row slabs) cost nothing.  The
+//     consumer kernels map a virtual segment to its slot through cslot[v] (-1 = empty).
+// Summation order per piece is the same as in v6 (serial inside the lane, tree across lanes, carry added last).
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include <vector>
+
+typedef long long i64;
+#ifndef V7_CARRY_RED
+#define V7_CARRY_RED 1
+#endif
+constexpr int V7_THREADS = 1024, V7_WARPS = V7_THREADS / 32, V7_ITEMS = 16, V7_TILE = 32 * V7_ITEMS;
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "%s:%d %s\n", __FILE__, __LINE__, cudaGetErrorString(e_)); exit(2); } } while (0)
+
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+
+__device__ __forceinline__ void fetch_idx(int (&ri)[V7_ITEMS], const int* __restrict__ idx, int start, int end, int lane) {
+    if (end - start == V7_TILE) {
+        const int4* ip = reinterpret_cast<const int4*>(idx + start) + lane * 4;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            int4 a = ip[q];
+            ri[4 * q] = a.x; ri[4 * q + 1] = a.y; ri[4 * q + 2] = a.z; ri[4 * q + 3] = a.w;
+        }
+    } else if (end > start) {
+#pragma unroll
+        for (int j = 0; j < V7_ITEMS; ++j) ri[j] = idx[min(start + lane * V7_ITEMS + j, end - 1)];
+    }
+}
+
+// One tile.  `out_tile` = out + tile_out[t]; slot 0 = piece continued from the previous tile.
+template <bool BINARY, bool PARTIAL>
+__device__ __forceinline__ void tile_body(const int (&ri)[V7_ITEMS], const double* __restrict__ val, int start, int len,
+                                          unsigned meta, int nheads, int lane, unsigned sbase, double* __restrict__ out_tile) {
+    const unsigned f = meta & 0xffffu;
+    unsigned o = meta >> 16;                      // heads in the lower lanes = ordinal of the piece open at lane start
+    double g[V7_ITEMS];
+#pragma unroll
+    for (int j = 0; j < V7_ITEMS; ++j) g[j] = lds_f64(sbase + ((unsigned)ri[j] << 3));
+    if (!BINARY) {
+#pragma unroll
+        for (int j = 0; j < V7_ITEMS; ++j) {
+            const int q = lane * V7_ITEMS + j;
+            g[j] *= val[start + (PARTIAL ? min(q, len - 1) : q)];
+        }
+    }
+    // Branch-free serial pass.  At a head the running sum is the total of the piece that ends there and is stored to
+    // the piece's slot right away (predicated store, running 32-bit slot offset).  For the FIRST head of a lane that
+    // value still lacks the carry of the lower lanes: it is added after the scan, either by a fire-and-forget
+    // red.global.add.f64 onto the stored value (V7_CARRY_RED: one store + one add per slot, so the result is the
+    // exactly rounded sum of the two, deterministic) or by keeping the lane's leading sum in a register.
+    double run = 0.0;
+#if !V7_CARRY_RED
+    double first_run = 0.0;
+    const int jf = __ffs((int)f) - 1;             // position of the lane's first head (-1: none)
+#endif
+    double* op = out_tile + o;                    // slot of the piece open at the current position
+#pragma unroll
+    for (int j = 0; j < V7_ITEMS; ++j) {
+        double gj = g[j];
+        if (PARTIAL) gj = (lane * V7_ITEMS + j < len) ? gj : 0.0;
+#if !V7_CARRY_RED
+        first_run = (j == jf) ? run : first_run;
+#endif
+        // head at j:  *op++ = run; run = gj      else:  run += gj      (one predicate, no branch)
+        asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t.reg .f64 s;\n\t"
+                     "and.b32 t, %2, %3;\n\tsetp.ne.u32 p, t, 0;\n\t"
+                     "@p st.global.f64 [%1], %0;\n\t@p add.u64 %1, %1, 8;\n\t"
+                     "add.rn.f64 s, %0, %4;\n\tselp.f64 %0, %4, s, p;\n\t}"
+                     : "+d"(run), "+l"(op) : "r"(f), "r"(1u << j), "d"(gj) : "memory");
+    }
+    // segmented inclusive scan of the lane tails across the warp
+    const unsigned hm = __ballot_sync(0xffffffffu, f != 0u);
+    double x = run;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        double y = __shfl_up_sync(0xffffffffu, x, d);
+        if (lane >= d && ((hm >> (lane - d + 1)) & ((1u << d) - 1u)) == 0u) x += y;
+    }
+    double carry = __shfl_up_sync(0xffffffffu, x, 1);
+    if (lane == 0) carry = 0.0;
+#if V7_CARRY_RED
+    if (f != 0u) asm volatile("red.global.add.f64 [%0], %1;" : : "l"(out_tile + (meta >> 16)), "d"(carry) : "memory");
+#else
+    if (f != 0u) out_tile[meta >> 16] = first_run + carry;            // the piece that ends at the lane's first head
+#endif
+    if (lane == 31) out_tile[nheads] = (f != 0u) ? run : run + carry; // the piece that reaches the end of the tile
+}
+
+// Fast path for tiles with at most V7_SLOTS - 1 heads: the piece sums are parked in a small per-warp shared buffer
+// (32-bit addresses: one predicated STS + one predicated add per element instead of a 64-bit pointer chain), the lane
+// that owns a piece's first head adds the carry to its own entry, and the warp then writes the tile's slots
+// to global memory with ONE coalesced store instead of ~26 scattered 8-byte ones.
+constexpr int V7_SLOTS = 64;
+static_assert(V7_SLOTS == 64, "the copy-out below handles exactly two slots per lane");
+template <bool BINARY, bool PARTIAL>
+__device__ __forceinline__ void tile_body_staged(const int (&ri)[V7_ITEMS], const double* __restrict__ val, int start, int len,
+                                                 unsigned meta, int nheads, int lane, unsigned sbase, unsigned wbuf,
+                                                 double* __restrict__ out_tile) {
+    const unsigned f = meta & 0xffffu;
+    double g[V7_ITEMS];
+#pragma unroll
+    for (int j = 0; j < V7_ITEMS; ++j) g[j] = lds_f64(sbase + ((unsigned)ri[j] << 3));
+    if (!BINARY) {
+#pragma unroll
+        for (int j = 0; j < V7_ITEMS; ++j) {
+            const int q = lane * V7_ITEMS + j;
+            g[j] *= val[start + (PARTIAL ? min(q, len - 1) : q)];
+        }
+    }
+    double run = 0.0;
+    const unsigned first = wbuf + ((meta >> 16) << 3);   // shared address of the slot open at the start of the lane
+    unsigned sp = first;
+#pragma unroll
+    for (int j = 0; j < V7_ITEMS; ++j) {
+        double gj = g[j];
+        if (PARTIAL) gj = (lane * V7_ITEMS + j < len) ? gj : 0.0;
+        // head at j:  *sp++ = run; run = gj      else:  run += gj
+        asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t.reg .f64 s;\n\t"
+                     "and.b32 t, %2, %3;\n\tsetp.ne.u32 p, t, 0;\n\t"
+                     "@p st.shared.f64 [%1], %0;\n\t@p add.u32 %1, %1, 8;\n\t"
+                     "add.rn.f64 s, %0, %4;\n\tselp.f64 %0, %4, s, p;\n\t}"
+                     : "+d"(run), "+r"(sp) : "r"(f), "r"(1u << j), "d"(gj) : "memory");
+    }
+    const unsigned hm = __ballot_sync(0xffffffffu, f != 0u);
+    double x = run;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        double y = __shfl_up_sync(0xffffffffu, x, d);
+        if (lane >= d && ((hm >> (lane - d + 1)) & ((1u << d) - 1u)) == 0u) x += y;
+    }
+    double carry = __shfl_up_sync(0xffffffffu, x, 1);
+    if (lane == 0) carry = 0.0;
+    if (f != 0u) {                                        // this lane parked the piece that ends at its first head
+        double lead;
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(lead) : "r"(first) : "memory");
+        lead += carry;
+        asm volatile("st.shared.f64 [%0], %1;" : : "r"(first), "d"(lead) : "memory");
+    }
+    if (lane == 31) {                                     // the piece that reaches the end of the tile
+        const double last = (f != 0u) ? run : run + carry;
+        asm volatile("st.shared.f64 [%0], %1;" : : "r"(wbuf + ((unsigned)nheads << 3)), "d"(last) : "memory");
+    }
+    __syncwarp();
+    // nheads < V7_SLOTS = 64: at most two coalesced stores per lane
+    if (lane <= nheads) out_tile[lane] = lds_f64(wbuf + ((unsigned)lane << 3));
+    if (lane + 32 <= nheads) out_tile[lane + 32] = lds_f64(wbuf + ((unsigned)(lane + 32) << 3));
+    __syncwarp();                                         // the buffer is reused by the next tile
+}
+
+template <bool BINARY>
+__global__ void __launch_bounds__(V7_THREADS, 1)
+k_seg_spmv_v7(const int* __restrict__ idx, const double* __restrict__ val, const unsigned* __restrict__ lane_meta,
+              const int2* __restrict__ tile_out /* {first slot, n_heads} */, const int* __restrict__ slab_tile0,
+              const int* __restrict__ slab_nnz0, const int* __restrict__ slab_nnz1, int nslab, int ntiles,
+              const double* __restrict__ gvec, int W, i64 n_gather, double* __restrict__ out) {
+    extern __shared__ double sv[];                        // [W staged entries][V7_WARPS x V7_SLOTS piece sums]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned wbuf = (unsigned)__cvta_generic_to_shared(sv + W + warp * V7_SLOTS);
+    const int t_lo = (int)((i64)ntiles * blockIdx.x / gridDim.x);
+    const int t_hi = (int)((i64)ntiles * (blockIdx.x + 1) / gridDim.x);
+    if (t_lo >= t_hi) return;
+    int slab;
+    {
+        int lo = 0, hi = nslab;
+        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (slab_tile0[mid] <= t_lo) lo = mid; else hi = mid; }
+        slab = lo;
+    }
+    int cur = t_lo;
+    while (cur < t_hi) {
+        const int s_t0 = slab_tile0[slab];
+        const int sec_end = min(t_hi, slab_tile0[slab + 1]);
+        const int nnz0 = slab_nnz0[slab], nnz1 = slab_nnz1[slab];
+        const i64 gbase = (i64)slab * W;
+        __syncthreads();                                   // the previous section's readers are done
+        {
+            const i64 rem = n_gather - gbase;
+            const int wlen = rem < (i64)W ? (int)rem : W;
+            const double* src = gvec + gbase;
+            int i = tid;
+            for (; i + 3 * V7_THREADS < wlen; i += 4 * V7_THREADS) {
+                double a0 = src[i], a1 = src[i + V7_THREADS], a2 = src[i + 2 * V7_THREADS], a3 = src[i + 3 * V7_THREADS];
+                sv[i] = a0; sv[i + V7_THREADS] = a1; sv[i + 2 * V7_THREADS] = a2; sv[i + 3 * V7_THREADS] = a3;
+            }
+            for (; i < wlen; i += V7_THREADS) sv[i] = src[i];
+        }
+        const unsigned sbase = (unsigned)__cvta_generic_to_shared(sv) - (unsigned)((unsigned)gbase << 3);
+        int t = cur + warp;
+        int ri[V7_ITEMS];
+        unsigned meta = 0u;
+        int2 tm = make_int2(0, 0);
+        if (t < sec_end) {
+            const int st0 = nnz0 + (t - s_t0) * V7_TILE;
+            fetch_idx(ri, idx, st0, min(st0 + V7_TILE, nnz1), lane);
+            meta = lane_meta[(i64)t * 32 + lane];
+            tm = tile_out[t];
+        }
+        __syncthreads();
+        while (t < sec_end) {
+            const int start = nnz0 + (t - s_t0) * V7_TILE;
+            const int len = min(start + V7_TILE, nnz1) - start;
+            double* out_tile = out + tm.x;
+            if (len == V7_TILE && tm.y < V7_SLOTS) tile_body_staged<BINARY, false>(ri, val, start, len, meta, tm.y, lane, sbase, wbuf, out_tile);
+            else if (len == V7_TILE) tile_body<BINARY, false>(ri, val, start, len, meta, tm.y, lane, sbase, out_tile);
+            else if (len > 0)   tile_body<BINARY, true>(ri, val, start, len, meta, tm.y, lane, sbase, out_tile);
+            else if (lane == 0) out_tile[0] = 0.0;         // a slab without nnz: its single empty tile
+            t += V7_WARPS;
+            if (t < sec_end) {
+                const int st1 = nnz0 + (t - s_t0) * V7_TILE;
+                fetch_idx(ri, idx, st1, min(st1 + V7_TILE, nnz1), lane);
+                meta = lane_meta[(i64)t * 32 + lane];
+                tm = tile_out[t];
+            }
+        }
+        cur = sec_end;
+        slab += 1;
+    }
+}
+
+// adds the pieces continued from previous tiles to the slot of the segment they belong to, in tile order
+__global__ void k_fixup_v7(const int* __restrict__ chead_slot, const int2* __restrict__ tile_out, int ntiles,
+                           double* __restrict__ out) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntiles) return;
+    const int s = chead_slot[t];
+    if (s < 0) return;
+    if (t > 0 && chead_slot[t - 1] == s) return;
+    double acc = 0.0;
+    for (int tt = t; tt < ntiles && chead_slot[tt] == s; ++tt) acc += out[tile_out[tt].x];
+    out[s] += acc;
+}
+
+// stand-in for the consumer kernels: y[seg] = sum over slabs of the segment's slot (empty: nothing)
+__global__ void k_consume_v7(const int* __restrict__ cslot, int nslab, i64 n_seg, const double* __restrict__ out,
+                             double* __restrict__ y) {
+    i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_seg) return;
+    double u = 0.0;
+    for (int s = 0; s < nslab; ++s) {
+        const int c = cslot[(i64)s * n_seg + i];
+        if (c >= 0) u += out[c];
+    }
+    y[i] = u;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host: format builder (the device builder comes with the integration), reference product, test driver
+struct HostFormat {
+    int nslab, W, ntiles;
+    i64 n_seg, n_gather, n_out;
+    std::vector<int> idx; std::vector<double> val;
+    std::vector<unsigned> lane_meta; std::vector<int2> tile_out; std::vector<int> chead_slot, cslot;
+    std::vector<int> slab_tile0, slab_nnz0, slab_nnz1;
+};
+
+// greedy bank-aware order inside a piece (same rule as k_bank_permute, 32 (load j, half-warp) groups per tile)
+static void bank_order(int* e, double* v, int a, int b, unsigned char* occ) {
+    for (int k = a; k < b; ++k) {
+        unsigned char* og = occ + (((k & 15) << 1 | (k >> 8)) << 4);
+        int best = k, bo = og[e[k] & 15];
+        for (int m = k + 1; bo > 0 && m < b; ++m) { int o = og[e[m] & 15]; if (o < bo) { bo = o; best = m; } }
+        std::swap(e[k], e[best]);
+        if (v) std::swap(v[k], v[best]);
+        og[e[k] & 15] = (unsigned char)(bo + 1);
+    }
+}
+
+static HostFormat build_format(const std::vector<int>& ptr, const std::vector<int>& ind, const std::vector<double>* data,
+                               i64 n_gather, int W, bool permute) {
+    HostFormat f;
+    f.n_seg = (i64)ptr.size() - 1; f.n_gather = n_gather; f.W = W;
+    f.nslab = (int)std::max<i64>(1, (n_gather + W - 1) / W);
+    const i64 V = (i64)f.nslab * f.n_seg;
+    std::vector<i64> count((size_t)V, 0);
+    for (i64 r = 0; r < f.n_seg; ++r)
+        for (int k = ptr[r]; k < ptr[r + 1]; ++k) count[(size_t)((i64)(ind[k] / W) * f.n_seg + r)]++;
+    std::vector<i64> vptr((size_t)V + 1, 0), vend((size_t)V, 0);
+    f.slab_nnz0.assign(f.nslab + 1, 0); f.slab_nnz1.assign(f.nslab + 1, 0); f.slab_tile0.assign(f.nslab + 1, 0);
+    i64 pos = 0;
+    for (int s = 0; s < f.nslab; ++s) {
+        pos = (pos + 3) & ~(i64)3;
+        f.slab_nnz0[s] = (int)pos;
+        for (i64 r = 0; r < f.n_seg; ++r) { size_t v = (size_t)((i64)s * f.n_seg + r); vptr[v] = pos; pos += count[v]; vend[v] = pos; }
+        f.slab_nnz1[s] = (int)pos;
+    }
+    vptr[(size_t)V] = pos;
+    f.idx.assign((size_t)pos + 16, 0);
+    if (data) f.val.assign((size_t)pos + 16, 0.0);
+    {
+        std::vector<i64> fill(vptr.begin(), vptr.end() - 1);
+        for (i64 r = 0; r < f.n_seg; ++r)
+            for (int k = ptr[r]; k < ptr[r + 1]; ++k) {
+                size_t v = (size_t)((i64)(ind[k] / W) * f.n_seg + r);
+                f.idx[(size_t)fill[v]] = ind[k];
+                if (data) f.val[(size_t)fill[v]] = (*data)[k];
+                fill[v]++;
+            }
+    }
+    f.cslot.assign((size_t)V, -1);
+    int slot = 0;
+    for (int s = 0; s < f.nslab; ++s) {
+        f.slab_tile0[s] = (int)f.tile_out.size();
+        const int a = f.slab_nnz0[s], b = f.slab_nnz1[s];
+        const int nt = std::max(1, (b - a + V7_TILE - 1) / V7_TILE);
+        i64 v = (i64)s * f.n_seg;                       // first virtual segment that can start at or after the tile
+        int open_slot = -1;                             // slot of the last head seen so far in this slab
+        for (int k = 0; k < nt; ++k) {
+            const int start = a + k * V7_TILE, end = std::max(start, std::min(start + V7_TILE, b));
+            std::vector<unsigned> flags(32, 0u);
+            std::vector<int> cuts;                      // piece boundaries inside the tile (relative)
+            int nheads = 0;
+            const int first_slot = slot++;              // slot 0 of the tile: the continued piece
+            const int open_before = open_slot;
+            while (v < (i64)(s + 1) * f.n_seg && vptr[(size_t)v] < end) {
+                if (vend[(size_t)v] > vptr[(size_t)v] && vptr[(size_t)v] >= start) {
+                    const int rel = (int)(vptr[(size_t)v] - start);
+                    flags[rel / V7_ITEMS] |= 1u << (rel % V7_ITEMS);
+                    cuts.push_back(rel);
+                    f.cslot[(size_t)v] = open_slot = slot++;
+                    ++nheads;
+                }
+                ++v;
+            }
+            unsigned below = 0;
+            for (int l = 0; l < 32; ++l) { f.lane_meta.push_back(flags[l] | (below << 16)); below += __builtin_popcount(flags[l]); }
+            f.tile_out.push_back(make_int2(first_slot, nheads));
+            // the segment continued from the previous tile = the last head seen before this tile (same slab)
+            const int ch = (end > start && !(nheads > 0 && cuts[0] == 0)) ? open_before : -1;
+            f.chead_slot.push_back(ch);
+            if (permute && end > start) {
+                unsigned char occ[512];
+                memset(occ, 0, sizeof(occ));
+                int prev = 0;
+                cuts.push_back(end - start);
+                for (int c : cuts) { if (c > prev) bank_order(&f.idx[(size_t)start], data ? &f.val[(size_t)start] : nullptr, prev, c, occ); prev = c; }
+            }
+        }
+    }
+    f.slab_tile0[f.nslab] = (int)f.tile_out.size();
+    f.slab_nnz0[f.nslab] = f.slab_nnz1[f.nslab] = (int)pos;
+    f.ntiles = (int)f.tile_out.size();
+    f.n_out = slot;
+    return f;
+}
+
+// CPU transliteration of the kernel + fix-up + consumer on the host format (`--host`): checks build_format and the
+// slot logic of this file without a GPU.
+static std::vector<double> host_product(const HostFormat& f, const std::vector<double>& x, bool binary) {
+    std::vector<double> out((size_t)f.n_out, NAN);
+    for (int s = 0; s < f.nslab; ++s)
+        for (int t = f.slab_tile0[s]; t < f.slab_tile0[s + 1]; ++t) {
+            const int start = f.slab_nnz0[s] + (t - f.slab_tile0[s]) * V7_TILE;
+            const int len = std::max(0, std::min(start + V7_TILE, f.slab_nnz1[s]) - start);
+            double* ot = out.data() + f.tile_out[(size_t)t].x;
+            const int nheads = f.tile_out[(size_t)t].y;
+            if (len == 0) { ot[0] = 0.0; continue; }
+            double run[32], lead[32]; bool has[32];
+            for (int l = 0; l < 32; ++l) {
+                const unsigned meta = f.lane_meta[(size_t)t * 32 + l], fl = meta & 0xffffu;
+                unsigned o = meta >> 16;
+                double r = 0.0; lead[l] = 0.0; has[l] = fl != 0u;
+                for (int j = 0; j < V7_ITEMS; ++j) {
+                    const int q = l * V7_ITEMS + j;
+                    double g = 0.0;
+                    if (q < len) g = (binary ? 1.0 : f.val[(size_t)start + q]) * x[(size_t)f.idx[(size_t)start + q]];
+                    if ((fl >> j) & 1u) { ot[o] = r; if ((fl & ((1u << j) - 1u)) == 0u) lead[l] = r; ++o; r = g; }
+                    else r += g;
+                }
+                run[l] = r;
+            }
+            double xs[32];
+            for (int l = 0; l < 32; ++l) xs[l] = run[l];
+            for (int d = 1; d < 32; d <<= 1) {
+                double y[32];
+                for (int l = 0; l < 32; ++l) y[l] = l >= d ? xs[l - d] : 0.0;
+                for (int l = d; l < 32; ++l) {
+                    bool head = false;
+                    for (int m = l - d + 1; m <= l; ++m) head = head || has[m];
+                    if (!head) xs[l] += y[l];
+                }
+            }
+            for (int l = 0; l < 32; ++l) {
+                const double carry = l ? xs[l - 1] : 0.0;
+                if (has[l]) ot[f.lane_meta[(size_t)t * 32 + l] >> 16] = lead[l] + carry;
+                if (l == 31) ot[nheads] = has[l] ? run[l] : run[l] + carry;
+            }
+        }
+    for (int t = 0; t < f.ntiles; ++t) {                      // k_fixup_v7
+        const int s = f.chead_slot[(size_t)t];
+        if (s < 0 || (t > 0 && f.chead_slot[(size_t)t - 1] == s)) continue;
+        double acc = 0.0;
+        for (int tt = t; tt < f.ntiles && f.chead_slot[(size_t)tt] == s; ++tt) acc += out[(size_t)f.tile_out[(size_t)tt].x];
+        out[(size_t)s] += acc;
+    }
+    std::vector<double> y((size_t)f.n_seg, 0.0);              // k_consume_v7
+    for (i64 i = 0; i < f.n_seg; ++i)
+        for (int s = 0; s < f.nslab; ++s) { const int c = f.cslot[(size_t)((i64)s * f.n_seg + i)]; if (c >= 0) y[(size_t)i] += out[(size_t)c]; }
+    return y;
+}
+
+template <typename T> static T* upload(const std::vector<T>& h) {
+    T* d = nullptr;
+    CK(cudaMalloc((void**)&d, std::max<size_t>(1, h.size()) * sizeof(T)));
+    if (!h.empty()) CK(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return d;
+}
+
+int main(int argc, char** argv) {
+    const i64 n = argc > 1 ? atoll(argv[1]) : 20000, p = argc > 2 ? atoll(argv[2]) : 3000;
+    const double density = argc > 3 ? atof(argv[3]) : 0.01;
+    const bool binary = argc > 4 ? atoi(argv[4]) != 0 : true;
+    const bool permute = argc > 5 ? atoi(argv[5]) != 0 : true;
+    const bool host_only = argc > 6 && !strcmp(argv[6], "--host");      // CPU check of the format builder, no GPU needed
+    int dev = 0; cudaDeviceProp prop;
+    memset(&prop, 0, sizeof(prop));
+    if (host_only) { prop.sharedMemPerBlockOptin = 227 * 1024; prop.multiProcessorCount = 148; }
+    else { CK(cudaSetDevice(dev)); CK(cudaGetDeviceProperties(&prop, dev)); }
+    int W = (int)(((prop.sharedMemPerBlockOptin - 1024 - V7_WARPS * V7_SLOTS * 8) / 8) & ~(size_t)31);
+    if (argc > 7) W = atoi(argv[7]);                                     // slab width override (multiple of 32)
+    // random CSR with skewed row lengths (a few empty rows, a few long ones)
+    std::mt19937_64 rng(1);
+    std::vector<int> ptr((size_t)n + 1, 0), ind; std::vector<double> data;
+    std::uniform_real_distribution<double> U(0.0, 1.0);
+    for (i64 r = 0; r < n; ++r) {
+        double mean = density * p * (r % 17 == 0 ? 0.0 : (r % 101 == 0 ? 20.0 : 1.0));
+        int cnt = (int)std::min<double>(p, std::floor(mean + U(rng)));
+        std::vector<int> cols;
+        for (int k = 0; k < cnt; ++k) cols.push_back((int)(U(rng) * U(rng) * p) % (int)p);    // skewed towards low columns
+        std::sort(cols.begin(), cols.end()); cols.erase(std::unique(cols.begin(), cols.end()), cols.end());
+        for (int c : cols) { ind.push_back(c); data.push_back(binary ? 1.0 : U(rng) - 0.5); }
+        ptr[(size_t)r + 1] = (int)ind.size();
+    }
+    const i64 nnz = (i64)ind.size();
+    std::vector<double> x((size_t)p);
+    for (auto& e : x) e = U(rng) - 0.5;
+    HostFormat f = build_format(ptr, ind, binary ? nullptr : &data, p, W, permute);
+    printf("n=%lld p=%lld nnz=%lld slabs=%d W=%d tiles=%d out slots=%lld (%.2f B/nnz metadata)\n", n, p, nnz, f.nslab, W,
+           f.ntiles, f.n_out, (f.lane_meta.size() * 4.0 + f.tile_out.size() * 8.0) / std::max<i64>(1, nnz));
+    auto verify = [&](const std::vector<double>& y) {
+        double err = 0.0, scale = 0.0;
+        for (i64 r = 0; r < n; ++r) {
+            double sref = 0.0;
+            for (int k = ptr[r]; k < ptr[r + 1]; ++k) sref += data[k] * x[ind[k]];
+            err = std::max(err, std::isfinite(y[r]) ? std::fabs(y[r] - sref) : 1e300);
+            scale = std::max(scale, std::fabs(sref));
+        }
+        const bool ok = err <= 1e-12 * std::max(1.0, scale);
+        printf("max abs err %.3e (scale %.3e) -> %s\n", err, scale, ok ? "PASS" : "FAIL");
+        return ok;
+    };
+    if (host_only) return verify(host_product(f, x, binary)) ? 0 : 1;
+    int* d_idx = upload(f.idx); double* d_val = binary ? nullptr : upload(f.val);
+    unsigned* d_meta = upload(f.lane_meta); int2* d_tout = upload(f.tile_out);
+    int *d_ch = upload(f.chead_slot), *d_cslot = upload(f.cslot);
+    int *d_t0 = upload(f.slab_tile0), *d_n0 = upload(f.slab_nnz0), *d_n1 = upload(f.slab_nnz1);
+    double* d_x = upload(x);
+    double *d_out = nullptr, *d_y = nullptr;
+    CK(cudaMalloc((void**)&d_out, std::max<i64>(1, f.n_out) * sizeof(double)));
+    CK(cudaMemset(d_out, 0xff, std::max<i64>(1, f.n_out) * sizeof(double)));      // NaNs: every slot must be written
+    CK(cudaMalloc((void**)&d_y, (size_t)n * sizeof(double)));
+    const size_t smem = (size_t)(W + V7_WARPS * V7_SLOTS) * sizeof(double);
+    CK(cudaFuncSetAttribute(k_seg_spmv_v7<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(k_seg_spmv_v7<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = std::min(prop.multiProcessorCount, f.ntiles);
+    auto launch = [&]() {
+        if (binary) k_seg_spmv_v7<true><<<grid, V7_THREADS, smem>>>(d_idx, d_val, d_meta, d_tout, d_t0, d_n0, d_n1, f.nslab, f.ntiles, d_x, W, p, d_out);
+        else k_seg_spmv_v7<false><<<grid, V7_THREADS, smem>>>(d_idx, d_val, d_meta, d_tout, d_t0, d_n0, d_n1, f.nslab, f.ntiles, d_x, W, p, d_out);
+    };
+    launch();
+    k_fixup_v7<<<(f.ntiles + 255) / 256, 256>>>(d_ch, d_tout, f.ntiles, d_out);
+    k_consume_v7<<<(unsigned)((n + 255) / 256), 256>>>(d_cslot, f.nslab, n, d_out, d_y);
+    CK(cudaDeviceSynchronize());
+    std::vector<double> y((size_t)n);
+    CK(cudaMemcpy(y.data(), d_y, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
+    const bool ok = verify(y);
+    // timing: L2 flushed between launches
+    void* flush = nullptr; const size_t fb = 256u << 20;
+    CK(cudaMalloc(&flush, fb));
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    double ms_sum = 0.0; const int reps = 10;
+    for (int r = 0; r < reps + 2; ++r) {
+        CK(cudaMemsetAsync(flush, r, fb));
+        CK(cudaEventRecord(e0)); launch(); CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (r >= 2) ms_sum += ms;
+    }
+    const double ms = ms_sum / reps, bytes = (binary ? 4.0 : 12.0) * nnz + 4.0 * (n + 1) + 8.0 * p + 8.0 * n;
+    printf("k_seg_spmv_v7<%s>: %.1f us per launch, %.0f GB/s algorithmic\n", binary ? "pattern" : "valued", ms * 1e3, bytes / ms / 1e6);
+    return ok ? 0 : 1;
+}

@@ -63,3 +63,22 @@ def test_every_compact_entry_is_written_exactly_once():
     for t in range(len(f['tiles'])):
         em.warp_tile(f, t, x, cpart, head_part)
     assert np.all(writes == 1)
+
+
+def test_cuda_translation_host_mode(tmp_path):
+    """experimental/spmv_v7.cu must compile for sm_100a, and its host format builder + the CPU transliteration of its
+    kernel (`--host`) must reproduce a plain segmented sum (several slab widths, pattern-only and valued)."""
+    import os
+    import shutil
+    import subprocess
+    nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
+    if not os.path.exists(nvcc):
+        pytest.skip('nvcc not available')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / 'spmv_v7_test')
+    subprocess.run([nvcc, '-gencode', 'arch=compute_100a,code=sm_100a', '-O1', '-o', exe,
+                    os.path.join(root, 'experimental', 'spmv_v7.cu')], check=True, timeout=600)
+    for args in (['4000', '900', '0.02', '1', '1', '--host'], ['4000', '900', '0.02', '0', '1', '--host', '64'],
+                 ['300', '20000', '0.001', '1', '0', '--host', '1024'], ['2000', '40', '0.5', '0', '1', '--host', '32']):
+        out = subprocess.run([exe] + args, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0 and 'PASS' in out.stdout, out.stdout + out.stderr
