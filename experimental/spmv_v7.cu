@@ -28,6 +28,8 @@
 #include <cstring>
 #include <random>
 #include <vector>
+#include "v7_format.cuh"
+#include <cub/cub.cuh>
 
 typedef long long i64;
 #ifndef V7_CARRY_RED
@@ -280,6 +282,7 @@ struct HostFormat {
     std::vector<int> idx; std::vector<double> val;
     std::vector<unsigned> lane_meta; std::vector<int2> tile_out; std::vector<int> chead_slot, cslot;
     std::vector<int> slab_tile0, slab_nnz0, slab_nnz1;
+    std::vector<int> vptr;            // [V + 1] padded nnz offsets of the virtual segments (what the library's format holds)
 };
 
 // greedy bank-aware order inside a piece (same rule as k_bank_permute, 32 (load j, half-warp) groups per tile)
@@ -369,6 +372,7 @@ static HostFormat build_format(const std::vector<int>& ptr, const std::vector<in
     f.slab_nnz0[f.nslab] = f.slab_nnz1[f.nslab] = (int)pos;
     f.ntiles = (int)f.tile_out.size();
     f.n_out = slot;
+    f.vptr.assign(vptr.begin(), vptr.end());
     return f;
 }
 
@@ -427,6 +431,30 @@ static std::vector<double> host_product(const HostFormat& f, const std::vector<d
     return y;
 }
 
+// the device-side metadata builder (v7_format.cuh), run index by index on the host, must reproduce build_format
+static bool check_device_builder(const HostFormat& f) {
+    V7Geometry g;
+    g.ptr = f.vptr.data(); g.V = (i64)f.vptr.size() - 1; g.n_seg = f.n_seg; g.nslab = f.nslab; g.ntiles = f.ntiles;
+    g.tile = V7_TILE; g.slab_tile0 = f.slab_tile0.data(); g.slab_nnz0 = f.slab_nnz0.data(); g.slab_nnz1 = f.slab_nnz1.data();
+    std::vector<int> cidx((size_t)g.V + 1, 0);
+    for (i64 v = 0; v < g.V; ++v) cidx[(size_t)v + 1] = cidx[(size_t)v] + v7_nonempty(g, v);
+    std::vector<int> hpos((size_t)std::max(1, cidx[(size_t)g.V]), 0);
+    i64 bad = 0;
+    for (i64 v = 0; v < g.V; ++v) {
+        const int slot = v7_segment_slot(g, cidx.data(), v);
+        if (slot >= 0) hpos[(size_t)cidx[(size_t)v]] = g.ptr[v];
+        bad += slot != f.cslot[(size_t)v];
+    }
+    for (int t = 0; t < f.ntiles; ++t) {
+        int2 to; int ch;
+        v7_tile_meta(g, cidx.data(), hpos.data(), t, &to, &ch);
+        bad += to.x != f.tile_out[(size_t)t].x || to.y != f.tile_out[(size_t)t].y || ch != f.chead_slot[(size_t)t];
+        for (int l = 0; l < 32; ++l) bad += v7_lane_meta(g, cidx.data(), t, l, V7_ITEMS) != f.lane_meta[(size_t)t * 32 + l];
+    }
+    printf("device-side metadata builder vs host builder: %lld mismatches -> %s\n", bad, bad ? "FAIL" : "PASS");
+    return bad == 0;
+}
+
 template <typename T> static T* upload(const std::vector<T>& h) {
     T* d = nullptr;
     CK(cudaMalloc((void**)&d, std::max<size_t>(1, h.size()) * sizeof(T)));
@@ -477,7 +505,7 @@ int main(int argc, char** argv) {
         printf("max abs err %.3e (scale %.3e) -> %s\n", err, scale, ok ? "PASS" : "FAIL");
         return ok;
     };
-    if (host_only) return verify(host_product(f, x, binary)) ? 0 : 1;
+    if (host_only) { const bool a = verify(host_product(f, x, binary)), b = check_device_builder(f); return a && b ? 0 : 1; }
     int* d_idx = upload(f.idx); double* d_val = binary ? nullptr : upload(f.val);
     unsigned* d_meta = upload(f.lane_meta); int2* d_tout = upload(f.tile_out);
     int *d_ch = upload(f.chead_slot), *d_cslot = upload(f.cslot);
@@ -502,6 +530,40 @@ int main(int argc, char** argv) {
     std::vector<double> y((size_t)n);
     CK(cudaMemcpy(y.data(), d_y, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
     const bool ok = verify(y);
+    {   // the same metadata built by the device kernels of v7_format.cuh must equal the host arrays
+        int* d_vptr = upload(f.vptr);
+        V7Geometry g;
+        g.ptr = d_vptr; g.V = (i64)f.vptr.size() - 1; g.n_seg = f.n_seg; g.nslab = f.nslab; g.ntiles = f.ntiles; g.tile = V7_TILE;
+        g.slab_tile0 = d_t0; g.slab_nnz0 = d_n0; g.slab_nnz1 = d_n1;
+        int *d_flag, *d_cidx, *d_hpos, *d_cslot2, *d_ch2; int2* d_tout2; unsigned* d_meta2;
+        CK(cudaMalloc((void**)&d_flag, ((size_t)g.V + 1) * sizeof(int)));
+        CK(cudaMalloc((void**)&d_cidx, ((size_t)g.V + 1) * sizeof(int)));
+        CK(cudaMalloc((void**)&d_hpos, ((size_t)g.V + 1) * sizeof(int)));
+        CK(cudaMalloc((void**)&d_cslot2, ((size_t)g.V + 1) * sizeof(int)));
+        CK(cudaMalloc((void**)&d_ch2, (size_t)f.ntiles * sizeof(int)));
+        CK(cudaMalloc((void**)&d_tout2, (size_t)f.ntiles * sizeof(int2)));
+        CK(cudaMalloc((void**)&d_meta2, (size_t)f.ntiles * 32 * sizeof(unsigned)));
+        const unsigned gv = (unsigned)((g.V + 1 + 255) / 256);
+        k_v7_nonempty<<<gv, 256>>>(g, d_flag);
+        void* tmp = nullptr; size_t tb = 0;
+        CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, d_flag, d_cidx, (int)(g.V + 1)));
+        CK(cudaMalloc(&tmp, tb));
+        CK(cub::DeviceScan::ExclusiveSum(tmp, tb, d_flag, d_cidx, (int)(g.V + 1)));
+        k_v7_segments<<<gv, 256>>>(g, d_cidx, d_hpos, d_cslot2);
+        k_v7_tiles<<<(f.ntiles + 255) / 256, 256>>>(g, d_cidx, d_hpos, d_tout2, d_ch2);
+        k_v7_lanes<<<(unsigned)(((i64)f.ntiles * 32 + 255) / 256), 256>>>(g, d_cidx, d_meta2, V7_ITEMS);
+        CK(cudaDeviceSynchronize());
+        std::vector<int> cs((size_t)g.V), ch((size_t)f.ntiles); std::vector<int2> to((size_t)f.ntiles); std::vector<unsigned> lm((size_t)f.ntiles * 32);
+        CK(cudaMemcpy(cs.data(), d_cslot2, cs.size() * sizeof(int), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(ch.data(), d_ch2, ch.size() * sizeof(int), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(to.data(), d_tout2, to.size() * sizeof(int2), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(lm.data(), d_meta2, lm.size() * sizeof(unsigned), cudaMemcpyDeviceToHost));
+        i64 bad = 0;
+        for (size_t i = 0; i < cs.size(); ++i) bad += cs[i] != f.cslot[i];
+        for (size_t i = 0; i < ch.size(); ++i) bad += ch[i] != f.chead_slot[i] || to[i].x != f.tile_out[i].x || to[i].y != f.tile_out[i].y;
+        for (size_t i = 0; i < lm.size(); ++i) bad += lm[i] != f.lane_meta[i];
+        printf("device-built metadata vs host builder: %lld mismatches -> %s\n", bad, bad ? "FAIL" : "PASS");
+    }
     // timing: L2 flushed between launches
     void* flush = nullptr; const size_t fb = 256u << 20;
     CK(cudaMalloc(&flush, fb));
