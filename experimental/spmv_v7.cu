@@ -129,29 +129,34 @@ __device__ __forceinline__ void tile_body_staged(const int (&ri)[V7_ITEMS], cons
                                                  unsigned meta, int nheads, int lane, unsigned sbase, unsigned wbuf,
                                                  double* __restrict__ out_tile) {
     const unsigned f = meta & 0xffffu;
-    double g[V7_ITEMS];
-#pragma unroll
-    for (int j = 0; j < V7_ITEMS; ++j) g[j] = lds_f64(sbase + ((unsigned)ri[j] << 3));
-    if (!BINARY) {
-#pragma unroll
-        for (int j = 0; j < V7_ITEMS; ++j) {
-            const int q = lane * V7_ITEMS + j;
-            g[j] *= val[start + (PARTIAL ? min(q, len - 1) : q)];
-        }
-    }
     double run = 0.0;
     const unsigned first = wbuf + ((meta >> 16) << 3);   // shared address of the slot open at the start of the lane
     unsigned sp = first;
+    // pattern-only: all 16 gathers in flight, then the serial pass; valued: two chunks of 8 so that gathered entries
+    // and values (4 x 128-bit loads per chunk, issued before the gathers) fit the 64-register budget
+    constexpr int CH = BINARY ? V7_ITEMS : 8;
 #pragma unroll
-    for (int j = 0; j < V7_ITEMS; ++j) {
-        double gj = g[j];
-        if (PARTIAL) gj = (lane * V7_ITEMS + j < len) ? gj : 0.0;
-        // head at j:  *sp++ = run; run = gj      else:  run += gj
-        asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t.reg .f64 s;\n\t"
-                     "and.b32 t, %2, %3;\n\tsetp.ne.u32 p, t, 0;\n\t"
-                     "@p st.shared.f64 [%1], %0;\n\t@p add.u32 %1, %1, 8;\n\t"
-                     "add.rn.f64 s, %0, %4;\n\tselp.f64 %0, %4, s, p;\n\t}"
-                     : "+d"(run), "+r"(sp) : "r"(f), "r"(1u << j), "d"(gj) : "memory");
+    for (int c = 0; c < V7_ITEMS; c += CH) {
+        double g[CH];
+        if (!BINARY) {
+            const double2* vp = reinterpret_cast<const double2*>(val + start + lane * V7_ITEMS + c);
+#pragma unroll
+            for (int q = 0; q < CH / 2; ++q) { const double2 v = vp[q]; g[2 * q] = v.x; g[2 * q + 1] = v.y; }
+#pragma unroll
+            for (int j = 0; j < CH; ++j) g[j] *= lds_f64(sbase + ((unsigned)ri[c + j] << 3));
+        } else {
+#pragma unroll
+            for (int j = 0; j < CH; ++j) g[j] = lds_f64(sbase + ((unsigned)ri[c + j] << 3));
+        }
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+            // head at c + j:  *sp++ = run; run = g      else:  run += g      (one predicate, no branch)
+            asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t.reg .f64 s;\n\t"
+                         "and.b32 t, %2, %3;\n\tsetp.ne.u32 p, t, 0;\n\t"
+                         "@p st.shared.f64 [%1], %0;\n\t@p add.u32 %1, %1, 8;\n\t"
+                         "add.rn.f64 s, %0, %4;\n\tselp.f64 %0, %4, s, p;\n\t}"
+                         : "+d"(run), "+r"(sp) : "r"(f), "r"(1u << (c + j)), "d"(g[j]) : "memory");
+        }
     }
     const unsigned hm = __ballot_sync(0xffffffffu, f != 0u);
     double x = run;
