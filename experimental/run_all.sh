@@ -14,6 +14,8 @@ timeout 120 /tmp/bbx/spmv_v7 20000 3000 0.01 0 1 x 256
 timeout 120 /tmp/bbx/spmv_v7 200000 400 0.01 1
 timeout 200 /tmp/bbx/spmv_v7 125000 100000 0.001 1
 timeout 400 /tmp/bbx/spmv_v7 1000000 100000 0.001 1
+echo "== same, next-tile index prefetch after the tile instead of after the gathers =="
+$NVCC -DV7_EARLY_PREFETCH=0 -o /tmp/bbx/spmv_v7_late experimental/spmv_v7.cu && timeout 400 /tmp/bbx/spmv_v7_late 1000000 100000 0.001 1
 echo "== cluster-fused CG vector kernel =="
 timeout 60 /tmp/bbx/cgc 100001 300 16
 echo "== two-shot all-reduce =="

@@ -8,6 +8,9 @@ typedef long long v7_i64;
 #ifndef V7_CARRY_RED
 #define V7_CARRY_RED 1
 #endif
+#ifndef V7_EARLY_PREFETCH          // 1: next tile's indices are fetched right after the gathers (costs a few spills), 0: after the tile
+#define V7_EARLY_PREFETCH 1
+#endif
 constexpr int V7_THREADS = 1024, V7_WARPS = V7_THREADS / 32, V7_ITEMS = 16, V7_TILE = 32 * V7_ITEMS;
 
 
@@ -97,9 +100,10 @@ __device__ __forceinline__ void v7_tile_body(const int (&ri)[V7_ITEMS], const do
 constexpr int V7_SLOTS = 64;
 static_assert(V7_SLOTS == 64, "the copy-out below handles exactly two slots per lane");
 template <bool BINARY, bool PARTIAL>
-__device__ __forceinline__ void v7_tile_body_staged(const int (&ri)[V7_ITEMS], const double* __restrict__ val, int start, int len,
+__device__ __forceinline__ void v7_tile_body_staged(int (&ri)[V7_ITEMS], const double* __restrict__ val, int start, int len,
                                                  unsigned meta, int nheads, int lane, unsigned sbase, unsigned wbuf,
-                                                 double* __restrict__ out_tile) {
+                                                 double* __restrict__ out_tile,
+                                                 const int* __restrict__ idx, int next_start, int next_end) {
     const unsigned f = meta & 0xffffu;
     double run = 0.0;
     const unsigned first = wbuf + ((meta >> 16) << 3);   // shared address of the slot open at the start of the lane
@@ -120,6 +124,8 @@ __device__ __forceinline__ void v7_tile_body_staged(const int (&ri)[V7_ITEMS], c
 #pragma unroll
             for (int j = 0; j < CH; ++j) g[j] = v7_lds_f64(sbase + ((unsigned)ri[c + j] << 3));
         }
+        // early prefetch: the index registers are dead once the last gather has been issued (next_end <= next_start: none)
+        if (c + CH == V7_ITEMS) v7_fetch_idx(ri, idx, next_start, next_end, lane);
 #pragma unroll
         for (int j = 0; j < CH; ++j) {
             // head at c + j:  *sp++ = run; run = g      else:  run += g      (one predicate, no branch)
@@ -210,17 +216,26 @@ k_seg_spmv_v7(const int* __restrict__ idx, const double* __restrict__ val, const
             const int start = nnz0 + (t - s_t0) * V7_TILE;
             const int len = min(start + V7_TILE, nnz1) - start;
             double* out_tile = out + tm.x;
-            if (len == V7_TILE && tm.y < V7_SLOTS) v7_tile_body_staged<BINARY, false>(ri, val, start, len, meta, tm.y, lane, sbase, wbuf, out_tile);
-            else if (len == V7_TILE) v7_tile_body<BINARY, false>(ri, val, start, len, meta, tm.y, lane, sbase, out_tile);
-            else if (len > 0)   v7_tile_body<BINARY, true>(ri, val, start, len, meta, tm.y, lane, sbase, out_tile);
-            else if (lane == 0) out_tile[0] = 0.0;         // a slab without nnz: its single empty tile
-            t += V7_WARPS;
-            if (t < sec_end) {
-                const int st1 = nnz0 + (t - s_t0) * V7_TILE;
-                v7_fetch_idx(ri, idx, st1, min(st1 + V7_TILE, nnz1), lane);
-                meta = lane_meta[(v7_i64)t * 32 + lane];
-                tm = tile_out[t];
+            const int tn = t + V7_WARPS;
+            const int st1 = nnz0 + (tn - s_t0) * V7_TILE;
+            const int en1 = tn < sec_end ? min(st1 + V7_TILE, nnz1) : st1;       // empty range: nothing to prefetch
+            unsigned meta_next = 0u;
+            int2 tm_next = make_int2(0, 0);
+            if (tn < sec_end) { meta_next = lane_meta[(v7_i64)tn * 32 + lane]; tm_next = tile_out[tn]; }
+            if (len == V7_TILE && tm.y < V7_SLOTS) {
+#if V7_EARLY_PREFETCH
+                v7_tile_body_staged<BINARY, false>(ri, val, start, len, meta, tm.y, lane, sbase, wbuf, out_tile, idx, st1, en1);
+#else
+                v7_tile_body_staged<BINARY, false>(ri, val, start, len, meta, tm.y, lane, sbase, wbuf, out_tile, idx, st1, st1);
+                v7_fetch_idx(ri, idx, st1, en1, lane);
+#endif
+            } else {
+                if (len == V7_TILE) v7_tile_body<BINARY, false>(ri, val, start, len, meta, tm.y, lane, sbase, out_tile);
+                else if (len > 0)   v7_tile_body<BINARY, true>(ri, val, start, len, meta, tm.y, lane, sbase, out_tile);
+                else if (lane == 0) out_tile[0] = 0.0;     // a slab without nnz: its single empty tile
+                v7_fetch_idx(ri, idx, st1, en1, lane);
             }
+            t = tn; meta = meta_next; tm = tm_next;
         }
         cur = sec_end;
         slab += 1;
