@@ -33,6 +33,7 @@ SIGNATURES = {
     'bb_sync': (c_int, [c_void_p]),
     'bb_comm_unique_id': (c_int, [c_char_p, ctypes.c_char_p]),
     'bb_comm_init': (c_int, [c_void_p, c_char_p, c_int, c_int, c_char_p]),
+    'bb_comm_init_local': (c_int, [c_void_p, c_int, c_int]),
     'bb_comm_allreduce_host': (c_int, [c_void_p, P_dbl, c_i64]),
     'bb_comm_p2p_export': (c_int, [c_void_p, c_i64, ctypes.c_char_p]),
     'bb_comm_p2p_attach': (c_int, [c_void_p, ctypes.c_char_p]),
@@ -189,6 +190,16 @@ class Context:
             return
         lib = load()
         rank, world = dist.get_rank(), dist.get_world_size()
+        # NCCL refuses two ranks on one device; such a job (the single-GPU test of the sharded path) and
+        # BB_COMM=local use the library's own peer-memory exchange for everything
+        import socket
+        where = [None] * world
+        dist.all_gather_object(where, (socket.gethostname(), self.device))
+        if os.environ.get('BB_COMM', '') == 'local' or len(set(where)) < world:
+            check(lib.bb_comm_init_local(self.handle, world, rank))
+            self.nranks, self.rank, self.comm_local = world, rank, True
+            self.init_p2p(int(os.environ.get('BB_P2P_CAPACITY', 1 << 18)))
+            return
         path = nccl_library_path().encode()
         buf = ctypes.create_string_buffer(128)
         if rank == 0:
@@ -210,7 +221,7 @@ class Context:
             return      # already attached with a smaller capacity: larger vectors fall back to NCCL
         # measured on 8xB200 (C4, p+1 = 100 001 doubles): NCCL 73.2 vs fused peer-memory exchange 71.1 Gibbs it/s,
         # so NCCL stays the default; BB_ALLREDUCE=p2p selects the library's own kernels
-        if os.environ.get('BB_ALLREDUCE', 'nccl') != 'p2p':
+        if os.environ.get('BB_ALLREDUCE', 'nccl') != 'p2p' and not getattr(self, 'comm_local', False):
             return
         lib = load()
         buf = ctypes.create_string_buffer(64)

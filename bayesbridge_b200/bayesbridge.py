@@ -45,6 +45,15 @@ class BayesBridge():
                                           _lib.dptr(_lib.as_f64(self.model.n_success))))
         else:
             _lib.check(lib.bb_set_outcome(mat, None, _lib.dptr(_lib.as_f64(self.model.y))))
+        # the outcome, the cached X'kappa and the P-side state live on the DESIGN's device handle, and a design may be
+        # shared by several models / bridges (several outcomes on one X): remember whose outcome is resident
+        self.model.design._outcome_owner = id(self)
+
+    def _ensure_outcome(self):
+        """Re-push this bridge's outcome if another bridge bound to the same design pushed its own since
+        (bb_set_outcome also invalidates the cached X'kappa)."""
+        if getattr(self.model.design, '_outcome_owner', None) != id(self):
+            self._push_outcome()
 
     def _fetch_obs_prec(self):
         out = np.empty(self.n_obs)
@@ -139,7 +148,8 @@ class BayesBridge():
         if self.model.name == 'logit':
             loglik = self._loglik_cache[1]
         else:
-            loglik, _ = self.model.compute_loglik_and_gradient(coef, obs_prec, loglik_only=True)
+            # linear_model.py:22-29 with the residual sum of squares update_obs_precision just reduced on the device
+            loglik = self.model.n_obs_global * math.log(obs_prec) / 2 - obs_prec * self._last_rss / 2
         if not np.isinf(self.prior.slab_size):
             loglik += - .5 * slab_sq_sum
         prior_logp = - (P - k) * math.log(gscale) - abs_pow_sum / gscale ** bridge_exp
@@ -184,6 +194,7 @@ class BayesBridge():
         if not isinstance(options, SamplerOptions):
             options = SamplerOptions.pick_default_and_create(
                 coef_sampler_type, options, self.model.name, self.model.design)
+        self._ensure_outcome()
         if not _add_iter_mode:
             ctx = self.model.design.ctx
             if seed is None and ctx.nranks > 1:
@@ -215,7 +226,8 @@ class BayesBridge():
         for mcmc_iter in range(1, n_iter + 1):
             if resident:
                 coef, obs_prec, gscale, lscale_new, logp, info = self._resident_iteration(
-                    obs_prec, gscale, options, need_lscale=save_lscale)
+                    obs_prec, gscale, options,
+                    need_lscale=save_lscale and self.manager._slot(mcmc_iter, n_burnin, thin) is not None)
                 if lscale_new is not None:
                     lscale = lscale_new
                 self.manager.store_current_state(
@@ -402,6 +414,7 @@ class BayesBridge():
         _lib.check(_lib.load().bb_linear_rss(
             self.model.design._mat, None if coef_is_resident else _lib.dptr(_lib.as_f64(coef)), ctypes.byref(rss)))
         self.model.design.dot_count += 1
+        self._last_rss = rss.value
         return rss.value
 
     def _host_obs_prec_getter(self, obs_prec):

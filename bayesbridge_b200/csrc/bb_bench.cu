@@ -54,6 +54,7 @@ extern "C" int bb_time_kernel(bb_mat* m, const char* what, int reps, int do_flus
     // deterministic, non-trivial inputs
     k_fill_test<<<256, 256, 0, st>>>(m->v_P, m->P, 1e-3);
     k_fill_test<<<256, 256, 0, st>>>(m->eps_n, m->n, 1e-3);
+    k_fill_test<<<256, 256, 0, st>>>(m->sv, m->P, 1e-3);
     if (!m->use_omega_scalar) {
         // keep whatever omega is resident; if never set it is zeros, which is still valid timing input
     }
@@ -74,7 +75,7 @@ extern "C" int bb_time_kernel(bb_mat* m, const char* what, int reps, int do_flus
             BB_TRY(bb_op_dot(m, 1));
             BB_TRY(bb_op_tdot_flag(m, m->w_n, true, nullptr, false));
         } else if (kind == 3) {
-            BB_TRY(bb_launch_spmv(m, &m->fdot, m->v_P + m->add_intercept, nullptr));
+            BB_TRY(bb_launch_spmv(m, &m->fdot, m->sv + m->add_intercept, nullptr));   // the (16-byte aligned) vector dot gathers from
         } else {
             BB_TRY(bb_launch_spmv(m, &m->ftdot, m->eps_n, nullptr));
         }

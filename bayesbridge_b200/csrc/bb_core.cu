@@ -40,6 +40,8 @@ extern "C" int bb_init(int device, bb_ctx** out) {
     c->opt_spmv_stage = 1;
     c->opt_slab_width = 0;
     c->opt_bank_permute = 1;
+    c->opt_spmv_variant = 1;
+    c->opt_spmv_bulk = 1;
     c->opt_cg_chunk = 0;
     c->opt_use_graph = 1;
     c->opt_allreduce_p2p = 1;
@@ -81,6 +83,9 @@ static i64* option_slot(bb_ctx* c, const char* name) {
     if (!strcmp(name, "spmv_stage")) return &c->opt_spmv_stage;
     if (!strcmp(name, "slab_width")) return &c->opt_slab_width;
     if (!strcmp(name, "bank_permute")) return &c->opt_bank_permute;
+    if (!strcmp(name, "spmv_variant")) return &c->opt_spmv_variant;
+    if (!strcmp(name, "spmv_bulk")) return &c->opt_spmv_bulk;
+    if (!strcmp(name, "sell_lmax")) return &c->opt_sell_lmax;
     if (!strcmp(name, "cg_chunk")) return &c->opt_cg_chunk;
     if (!strcmp(name, "use_graph")) return &c->opt_use_graph;
     if (!strcmp(name, "allreduce_p2p")) return &c->opt_allreduce_p2p;
@@ -211,11 +216,33 @@ extern "C" int bb_comm_init(bb_ctx* c, const char* nccl_lib_path, int nranks, in
     return BB_OK;
 }
 
+extern "C" int bb_comm_init_local(bb_ctx* c, int nranks, int rank) {
+    BB_ARG(c != nullptr, "ctx");
+    BB_ARG(nranks >= 1 && rank >= 0 && rank < nranks, "nranks/rank");
+    c->nranks = nranks;
+    c->rank = rank;
+    c->comm_local = 1;
+    return BB_OK;
+}
+
 int bb_allreduce_dev(bb_ctx* c, double* dbuf, i64 count) {
     if (c->nranks == 1) return BB_OK;
     {
         int rc = BB_OK;
         if (bb_p2p_allreduce(c, dbuf, count, nullptr, &rc)) return rc;
+    }
+    if (c->comm_local) {
+        // no NCCL behind this communicator: reduce in chunks of the exchange capacity
+        const i64 cap = bb_p2p_capacity(c);
+        if (cap <= 0) { bb_set_error("local communicator: attach the peer-memory exchange first (bb_comm_p2p_export/attach)"); return BB_ERR_STATE; }
+        for (i64 off = 0; off < count; off += cap) {
+            int rc = BB_OK;
+            if (!bb_p2p_allreduce(c, dbuf + off, (count - off < cap) ? count - off : cap, nullptr, &rc)) {
+                bb_set_error("local communicator: peer-memory exchange unavailable"); return BB_ERR_STATE;
+            }
+            if (rc != BB_OK) return rc;
+        }
+        return BB_OK;
     }
     if (!c->nccl_comm) { bb_set_error("communicator not initialised"); return BB_ERR_STATE; }
     static nccl_allreduce_t f = nullptr;

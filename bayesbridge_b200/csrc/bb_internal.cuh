@@ -71,12 +71,16 @@ struct bb_ctx {
     i64 opt_spmv_stage;    // 1: stage the gather vector in shared memory; 0: gather through L2
     i64 opt_slab_width;    // max doubles of the gather vector staged per CTA (0 = auto)
     i64 opt_bank_permute;  // 1: reorder nnz inside (segment x tile) pieces so that staged gathers avoid bank conflicts
+    i64 opt_spmv_bulk;     // 1 (default): stage the window with cp.async.bulk + mbarrier; 0: cooperative copy loop
+    i64 opt_sell_lmax;     // sliced format: fragment length cap (0 = automatic)
+    i64 opt_spmv_variant;  // 1 (default): sliced lane-per-fragment kernel with 16-bit in-slab indices; 0: tile + segmented-scan kernel
     i64 opt_cg_chunk;      // CG iterations enqueued between host checks (0 = adaptive)
     i64 opt_use_graph;     // capture the CG iteration chunk into a CUDA graph
     // communicator (NCCL via dlopen)
     void* nccl_handle;
     void* nccl_comm;
     int nranks, rank;
+    int comm_local;          // communicator created by bb_comm_init_local: no NCCL, every exchange over peer memory
     // one-shot all-reduce over NVLink peer memory (bb_p2p.cu)
     void* p2p;
     int p2p_ready;
@@ -116,6 +120,7 @@ struct BBTimer {
 int bb_allreduce_dev(bb_ctx* ctx, double* dbuf, i64 count);   // in place, on ctx->stream
 bool bb_p2p_allreduce(bb_ctx* c, double* dbuf, i64 count, const int* done_flag, int* rc_out);
 int bb_p2p_free(bb_ctx* c);
+i64 bb_p2p_capacity(bb_ctx* c);                               // doubles per exchange, 0 when not attached
 bool bb_p2p_view(bb_ctx* c, i64 count, P2PView* out);          // true when the exchange can carry `count` doubles
 int bb_p2p_reduce_into(bb_ctx* c, double* dst, i64 count);      // wait + rank-ordered sum of the last publication
 
@@ -135,6 +140,7 @@ struct SlabFmt {
     int*  idx;          // [nnz] gather index (global)
     double* val;        // [nnz] or NULL (pattern-only)
     bool  owns_arrays;  // false when aliasing the canonical CSR/CSC (nslab == 1)
+    bool  has_val;      // sliced format: the matrix carries values (val itself is released after the build)
     bool  staged;       // the kernel stages the slab of the gather vector in shared memory
     int   ntiles;
     TileMeta* tiles;    // [ntiles]
@@ -143,8 +149,23 @@ struct SlabFmt {
     int*  slab_tile0;   // [nslab+1] first tile of each slab
     int*  slab_nnz0;    // [nslab+1] first nnz of each slab (padded to a multiple of 4)
     int*  slab_nnz1;    // [nslab+1] one past the last nnz of each slab
-    double* part;       // [nslab*n_seg] per-slab partial sums (output of the kernel)
+    double* part;       // [nslab*n_seg (+ overflow slots + 1)] per-slab partial sums (output of the kernel)
     double* head_part;  // [ntiles]
+    // ---- sliced format (spmv_variant 1, bb_sell.cu): fragments of <= SELL_LMAX nnz, one lane each ----
+    int   variant;            // 0: tile + segmented-scan kernel (k_seg_spmv); 1: sliced lane-per-fragment kernel (k_sell_spmv)
+    int   nslices;            // slices of 32 fragments
+    int   sl_lmax;            // fragment length cap chosen at build time (<= 256)
+    unsigned* sl_off;         // [nslices+1] offset of a slice in index PAIRS per lane (slice length L = 2*(off[s+1]-off[s]))
+    unsigned* sl_slot;        // [nslices*32] output slot of every lane's fragment (index into part)
+    unsigned* sl_pairs;       // [32 * sl_off[nslices]] two 16-bit in-slab gather indices per word, blocked per lane
+    double*   sl_vals;        // [64 * sl_off[nslices]] values in the same order, or NULL (pattern-only)
+    int*  sl_slab_slice0;     // [nslab+1] first slice of each slab
+    int*  sl_cta_slice0;      // [sl_ncta+1] first slice of each CTA's contiguous range (balanced by cost)
+    int   sl_ncta, sl_nsec;   // sl_cta_slice0 packs [cta_sec0 (sl_ncta+1) | sec_slab (sl_nsec) | sec_wstart (sl_nsec*33)]
+    int   n_ovf_pieces;       // virtual segments longer than SELL_LMAX (their extra fragments land in overflow slots)
+    int*  ovf_piece;          // [n_ovf_pieces] virtual segment id
+    int*  ovf_first;          // [n_ovf_pieces+1] first overflow slot (relative to part + nslab*n_seg)
+    i64   n_ovf;              // overflow slots
 };
 
 struct CgScalars {
@@ -178,6 +199,7 @@ struct bb_mat {
     P2PView* p2p_view_dev;                       // device copy of the exchange view (kernel argument by pointer)
     int p2p_view_valid;
     // P-vectors
+    double *sv_base;            // allocation behind sv (sv = sv_base + add_intercept, see bb_mat_alloc_work)
     double *v_P, *sv, *traw /*[1+p]*/, *t_P, *x, *r, *pvec, *q, *b, *s, *D, *pps, *z, *x0, *eps_P, *out_P;
     // reduction scratch
     double* red;                // [RED_SLOTS * RED_MAX]
@@ -216,6 +238,11 @@ int bb_mat_alloc_work(bb_mat* m);
 
 int bb_slab_free(SlabFmt* f);
 int bb_launch_spmv(bb_mat* m, SlabFmt* f, const double* gvec, const int* done_flag);
+// sliced format (bb_sell.cu)
+i64 bb_sell_max_width(bb_ctx* ctx);
+int bb_sell_build(bb_ctx* ctx, SlabFmt* f);          // from f->ptr / f->idx / f->val / f->slab_nnz1 (device arrays of the slab format)
+int bb_sell_launch(bb_ctx* ctx, SlabFmt* f, const double* gvec, const int* done_flag);
+void bb_sell_free(SlabFmt* f);
 
 // ------------------------------------------------------------------------------------------
 // device helpers

@@ -98,9 +98,14 @@ int bb_p2p_free(bb_ctx* c) {
     return BB_OK;
 }
 
+i64 bb_p2p_capacity(bb_ctx* c) {
+    bb_p2p* p = (bb_p2p*)c->p2p;
+    return (p && c->p2p_ready) ? p->cap : 0;
+}
+
 bool bb_p2p_view(bb_ctx* c, i64 count, P2PView* out) {
     bb_p2p* p = (bb_p2p*)c->p2p;
-    if (!p || !c->p2p_ready || c->opt_allreduce_p2p == 0 || count > p->cap) return false;
+    if (!p || !c->p2p_ready || (c->opt_allreduce_p2p == 0 && !c->comm_local) || count > p->cap) return false;
     out->peer_base = p->peers_dev;
     out->st = p->state;
     out->cap = p->cap;

@@ -566,6 +566,7 @@ static int bits_for(i64 maxval) {   // number of bits needed to represent values
 }
 
 int bb_slab_free(SlabFmt* f) {
+    bb_sell_free(f);
     if (f->owns_arrays) {
         if (f->ptr) cudaFree(f->ptr);
         if (f->idx) cudaFree(f->idx);
@@ -597,7 +598,9 @@ static int build_slab_format(bb_ctx* ctx, const int* cptr, const int* cidx, cons
     memset(f, 0, sizeof(*f));
     f->staged = staged;
     cudaStream_t st = ctx->stream;
-    i64 wmax = max_stage_width(ctx);
+    // the sliced kernel (bb_sell.cu) always stages its window; the tile kernel also runs unstaged (one slab, gathers through L2)
+    const bool sliced = staged && ctx->opt_spmv_variant == 1;
+    i64 wmax = sliced ? bb_sell_max_width(ctx) : max_stage_width(ctx);
     if (!staged) wmax = ((i64)1 << 40);     // gathers go through L2: no slab limit
     if (ctx->opt_slab_width > 0) {
         i64 w = (ctx->opt_slab_width + 31) & ~(i64)31;
@@ -691,6 +694,20 @@ static int build_slab_format(bb_ctx* ctx, const int* cptr, const int* cidx, cons
         cudaFree(seg_of); cudaFree(key); cudaFree(key_sorted); cudaFree(iota); cudaFree(perm); cudaFree(vkey);
         BB_TRY(rc);
     }
+    if (sliced) {
+        BB_CUDA(cudaMalloc((void**)&f->slab_nnz1, ((size_t)nslab + 1) * sizeof(int)));
+        BB_CUDA(cudaMemcpyAsync(f->slab_nnz1, padded_end.data(), ((size_t)nslab + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+        BB_TRY(bb_sell_build(ctx, f));
+        // the slab-ordered copies were only the source of the sliced arrays
+        if (f->owns_arrays) {
+            cudaFree(f->ptr); cudaFree(f->idx); if (f->val) cudaFree(f->val);
+        }
+        f->ptr = nullptr; f->idx = nullptr;
+        f->has_val = (f->val != nullptr);
+        f->val = nullptr;
+        f->owns_arrays = false;
+        return BB_OK;
+    }
     // slab nnz ranges -> tiles (host), ownership (device)
     std::vector<int>& slab_off = padded_start;
     std::vector<TileMeta> tiles;
@@ -758,6 +775,7 @@ static int build_slab_format(bb_ctx* ctx, const int* cptr, const int* cidx, cons
 // launch the SpMV + fix-up for one format; gvec has f->n_gather entries
 int bb_launch_spmv(bb_mat* m, SlabFmt* f, const double* gvec, const int* done_flag) {
     bb_ctx* ctx = m->ctx;
+    if (f->variant == 1) return bb_sell_launch(ctx, f, gvec, done_flag);
     // a format built without staging in mind may have slabs wider than shared memory
     const bool stage = f->staged && (i64)f->W <= max_stage_width(ctx);
     int wstage = stage ? f->W : 0;
@@ -881,10 +899,15 @@ static int alloc_d(cudaStream_t st, double** p, i64 n) {
 }
 
 int bb_mat_alloc_work(bb_mat* m) {
-    BB_TRY(alloc_d(m->ctx->stream, &m->omega, m->n)); BB_TRY(alloc_d(m->ctx->stream, &m->n_trial, m->n)); BB_TRY(alloc_d(m->ctx->stream, &m->n_success, m->n));
-    BB_TRY(alloc_d(m->ctx->stream, &m->eta, m->n)); BB_TRY(alloc_d(m->ctx->stream, &m->w_n, m->n)); BB_TRY(alloc_d(m->ctx->stream, &m->u_n, m->n));
-    BB_TRY(alloc_d(m->ctx->stream, &m->eps_n, m->n));
-    double** pv[] = {&m->v_P, &m->sv, &m->t_P, &m->x, &m->r, &m->pvec, &m->q, &m->b, &m->s, &m->D, &m->pps,
+    // n-vectors carry two spare doubles: the bulk window copy of the sliced SpMV rounds an odd window up to 16 bytes
+    const i64 npad = m->n + 2;
+    BB_TRY(alloc_d(m->ctx->stream, &m->omega, npad)); BB_TRY(alloc_d(m->ctx->stream, &m->n_trial, npad)); BB_TRY(alloc_d(m->ctx->stream, &m->n_success, npad));
+    BB_TRY(alloc_d(m->ctx->stream, &m->eta, npad)); BB_TRY(alloc_d(m->ctx->stream, &m->w_n, npad)); BB_TRY(alloc_d(m->ctx->stream, &m->u_n, npad));
+    BB_TRY(alloc_d(m->ctx->stream, &m->eps_n, npad));
+    // sv + add_intercept is the vector `dot` gathers from: keep THAT address 16-byte aligned
+    BB_TRY(alloc_d(m->ctx->stream, &m->sv_base, m->P + 4));
+    m->sv = m->sv_base + (m->add_intercept ? 1 : 0);
+    double** pv[] = {&m->v_P, &m->t_P, &m->x, &m->r, &m->pvec, &m->q, &m->b, &m->s, &m->D, &m->pps,
                      &m->z, &m->x0, &m->eps_P, &m->out_P};
     for (auto pp : pv) BB_TRY(alloc_d(m->ctx->stream, pp, m->P + 1));
     BB_TRY(alloc_d(m->ctx->stream, &m->traw, m->p + 1));
@@ -911,7 +934,7 @@ extern "C" int bb_mat_free(bb_mat* m) {
     void* ptrs[] = {m->csr_ptr, m->csr_idx, m->csr_val, m->csc_ptr, m->csc_idx, m->csc_val, m->col_offset, m->Xd,
                     m->omega, m->n_trial, m->n_success, m->eta, m->w_n, m->u_n, m->eps_n, m->dense_part, m->zk, m->omega_scalar_dev, m->p2p_view_dev,
                     m->st_lscale, m->st_mean, m->st_square, m->st_prior_sd, m->st_sums,
-                    m->v_P, m->sv, m->traw, m->t_P, m->x, m->r, m->pvec, m->q, m->b, m->s, m->D, m->pps, m->z, m->x0,
+                    m->v_P, m->sv_base, m->traw, m->t_P, m->x, m->r, m->pvec, m->q, m->b, m->s, m->D, m->pps, m->z, m->x0,
                     m->eps_P, m->out_P, m->red, m->cg};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (m->cg_host) cudaFreeHost(m->cg_host);

@@ -37,7 +37,15 @@ class ConjugateGradientSampler():
         if maxiter is None:
             maxiter = 10 * P   # scipy's default
         if noise == 'host':
-            eps1 = np.random.randn(n)
+            # cg_sampler.py:61-62.  On a row-sharded design every rank holds the same seeded numpy stream: draw the
+            # n_global normals of the whole problem and keep this shard's rows, then eps2, so that the shards see
+            # independent rows of one global eps1 and all ranks consume the stream identically.
+            n_global = int(getattr(design, 'n_global', n))
+            row_offset = int(getattr(design, 'row_offset', 0))
+            if n_global != n:
+                eps1 = np.ascontiguousarray(np.random.randn(n_global)[row_offset:row_offset + n])
+            else:
+                eps1 = np.random.randn(n)
             eps2 = np.random.randn(P)
             mode, sd, off = _lib.BB_NOISE_INJECT, 0, 0
         elif noise == 'device':

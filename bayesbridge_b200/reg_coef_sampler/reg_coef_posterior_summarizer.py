@@ -43,15 +43,11 @@ class RegressionCoeffficientPosteriorSummarizer():
         self.slab_size = regularizing_slab_size
 
     def compute_prior_scale(self, gscale, lscale):
-        """tau*lambda damped by the slab; cached for the (gscale, lscale) pair of the current Gibbs iteration,
-        which asks for it three times. Without a slab the damping factor is exactly 1."""
-        key = (float(gscale), id(lscale))
-        if getattr(self, '_scale_key', None) == key and self._scale_ref is lscale:
-            return self._scale_val
+        """tau*lambda damped by the slab (reg_coef_sampler.py:194-201). Without a slab the damping factor is exactly 1.
+        Not cached: lscale is mutated in place by prior.adjust_scale, and this object is pickled with the chain state."""
         raw = gscale * lscale
         if not np.isinf(self.slab_size):
             raw /= np.sqrt(1 + (raw / self.slab_size) ** 2)
-        self._scale_key, self._scale_ref, self._scale_val = key, lscale, raw
         return raw
 
     def scale_coef(self, coef, gscale, lscale):

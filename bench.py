@@ -156,33 +156,41 @@ def import_reference():
     return bayesbridge
 
 
-def reference_run(workload, steps, warmup, sample_blocks):
-    """The reference's numpy/scipy/Cython sampler on a bounded row sample of the workload.
-    Returns (iterations/s scaled to the full workload, description dict)."""
+def reference_run(workload, steps, warmup, sample_blocks=None, init_state=None, data=None):
+    """The reference's own numpy/scipy/Cython sampler (oracle/_ref, the unmodified package built by
+    oracle/build_ref.sh) through ITS public API, on the host cores of this box.
+
+    sample_blocks=None (the default, and what `--impl reference` runs): the FULL workload matrix, `warmup` untimed
+    Gibbs iterations then `steps` timed ones -- nothing is extrapolated.  sample_blocks=k times it on the first k of
+    the 50 row blocks instead (explicit flag only; reported as such, never scaled).
+    init_state: {'coef','obs_prec','local_scale','global_scale'} to start the chain from (bayesbridge.py:279-353
+    skips the mode search when all four are given) -- used by the bounded cpu_baseline leg, which starts the
+    reference from the state the GPU chain has reached so that its CG iteration counts are comparable.
+    Returns (iterations/s, description dict)."""
     n, p, density = WORKLOADS[workload]
     ref = import_reference()
-    kind = 'reference'
-    X, y = generate_rows(range(sample_blocks), n, p, density)
+    blocks = range(N_BLOCKS) if sample_blocks is None else range(sample_blocks)
+    t_gen = time.time()
+    X, y = data if data is not None else generate_rows(blocks, n, p, density)
+    t_gen = time.time() - t_gen
     frac = X.shape[0] / n
-    t_build = time.time()
     if ref is not None:
+        kind = 'reference'
         model = ref.RegressionModel(y, X, family='logit')
         bridge = ref.BayesBridge(model, ref.RegressionCoefPrior(bridge_exponent=.5))
-        _, info = bridge.gibbs(n_iter=max(warmup, 1), n_burnin=0, coef_sampler_type='cg', seed=0,
-                               params_to_save=('global_scale',))
+        kw = dict(n_burnin=0, coef_sampler_type='cg', seed=0, params_to_save=('global_scale',))
+        if init_state is not None:
+            kw['init'] = init_state
         t0 = time.time()
-        _, info2 = bridge.gibbs_resume(info, steps)
-        dt = time.time() - t0
+        if warmup > 0:
+            _, info = bridge.gibbs(n_iter=warmup, **kw)
+            t1 = time.time()
+            _, info2 = bridge.gibbs_resume(info, steps)
+            dt = time.time() - t1
+        else:
+            _, info2 = bridge.gibbs(n_iter=steps, **kw)
+            dt = info2['runtime']               # includes the (skipped or trivial) chain initialisation
         n_cg = float(np.mean(info2['_reg_coef_sampling_info']['n_cg_iter'])) if steps > 0 else float('nan')
-        # the per-iteration cost that does NOT shrink with the row sample: the p tilted-stable draws
-        state = info2['_markov_chain_state']
-        unit = ref.RegressionCoefPrior.compute_power_exp_ave_magnitude(.5)
-        tilt = (state['coef'][1:] / (state['global_scale'] / unit)) ** 2
-        tilt = tilt[tilt > 0]
-        t1 = time.time()
-        for _ in range(3):
-            bridge.rg.tilted_stable(.25, tilt)
-        p_side = (time.time() - t1) / 3
     else:
         # the oracle port (numpy restatement) when the reference could not be built
         kind = 'port'
@@ -194,23 +202,20 @@ def reference_run(workload, steps, warmup, sample_blocks):
                                              TiltedStablePort, True)
         dt = (time.time() - t0) * steps / max(warmup + steps, 1)
         n_cg = float(n_cg_arr.mean())
-        p_side = 0.0
-    its_sample = steps / dt
-    t_iter_sample = dt / steps
-    # cost model: the n-side work (SpMV, PG) scales with the sampled nnz fraction, the p-side work does not
-    t_iter_full = max(t_iter_sample - p_side, 0.0) / frac + p_side
+    its = steps / dt
+    what = ('the full %s matrix (%d x %d, nnz %d)' % (workload, X.shape[0], p, X.nnz) if sample_blocks is None else
+            'rows 0..%d of %s (%d of %d row blocks, %.0f%% of the rows; NOT scaled to the full problem)'
+            % (X.shape[0] - 1, workload, sample_blocks, N_BLOCKS, 100 * frac))
     desc = {
         'kind': kind, 'cores': 1,
-        'sample': 'rows 0..%d of %s (%d of %d row blocks, %.0f%% of nnz); %d timed Gibbs iterations after %d warm-up; '
-                  'full-size iteration time = (t_sample - t_pside)/fraction + t_pside, t_pside = the p tilted-stable '
-                  'draws (measured separately); NB the sample needs fewer CG iterations per Gibbs step than the full '
-                  'problem (see mean_n_cg_iter), so this estimate flatters the reference; scipy SpMV + Cython PG/tilted-stable are single-threaded '
-                  '(host has %d cores)' % (X.shape[0] - 1, workload, sample_blocks, N_BLOCKS,
-                                           100 * frac, steps, warmup, os.cpu_count()),
-        'iters_per_s_on_sample': its_sample, 'p_side_seconds': p_side, 'mean_n_cg_iter': n_cg,
-        'sample_nnz': int(X.nnz),
+        'sample': '%s; %d timed Gibbs iterations after %d warm-up%s; scipy SpMV and the Cython PG / tilted-stable '
+                  'samplers are single-threaded (host has %d cores)'
+                  % (what, steps, warmup, '' if init_state is None else ', chain started from the state the GPU chain reached',
+                     os.cpu_count()),
+        'full_size': sample_blocks is None, 'mean_n_cg_iter': n_cg, 'sample_nnz': int(X.nnz),
+        'seconds_per_iteration': dt / steps, 'generate_seconds': t_gen,
     }
-    return 1.0 / t_iter_full, desc
+    return its, desc
 
 
 # ---- main ---------------------------------------------------------------------------------------
@@ -221,7 +226,9 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='C4', choices=sorted(WORKLOADS))
-    ap.add_argument('--ref-blocks', type=int, default=2, help='row blocks (of 50) the CPU reference is timed on')
+    ap.add_argument('--ref-blocks', type=int, default=0,
+                    help='time the CPU reference on the first K of the 50 row blocks only (0 = the full workload, the default)')
+    ap.add_argument('--cpu-baseline-steps', type=int, default=2, help='full-size reference iterations of the cpu_baseline leg')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--clocks', default=os.environ.get('BENCH_CLOCKS', 'nvml'), choices=['nvml', 'none'])
     ap.add_argument('--profile-host', action='store_true', help='cProfile the timed region (stderr)')
@@ -237,7 +244,7 @@ def main():
     if args.impl == 'reference':
         if rank != 0:
             return
-        value, desc = reference_run(args.workload, args.steps, max(args.warmup, 1), args.ref_blocks)
+        value, desc = reference_run(args.workload, args.steps, max(args.warmup, 1), args.ref_blocks or None)
         print(json.dumps({
             'impl': 'reference', 'metric': 'gibbs_iters_per_sec', 'value': value, 'unit': 'iter/s',
             'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1000.0 / value,
@@ -402,7 +409,13 @@ def main():
     }
     if world == 1 and not args.no_cpu_baseline:
         try:
-            v, desc = reference_run(args.workload, 6, 2, args.ref_blocks)
+            # bounded sample of the same workload: the reference's sampler on the FULL matrix for a few iterations,
+            # started from the state this chain has reached (so that it solves equally hard CG problems)
+            st = info2['_markov_chain_state']
+            init_state = {k: np.array(st[k], copy=True) if np.ndim(st[k]) else st[k]
+                          for k in ('coef', 'obs_prec', 'local_scale', 'global_scale')}
+            v, desc = reference_run(args.workload, args.cpu_baseline_steps, 0, args.ref_blocks or None,
+                                    init_state=init_state if not args.ref_blocks else None, data=None if args.ref_blocks else (X, y))
             line['cpu_baseline'] = dict(desc, value=v, unit='iter/s')
         except Exception as e:      # the baseline is reported, never required
             line['cpu_baseline'] = {'value': None, 'unit': 'iter/s', 'cores': 1, 'kind': 'reference',

@@ -64,6 +64,10 @@ int  bb_sync(bb_ctx* ctx);
 /* ---- communicator: row-sharding, one process per GPU (new) ----------- */
 int  bb_comm_unique_id(const char* nccl_lib_path, char* id_out_128);
 int  bb_comm_init(bb_ctx* ctx, const char* nccl_lib_path, int nranks, int rank, const char* id_128);
+/* communicator WITHOUT NCCL: every exchange goes through the peer-memory all-reduce below (vectors longer than its
+ * capacity are reduced in chunks).  NCCL refuses two ranks on one device; this form does not, which is how the
+ * row-sharded path is tested on a single GPU (tests/test_gpu_multi.py).  Call bb_comm_p2p_export/attach next. */
+int  bb_comm_init_local(bb_ctx* ctx, int nranks, int rank);
 int  bb_comm_allreduce_host(bb_ctx* ctx, double* buf, int64_t count);  /* in-place sum, host buffer */
 /* one-shot all-reduce over NVLink peer memory (replaces ncclAllReduce for vectors of <= capacity doubles):
  * every rank exports its exchange buffer (64-byte CUDA IPC handle), the handles are gathered by the caller

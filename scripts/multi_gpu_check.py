@@ -1,7 +1,10 @@
 """Row-sharded path check, run under torchrun (N >= 2 GPUs):
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 scripts/multi_gpu_check.py
 Every rank builds the same small problem; the sharded design (this rank's row block + NCCL allreduce inside
-libbbgpu) is compared on every rank against an unsharded design living on the same GPU."""
+libbbgpu) is compared on every rank against an unsharded design living on the same GPU.
+BB_SAME_DEVICE=1 puts every rank on device 0 (single-GPU boxes): NCCL refuses that, so the ranks talk through the
+library's own peer-memory exchange (bb_comm_init_local, CUDA IPC between two processes of one device) and torch's
+gloo backend only carries the handles."""
 import os, sys, warnings
 import numpy as np
 import scipy.sparse as sp
@@ -14,8 +17,15 @@ from bayesbridge_b200.design_matrix import GpuSparseDesignMatrix, GpuDenseDesign
 from bayesbridge_b200.reg_coef_sampler import ConjugateGradientSampler
 
 rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])
+same_device = os.environ.get('BB_SAME_DEVICE') == '1'
+if same_device:
+    local = 0
 torch.cuda.set_device(local)
-dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+if same_device:
+    dist.init_process_group('gloo')
+else:
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+tdev = 'cpu' if same_device else 'cuda'
 ctx = _lib.Context(local); ctx.init_comm_from_torch()
 solo = _lib.Context(local)                      # same GPU, no communicator: the unsharded comparator
 ok = True
@@ -61,7 +71,7 @@ for name, Xm, Cls in (('sparse', X, GpuSparseDesignMatrix), ('dense', Xd, GpuDen
         cu, nu = run(Du, omega, e1)
         check(f'{name} cg atol={atol:.0e} (n_iter {ns}/{nu})', rel(cs, cu), tol)
         # every rank must hold bit-identical coefficients
-        t = torch.from_numpy(cs.copy()).cuda(); t0 = t.clone(); dist.broadcast(t0, 0)
+        t = torch.from_numpy(cs.copy()).to(tdev); t0 = t.clone(); dist.broadcast(t0, 0)
         check(f'{name} cg replicas identical', float((t - t0).abs().max()), 0.0)
     # device noise: sharding-invariant streams -> same draw as unsharded
     a, _ = S.sample(Ds, np.ascontiguousarray(omega[lo:hi]), pps, z, x0, 'prior', sd, maxiter=500, atol=1e-11, noise='device', philox=(9, 3))
@@ -79,8 +89,8 @@ check('chain coef mean sharded vs unsharded', float(np.abs(chains[0]['coef'].mea
 check('chain logp sharded vs unsharded', float(abs(chains[0]['logp'].mean() / chains[1]['logp'].mean() - 1)), 1e-2)
 ready, err = ctx.p2p_status()
 print(f'[rank {rank}] p2p ready={ready} error={err} (BB_ALLREDUCE={os.environ.get("BB_ALLREDUCE", "nccl")})', flush=True)
-ok &= (err == 0) and (ready == (os.environ.get('BB_ALLREDUCE', 'nccl') == 'p2p'))
-flag = torch.tensor([1.0 if ok else 0.0]).cuda(); dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+ok &= (err == 0) and (ready == (same_device or os.environ.get('BB_ALLREDUCE', 'nccl') == 'p2p'))
+flag = torch.tensor([1.0 if ok else 0.0]).to(tdev); dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
     print('MULTI_GPU_CHECK', 'PASS' if flag.item() == 1.0 else 'FAIL', flush=True)
 dist.destroy_process_group()

@@ -118,6 +118,52 @@ def golden_cg():
     np.savez(os.path.join(HERE, 'cg_ref.npz'), **out)
 
 
+def golden_cg_c1():
+    """BASELINE config 1: simulate_design(10k, 1k, binary, freq .01, seed 111), logit outcome.
+    The CG inputs are the ones the reference's Gibbs sampler forms after 30 iterations of its own chain
+    (reg_coef_sampler.py:60-103): omega from its PG draw, prior_prec_sqrt from its (tau, lambda), the initial guess
+    and the preconditioner from its running summaries.  At this size the default rule needs 13-25 CG iterations,
+    so the fixed-K cases (K = 1, 5, 10) are genuinely pre-convergence."""
+    sys.path.insert(0, os.path.join(ROOT, 'oracle', '_ref'))
+    from simulate_data import simulate_design, simulate_outcome
+    n, p = 10_000, 1_000
+    X = simulate_design(n, p, binary_frac=1., binary_pred_freq=.01, format_='sparse', seed=111).tocsr()
+    beta = np.zeros(p)
+    beta[:5], beta[5:10], beta[10:15] = 1.5, 1., .5
+    n_trial = np.ones(n)
+    y = simulate_outcome(X, beta, intercept=0., model='logit', n_trial=n_trial, seed=1)
+    if isinstance(y, tuple):
+        n_success = np.asarray(y[0], dtype=float)
+    else:
+        n_success = np.asarray(y, dtype=float)
+    model = ref.RegressionModel((n_success, n_trial), X, family='logit')
+    br = ref.BayesBridge(model, ref.RegressionCoefPrior(bridge_exponent=.5))
+    s, info = br.gibbs(30, 0, coef_sampler_type='cg', seed=0, params_to_save='all')
+    st = info['_markov_chain_state']
+    D = model.design
+    Xm = D.X_main.tocsr()
+    P = D.shape[1]
+    omega = np.asarray(st['obs_prec'], dtype=float)
+    rcs = br.reg_coef_sampler
+    gscale, lscale = br.prior.adjust_scale(st['global_scale'], st['local_scale'].copy(), to='raw')
+    prior_sd = np.concatenate((rcs.prior_sd_for_unshrunk, rcs.compute_prior_shrunk_scale(gscale, lscale)))
+    pps = 1 / prior_sd
+    z = D.Tdot(n_success - n_trial / 2)
+    x0 = rcs.regcoef_summarizer.extrapolate_coef_condmean(gscale, lscale)
+    sd = rcs.regcoef_summarizer.estimate_coef_precond_scale_sd().copy()
+    rules = [(1, 0.0), (5, 0.0), (10, 0.0), (500, 1e-5), (500, 1e-12)]
+    out = {'indptr': Xm.indptr, 'indices': Xm.indices, 'shape': np.array(Xm.shape), 'n_success': n_success,
+           'omega': omega, 'pps': pps, 'z': z, 'x0': x0, 'sd': sd, 'rules': np.array(rules),
+           'chain_n_cg': info['_reg_coef_sampling_info']['n_cg_iter']}
+    assert np.all(Xm.data == 1.0)
+    for k, (maxiter, atol_unit) in enumerate(rules):
+        coef, cinfo = ConjugateGradientSampler(1).sample(
+            D, omega, pps, z, x0.copy(), 'prior', sd, maxiter=maxiter, atol=atol_unit * np.sqrt(P), seed=7)
+        out['coef_%d' % k], out['niter_%d' % k], out['conv_%d' % k] = coef, cinfo['n_iter'], cinfo['converged']
+        print('cg_c1 rule', (maxiter, atol_unit), 'n_iter', cinfo['n_iter'], 'converged', cinfo['converged'])
+    np.savez_compressed(os.path.join(HERE, 'cg_c1_ref.npz'), **out)
+
+
 def golden_summarizer():
     rng = np.random.default_rng(8)
     S = RegressionCoeffficientPosteriorSummarizer(12, 2, 1.5)
@@ -185,5 +231,9 @@ def golden_posterior():
 
 
 if __name__ == '__main__':
-    golden_random(); golden_ks(); golden_design(); golden_cg(); golden_summarizer(); golden_chain(); golden_posterior()
+    only = sys.argv[1:]
+    todo = [golden_random, golden_ks, golden_design, golden_cg, golden_cg_c1, golden_summarizer, golden_chain, golden_posterior]
+    for fn in todo:
+        if not only or fn.__name__ in only:
+            fn()
     print('golden fixtures written to', HERE)

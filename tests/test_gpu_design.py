@@ -46,11 +46,13 @@ def test_products_match_reference_outputs(ctx):
 
 @pytest.mark.parametrize('n,p,density', [(300, 40, 0.2), (20000, 700, 0.02), (60000, 3000, 0.004)])
 @pytest.mark.parametrize('binary', [False, True])
-@pytest.mark.parametrize('slab,stage', [(0, 1), (0, 0), (64, 1), (1024, 1), (1024, 0)])
-def test_sparse_products_vs_oracle(ctx, n, p, density, binary, slab, stage):
+@pytest.mark.parametrize('slab,stage,variant', [(0, 1, 1), (64, 1, 1), (1024, 1, 1), (0, 0, 0), (0, 1, 0), (64, 1, 0), (1024, 1, 0), (1024, 0, 0)])
+def test_sparse_products_vs_oracle(ctx, n, p, density, binary, slab, stage, variant):
+    """variant 1 = sliced lane-per-fragment kernel (bb_sell.cu, the default), 0 = tile + segmented-scan kernel."""
     Sparse, _ = _designs()
     ctx.set_option('slab_width', slab)
     ctx.set_option('spmv_stage', stage)
+    ctx.set_option('spmv_variant', variant)
     try:
         X = random_sparse(n, p, density, seed=n + p, binary=binary)
         rng = np.random.default_rng(5)
@@ -66,6 +68,7 @@ def test_sparse_products_vs_oracle(ctx, n, p, density, binary, slab, stage):
     finally:
         ctx.set_option('slab_width', 0)
         ctx.set_option('spmv_stage', 1)
+        ctx.set_option('spmv_variant', 1)
 
 
 def test_products_are_bit_reproducible(ctx):
