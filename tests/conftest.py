@@ -16,6 +16,21 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
 
 
+def record_achieved(test, case, achieved, bound, **extra):
+    """Append the achieved error of one parity case to gpurun_out/parity_achieved.jsonl (created on demand; merged
+    back from the GPU box by gpurun and copied to profiles/ per round) and print it (visible with pytest -s / -rP)."""
+    import json
+    row = dict(test=test, case=str(case), achieved=float(achieved), bound=float(bound), **extra)
+    print('PARITY', json.dumps(row))
+    try:
+        d = os.path.join(ROOT, 'gpurun_out')
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, 'parity_achieved.jsonl'), 'a') as f:
+            f.write(json.dumps(row) + '\n')
+    except OSError:
+        pass
+
+
 def golden(name):
     return np.load(os.path.join(GOLDEN, name), allow_pickle=False)
 

@@ -5,19 +5,24 @@ import numpy as np
 import scipy.sparse as sp
 import pytest
 
-from conftest import golden
+from conftest import golden, record_achieved
 from oracle import cg_oracle as co
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-8          # north_star: CG solution vs the reference, fp64, same omega and noise
-# Unconverged iterates (maxiter = K, tolerance 0) are a different matter: CG amplifies a 1e-16 change in
-# one matvec to >1e-9 in the K=5 iterate on these very problems (tests/test_oracle_cg.py::
-# test_fixed_iteration_iterates_are_chaotic measures it on the oracle itself), so two correct
-# implementations with different summation orders cannot agree to 1e-8 there; the same holds for a solve
-# stopped at the default tolerance (1e-5*sqrt(P) on the residual, reg_coef_sampler.py:95), which is itself only
-# ~1e-6 from the exact solution. Those cases are held to TOL_ITERATE and to identical iteration counts;
-# TOL applies where the statement "the CG solution" is meaningful: both sides converged (atol = 1e-12*sqrt(P)).
-TOL_ITERATE = 1e-5
+# Per-rule bounds.  Two correct fp64 implementations that sum a product in different orders differ by ~1e-16..1e-15
+# relative per product; CG amplifies that differently at different points of the iteration.  The amplification was
+# MEASURED on the oracle itself by perturbing every dot / Tdot by 1e-16 relative (5 seeds x 2 amplitudes):
+#   fixtures cg_ref.npz  (n <= 800, converge in 4-14 iterations): K=1 2e-16 | K=5 4.8e-10 | K=20 2e-16 | default 1.6e-8 | tight 1e-12
+#   fixture  cg_c1_ref.npz (BASELINE config 1, 10k x 1k, default rule = 21 iterations, tight = 42):
+#                                                                  K=1 6e-17 | K=5 1.3e-8  | K=10 2.8e-11 | default 4.6e-9 | tight 1.8e-14
+# (tests/test_oracle_cg.py::test_perturbation_sensitivity_c1 re-measures the second row.)  The bounds below are
+# ~30-100x those sensitivities -- the device products carry ~1e-15, not 1e-16 -- and never looser than 1e-6; the
+# north-star 1e-8 is required wherever the measured sensitivity allows it (K=1, K>=10, tight) and 1e-7 at the
+# default stopping rule.  Iteration counts must be identical in every case.  Achieved errors are recorded
+# (conftest.record_achieved -> profiles/r02_parity_achieved.jsonl).
+BOUNDS_SMALL = {(1, 0.0): 1e-12, (5, 0.0): 1e-7, (20, 0.0): 1e-10, (500, 1e-5): 1e-7, (500, 1e-12): 1e-10}
+BOUNDS_C1 = {(1, 0.0): 1e-13, (5, 0.0): 1e-6, (10, 0.0): 1e-8, (500, 1e-5): 1e-7, (500, 1e-12): 1e-11}
 
 
 def relerr(a, b):
@@ -44,10 +49,35 @@ def test_cg_sample_matches_reference(ctx, name):
         coef, info = ConjugateGradientSampler(1).sample(
             D, omega, pps, z, x0.copy(), 'prior', sd, maxiter=int(maxiter), atol=atol_unit * np.sqrt(P), seed=7)
         ref = g['%s_coef_%d' % (name, k)]
-        tight = atol_unit > 0 and atol_unit <= 1e-10      # both sides converged far below TOL
-        assert relerr(coef, ref) <= (TOL if tight or maxiter == 1 else TOL_ITERATE), (name, maxiter, atol_unit)
+        bound = BOUNDS_SMALL[(int(maxiter), float(atol_unit))]
+        err = relerr(coef, ref)
+        record_achieved('cg_sample_matches_reference', (name, int(maxiter), float(atol_unit)), err, bound,
+                        n_iter=info['n_iter'])
+        assert err <= bound, (name, maxiter, atol_unit, err)
         assert info['n_iter'] == int(g['%s_niter_%d' % (name, k)])
         assert info['converged'] == bool(g['%s_conv_%d' % (name, k)])
+
+
+def test_cg_sample_matches_reference_c1(ctx):
+    """BASELINE config 1 (10k x 1k binary, the reference's own simulate_design, seed 111) with the CG inputs of the
+    reference's chain after 30 Gibbs iterations (tests/golden/make_golden.py::golden_cg_c1): fixed K = 1, 5, 10 are
+    pre-convergence here (the default rule stops after 21 iterations), then the default and the tight rule."""
+    from bayesbridge_b200.design_matrix import GpuSparseDesignMatrix
+    from bayesbridge_b200.reg_coef_sampler import ConjugateGradientSampler
+    g = golden('cg_c1_ref.npz')
+    X = sp.csr_matrix((np.ones(len(g['indices'])), g['indices'], g['indptr']), shape=tuple(g['shape']))
+    D = GpuSparseDesignMatrix(X, center_predictor=True, add_intercept=True, ctx=ctx)
+    P = D.shape[1]
+    omega, pps, z, x0, sd = (g[k] for k in ('omega', 'pps', 'z', 'x0', 'sd'))
+    for k, (maxiter, atol_unit) in enumerate(g['rules']):
+        coef, info = ConjugateGradientSampler(1).sample(
+            D, omega, pps, z, x0.copy(), 'prior', sd, maxiter=int(maxiter), atol=atol_unit * np.sqrt(P), seed=7)
+        bound = BOUNDS_C1[(int(maxiter), float(atol_unit))]
+        err = relerr(coef, g['coef_%d' % k])
+        record_achieved('cg_sample_matches_reference_c1', (int(maxiter), float(atol_unit)), err, bound, n_iter=info['n_iter'])
+        assert err <= bound, (maxiter, atol_unit, err)
+        assert info['n_iter'] == int(g['niter_%d' % k])
+        assert info['converged'] == bool(g['conv_%d' % k])
 
 
 @pytest.mark.parametrize('n,p,density', [(5000, 400, 0.05), (30000, 2500, 0.01)])
@@ -71,7 +101,9 @@ def test_cg_sample_vs_oracle_and_dense_solve(ctx, n, p, density):
         ref, rinfo = co.cg_sample(O, omega, pps, z, x0, s, 500, atol_unit * np.sqrt(P), e1, e2)
         coef, info = ConjugateGradientSampler(1).sample(
             D, omega, pps, z, x0.copy(), 'prior', sd, maxiter=500, atol=atol_unit * np.sqrt(P), seed=11)
-        assert relerr(coef, ref) <= (TOL if atol_unit <= 1e-10 else TOL_ITERATE)
+        err, bound = relerr(coef, ref), (1e-10 if atol_unit <= 1e-10 else 1e-7)
+        record_achieved('cg_sample_vs_oracle_and_dense_solve', (n, p, atol_unit), err, bound, n_iter=info['n_iter'])
+        assert err <= bound
         assert info['n_iter'] == rinfo['n_iter'] and info['converged']
     if p <= 500:
         # tight solve == the exact Gaussian draw: Phi beta = z + X' sqrt(omega) e1 + pps e2
