@@ -210,18 +210,21 @@ class Context:
         self.nranks, self.rank = world, rank
 
     def init_p2p(self, capacity):
-        """Map every rank's exchange buffer into every other rank (CUDA IPC over NVLink) so that the
-        all-reduces of vectors of <= `capacity` doubles run as libbbgpu's own one-shot peer-memory kernels
-        instead of ncclAllReduce. Collective: every rank must call it. torch.distributed only carries the
-        64-byte IPC handles."""
+        """Map every rank's exchange buffer into every other rank (CUDA IPC over NVLink).  Collective: every rank
+        must call it.  torch.distributed only carries the 64-byte IPC handles.
+
+        The buffers serve two protocols of libbbgpu: the two-shot all-reduce fused into the P-side kernel of every CG
+        iteration (bb_pside.cu; used whenever the buffers are attached and option cg_fused is on), and a one-shot
+        all-reduce for the few other exchanges of a Gibbs step (RHS product, log-likelihood).  The latter go through
+        ncclAllReduce unless BB_ALLREDUCE=p2p (or the communicator is local, i.e. has no NCCL behind it).
+        BB_P2P=0 skips the attachment altogether (everything NCCL, unfused CG iteration)."""
         import torch.distributed as dist
         if self.nranks == 1 or getattr(self, 'p2p_capacity', 0) >= capacity:
             return
         if getattr(self, 'p2p_capacity', 0) > 0:
             return      # already attached with a smaller capacity: larger vectors fall back to NCCL
-        # measured on 8xB200 (C4, p+1 = 100 001 doubles): NCCL 73.2 vs fused peer-memory exchange 71.1 Gibbs it/s,
-        # so NCCL stays the default; BB_ALLREDUCE=p2p selects the library's own kernels
-        if os.environ.get('BB_ALLREDUCE', 'nccl') != 'p2p' and not getattr(self, 'comm_local', False):
+        local = getattr(self, 'comm_local', False)
+        if os.environ.get('BB_P2P', '1') == '0' and not local:
             return
         lib = load()
         buf = ctypes.create_string_buffer(64)
@@ -230,6 +233,7 @@ class Context:
         dist.all_gather_object(handles, bytes(buf.raw))
         check(lib.bb_comm_p2p_attach(self.handle, b''.join(handles)))
         self.p2p_capacity = int(capacity)
+        self.set_option('allreduce_p2p', 1 if (local or os.environ.get('BB_ALLREDUCE', 'nccl') == 'p2p') else 0)
 
     def p2p_status(self):
         ready, err = c_int(), c_int()

@@ -8,6 +8,8 @@
 // All vector state stays on the device; the host only reads back {iter, done} between chunks.
 #include "bb_internal.cuh"
 
+int bb_dense_tdot(bb_mat* m, const double* w, const int* done_flag);
+
 __device__ __forceinline__ double tdot_entry(const double* __restrict__ traw, const double* __restrict__ c, i64 j, int icpt) {
     const double sw = traw[0];
     if (j < icpt) return sw;
@@ -61,9 +63,12 @@ __global__ void k_cg_init(const double* __restrict__ traw, const double* __restr
     if (threadIdx.x == 0) red_bb[blockIdx.x] = acc;
 }
 
-__global__ void k_cg_scalars(CgScalars* st, const double* __restrict__ red_bb, int nred, double atol, int maxiter) {
+__global__ void k_cg_scalars(CgScalars* st, const double* __restrict__ red_bb, int nred, double atol, int maxiter,
+                             unsigned long long* ps_bar) {
     double bb = warp_sum_partials(red_bb, nred);
     if (threadIdx.x == 0) {
+        st->bar_base = 0ull;        // grid-barrier bookkeeping of the fused P-side kernel restarts with every solve
+        *ps_bar = 0ull;
         double bn = sqrt(bb);
         st->bnorm = bn;
         // cg_sampler.py:75 rtol = atol/||b|| ; scipy: atol_eff = max(0, rtol*||b||)
@@ -218,6 +223,23 @@ static int cg_iteration(bb_mat* m) {
     return BB_OK;
 }
 
+// Fused form: the stop test / direction update of iteration k+1 is the tail of iteration k's P-side kernel, so one
+// iteration is  X (s.p) -> omega. -> X' -> [collect + all-reduce + q + update + test + direction]  = 4 launches.
+static int cg_iteration_fused(bb_mat* m) {
+    const int* done = &m->cg->done;
+    const bool precollect = bb_pside_precollect(m);
+    if (!m->is_sparse && m->dense_stream) {
+        BB_TRY(bb_dense_fused(m, done));          // X read once: 8 n p bytes instead of 16 n p
+        if (precollect) BB_TRY(bb_op_collect_local(m, done));
+        return bb_pside_enqueue(m);
+    }
+    BB_TRY(bb_op_dot_flag(m, 1, done));
+    if (precollect) BB_TRY(bb_op_tdot_local(m, m->w_n, done));
+    else if (m->is_sparse) BB_TRY(bb_launch_spmv(m, &m->ftdot, m->w_n, done, /*skip_overflow_add=*/true));
+    else BB_TRY(bb_dense_tdot(m, m->w_n, done));
+    return bb_pside_enqueue(m);
+}
+
 // compute z = X'(omega.y_gaussian) into m->z (device)
 static int compute_z(bb_mat* m) {
     bb_ctx* ctx = m->ctx;
@@ -261,7 +283,7 @@ static int cg_core(bb_mat* m, double atol, int maxiter, int philox, uint64_t see
     k_cg_init<<<gP, 256, 0, st>>>(m->traw, m->col_offset, m->add_intercept, m->P, m->z, m->pps, m->s, m->x0, m->eps_P,
                                   philox, seed, offset, m->b, m->D, m->x, m->red + RED_BB * RED_MAX);
     BB_LAUNCHED(ctx);
-    k_cg_scalars<<<1, 32, 0, st>>>(m->cg, m->red + RED_BB * RED_MAX, gP, atol, maxiter);
+    k_cg_scalars<<<1, 32, 0, st>>>(m->cg, m->red + RED_BB * RED_MAX, gP, atol, maxiter, m->ps_bar);
     BB_LAUNCHED(ctx);
     // initial residual r = b - A x  (exactly b when x0 == 0)
     BB_TRY(bb_op_prepare_flag(m, m->x, m->s, &m->cg->done));
@@ -276,10 +298,24 @@ static int cg_core(bb_mat* m, double atol, int maxiter, int philox, uint64_t see
     int first = (ctx->opt_cg_chunk > 0) ? (int)ctx->opt_cg_chunk : (m->last_n_iter > 0 ? m->last_n_iter + 1 : 8);
     int chunk = first;
     const bool use_graph = ctx->opt_use_graph != 0;
+    const bool fused = bb_pside_available(m);
+    if (m->cg_graph && m->cg_graph_fused != (fused ? 1 : 0)) {
+        cudaGraphExecDestroy(m->cg_graph);
+        m->cg_graph = nullptr;
+    }
+    m->cg_graph_fused = fused ? 1 : 0;
+    if (fused) {
+        BB_TRY(bb_pside_prepare(m));
+        // stop test and direction of iteration 0; every later one is the tail of the fused kernel
+        k_cg_dir<<<gP, 256, 0, st>>>(m->cg, m->red + RED_RR * RED_MAX, gP, m->P, m->add_intercept, m->r, m->pvec, m->s,
+                                     m->col_offset, m->sv, m->red + RED_SHIFT * RED_MAX);
+        BB_LAUNCHED(ctx);
+    }
+    // unfused: launch k starts with the stop test of iteration k, so maxiter + 1 launches may be needed
+    const int max_launches = fused ? (maxiter > 0 ? maxiter : 1) : maxiter + 1;
     for (;;) {
-        // +1: the convergence test of iteration k runs at the start of launch k
         int todo = chunk;
-        if (total + todo > maxiter + 1) todo = maxiter + 1 - total;
+        if (total + todo > max_launches) todo = max_launches - total;
         if (todo < 1) todo = 1;
         if (use_graph) {
             if (!m->cg_graph) {
@@ -287,7 +323,7 @@ static int cg_core(bb_mat* m, double atol, int maxiter, int philox, uint64_t see
                 const i64 l0 = ctx->launches;
                 BB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
                 int rc = BB_OK;
-                for (int k = 0; k < CG_GRAPH_ITERS && rc == BB_OK; ++k) rc = cg_iteration(m);
+                for (int k = 0; k < CG_GRAPH_ITERS && rc == BB_OK; ++k) rc = fused ? cg_iteration_fused(m) : cg_iteration(m);
                 cudaError_t e = cudaStreamEndCapture(st, &g);
                 m->cg_graph_launches = (int)(ctx->launches - l0);
                 ctx->launches = l0;
@@ -302,13 +338,13 @@ static int cg_core(bb_mat* m, double atol, int maxiter, int philox, uint64_t see
             ctx->launches += (i64)ngraphs * m->cg_graph_launches;
             todo = ngraphs * CG_GRAPH_ITERS;
         } else {
-            for (int k = 0; k < todo; ++k) BB_TRY(cg_iteration(m));
+            for (int k = 0; k < todo; ++k) BB_TRY(fused ? cg_iteration_fused(m) : cg_iteration(m));
         }
         total += todo;
         BB_CUDA(cudaMemcpyAsync(m->cg_host, m->cg, sizeof(CgScalars), cudaMemcpyDeviceToHost, st));
         BB_CUDA(cudaStreamSynchronize(st));
         if (m->cg_host->done != 0) break;
-        if (total >= maxiter + 1) break;   // cannot happen: launch maxiter+1 sets done=2
+        if (total >= max_launches) break;   // cannot happen: the last allowed launch sets done=2
         chunk = (ctx->opt_cg_chunk > 0) ? (int)ctx->opt_cg_chunk : CG_GRAPH_ITERS;
     }
     k_cg_final<<<gP, 256, 0, st>>>(m->cg, m->s, m->x, m->P, m->out_P);

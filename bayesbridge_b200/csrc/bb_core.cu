@@ -44,6 +44,9 @@ extern "C" int bb_init(int device, bb_ctx** out) {
     c->opt_spmv_bulk = 1;
     c->opt_cg_chunk = 0;
     c->opt_use_graph = 1;
+    c->opt_cg_fused = 1;
+    c->opt_pside_ctas = 0;
+    c->opt_dense_stream = 1;
     c->opt_allreduce_p2p = 1;
     c->opt_p2p_variant = 3;      // one system fence + relaxed flag stores, parallel flag polls (fastest measured at N=8)
     c->nranks = 1;
@@ -88,6 +91,10 @@ static i64* option_slot(bb_ctx* c, const char* name) {
     if (!strcmp(name, "sell_lmax")) return &c->opt_sell_lmax;
     if (!strcmp(name, "cg_chunk")) return &c->opt_cg_chunk;
     if (!strcmp(name, "use_graph")) return &c->opt_use_graph;
+    if (!strcmp(name, "cg_fused")) return &c->opt_cg_fused;
+    if (!strcmp(name, "pside_ctas")) return &c->opt_pside_ctas;
+    if (!strcmp(name, "pside_collect_max")) return &c->opt_pside_collect_max;
+    if (!strcmp(name, "dense_stream")) return &c->opt_dense_stream;
     if (!strcmp(name, "allreduce_p2p")) return &c->opt_allreduce_p2p;
     if (!strcmp(name, "p2p_variant")) return &c->opt_p2p_variant;
     return nullptr;

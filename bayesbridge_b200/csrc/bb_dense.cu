@@ -77,6 +77,227 @@ k_dense_tdot(const double* __restrict__ X, i64 n, i64 p, const double* __restric
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Streaming kernel: X is read ONCE per operator application (dense_matrix.py:37-58 does two GEMV passes).
+// One persistent CTA per SM walks groups of R consecutive rows; a group is one contiguous chunk of R*p doubles, brought
+// into shared memory by TMA bulk copies (cp.async.bulk + mbarrier, two stages), so HBM sees long sequential bursts.
+// Thread t owns columns t, t+1024, ... (KMAX of them): its entries of the gather vector and its column accumulators
+// stay in registers for the whole launch.  Per group:
+//   pass 1  u_r = shift + sum_j X_rj sv_j      (block reduction, fixed tree)          -- DS_DOT, DS_DOT_W, DS_FUSED
+//           w_r = omega_r u_r                                                         -- DS_DOT_W, DS_FUSED
+//   pass 2  acc_j += w_r X_rj  from the same shared-memory copy                        -- DS_TDOT, DS_FUSED
+// and at the end part[cta][j] = acc_j (summed over CTAs by the consumer in CTA order).  Algorithmic bytes of the fused
+// operator: 8 n p (+ vectors), SURVEY section 8d.
+constexpr int DS_THREADS = 1024;
+constexpr int DS_RMAX = 8;
+enum { DS_DOT = 0, DS_DOT_W = 1, DS_TDOT = 2, DS_FUSED = 3 };
+
+struct DenseStreamArgs {
+    const double* X; i64 n, p; int R, nstage;
+    const double* sv; const double* red_shift; int nshift;
+    const double* omega; const double* omega_scalar;
+    const double* w_in;
+    double* out; double* red_w; double* part;
+    const int* done_flag;
+};
+
+__device__ __forceinline__ void ds_issue(const DenseStreamArgs& a, i64 g, unsigned dst, unsigned mbar) {
+    const i64 i0 = g * a.R;
+    i64 rows = a.n - i0; if (rows > a.R) rows = a.R;
+    const unsigned bytes = (unsigned)((((size_t)rows * a.p + 1) & ~(size_t)1) * sizeof(double));
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+    const char* src = reinterpret_cast<const char*>(a.X + i0 * a.p);
+    for (unsigned off = 0; off < bytes; off += 32768u) {
+        const unsigned sz = min(32768u, bytes - off);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst + off), "l"(src + off), "r"(sz), "r"(mbar) : "memory");
+    }
+}
+
+template <int KMAX, int MODE>
+__global__ void __launch_bounds__(DS_THREADS, 1)
+k_dense_stream(const DenseStreamArgs a) {
+    if (a.done_flag != nullptr && *a.done_flag) return;
+    extern __shared__ __align__(128) unsigned char ds_smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const i64 p = a.p;
+    const int R = a.R;
+    const size_t stage_elems = ((size_t)R * p + 1) & ~(size_t)1;
+    double* stage0 = reinterpret_cast<double*>(ds_smem);
+    double* red = stage0 + (size_t)a.nstage * stage_elems;                    // [32][R]
+    unsigned long long* mbar_p = reinterpret_cast<unsigned long long*>(red + 32 * DS_RMAX);
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(stage0);
+    const unsigned mbar0 = (unsigned)__cvta_generic_to_shared(mbar_p);
+    const i64 ngroups = (a.n + R - 1) / R;
+    if (tid == 0) {
+        for (int s = 0; s < a.nstage; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar0 + 8u * s));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0)
+        for (int s = 0; s < a.nstage; ++s) {
+            const i64 g = (i64)blockIdx.x + (i64)s * gridDim.x;
+            if (g < ngroups) ds_issue(a, g, sbase + (unsigned)(s * stage_elems * sizeof(double)), mbar0 + 8u * s);
+        }
+    double svr[KMAX], acc[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+        const i64 j = tid + (i64)k * DS_THREADS;
+        svr[k] = (MODE != DS_TDOT && j < p) ? a.sv[j] : 0.0;
+        acc[k] = 0.0;
+    }
+    double shift = 0.0;
+    if (MODE != DS_TDOT) shift = warp_sum_partials(a.red_shift, a.nshift);
+    double sw = 0.0;
+    unsigned phase_bits = 0;
+    int s = 0;
+    for (i64 g = blockIdx.x; g < ngroups; g += gridDim.x) {
+        const unsigned mb = mbar0 + 8u * s;
+        {
+            unsigned ok = 0;
+            const unsigned ph = (phase_bits >> s) & 1u;
+            while (!ok) {
+                asm volatile("{\n\t.reg .pred p;\n\t"
+                             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                             "selp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(ok) : "r"(mb), "r"(ph) : "memory");
+            }
+            phase_bits ^= 1u << s;
+        }
+        const double* xs = stage0 + (size_t)s * stage_elems;
+        const i64 i0 = g * R;
+        int rows = (int)((a.n - i0 < R) ? (a.n - i0) : R);
+        double wr[DS_RMAX];
+        if (MODE != DS_TDOT) {
+            for (int r = 0; r < rows; ++r) {
+                const double* row = xs + (size_t)r * p;
+                double t = 0.0;
+#pragma unroll
+                for (int k = 0; k < KMAX; ++k) {
+                    const i64 j = tid + (i64)k * DS_THREADS;
+                    if (j < p) t += row[j] * svr[k];
+                }
+                t = warp_sum(t);
+                if (lane == 0) red[warp * DS_RMAX + r] = t;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < DS_RMAX; ++r) {
+                wr[r] = 0.0;
+                if (r < rows) {
+                    const double u = warp_sum(red[lane * DS_RMAX + r]) + shift;
+                    if (MODE == DS_DOT) {
+                        if (tid == 0) a.out[i0 + r] = u;
+                    } else {
+                        const double w = (a.omega ? a.omega[i0 + r] : a.omega_scalar[0]) * u;
+                        wr[r] = w;
+                        sw += w;
+                        if (tid == 0 && a.out != nullptr) a.out[i0 + r] = w;
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < DS_RMAX; ++r) wr[r] = (r < rows) ? a.w_in[i0 + r] : 0.0;
+        }
+        if (MODE == DS_TDOT || MODE == DS_FUSED) {
+#pragma unroll
+            for (int r = 0; r < DS_RMAX; ++r) {
+                if (r < rows) {
+                    const double* row = xs + (size_t)r * p;
+#pragma unroll
+                    for (int k = 0; k < KMAX; ++k) {
+                        const i64 j = tid + (i64)k * DS_THREADS;
+                        if (j < p) acc[k] += wr[r] * row[j];
+                    }
+                }
+            }
+        }
+        __syncthreads();                          // everybody is done with stage s (and with red[])
+        const i64 gn = g + (i64)a.nstage * gridDim.x;
+        if (tid == 0 && gn < ngroups) ds_issue(a, gn, sbase + (unsigned)(s * stage_elems * sizeof(double)), mb);
+        s = (s + 1 == a.nstage) ? 0 : s + 1;
+    }
+    if (MODE == DS_TDOT || MODE == DS_FUSED) {
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+            const i64 j = tid + (i64)k * DS_THREADS;
+            if (j < p) a.part[(i64)blockIdx.x * p + j] = acc[k];
+        }
+    }
+    if ((MODE == DS_DOT_W || MODE == DS_FUSED) && tid == 0) a.red_w[blockIdx.x] = sw;
+}
+
+// stage geometry: R rows (even, <= DS_RMAX) per group, nstage buffers; R = 0 when a row pair does not fit
+static void ds_geometry(bb_ctx* ctx, i64 p, int* R_out, int* nstage_out, size_t* smem_out) {
+    *R_out = 0; *nstage_out = 0; *smem_out = 0;
+    if (p < 1 || p > (i64)8 * DS_THREADS) return;
+    const size_t fixed = 32 * DS_RMAX * sizeof(double) + 64;
+    for (int nstage = 2; nstage >= 1; --nstage)
+        for (int R = DS_RMAX; R >= 2; R -= 2) {
+            const size_t stage = (((size_t)R * p + 1) & ~(size_t)1) * sizeof(double);
+            const size_t need = nstage * stage + fixed;
+            if (need <= ctx->smem_optin) { *R_out = R; *nstage_out = nstage; *smem_out = need; return; }
+        }
+}
+
+bool bb_dense_stream_ok(bb_mat* m) {
+    int R, ns; size_t sm;
+    ds_geometry(m->ctx, m->p, &R, &ns, &sm);
+    return R > 0 && m->ctx->opt_dense_stream != 0;
+}
+
+template <int MODE>
+static int ds_launch_mode(bb_mat* m, const DenseStreamArgs& a, int grid, size_t smem) {
+    bb_ctx* ctx = m->ctx;
+    const int kmax = (int)((m->p + DS_THREADS - 1) / DS_THREADS);
+#define DS_CASE(K)                                                                                                    \
+    {                                                                                                                 \
+        static bool attr = false;                                                                                     \
+        if (!attr) {                                                                                                  \
+            BB_CUDA(cudaFuncSetAttribute(k_dense_stream<K, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin)); \
+            attr = true;                                                                                              \
+        }                                                                                                             \
+        k_dense_stream<K, MODE><<<grid, DS_THREADS, smem, ctx->stream>>>(a);                                         \
+    }
+    if (kmax <= 1) DS_CASE(1)
+    else if (kmax <= 2) DS_CASE(2)
+    else if (kmax <= 4) DS_CASE(4)
+    else DS_CASE(8)
+#undef DS_CASE
+    BB_LAUNCHED(ctx);
+    return BB_OK;
+}
+
+// mode: DS_DOT (u -> m->u_n), DS_DOT_W (omega u -> m->w_n), DS_TDOT (w given), DS_FUSED
+int bb_dense_stream(bb_mat* m, int mode, const double* w, const int* done_flag) {
+    bb_ctx* ctx = m->ctx;
+    int R, nstage; size_t smem;
+    ds_geometry(ctx, m->p, &R, &nstage, &smem);
+    if (R == 0) { bb_set_error("dense streaming kernel: p = %lld does not fit", (long long)m->p); return BB_ERR_ARG; }
+    DenseStreamArgs a;
+    memset(&a, 0, sizeof(a));
+    a.X = m->Xd; a.n = m->n; a.p = m->p; a.R = R; a.nstage = nstage;
+    a.sv = m->sv + m->add_intercept;
+    a.red_shift = m->red + RED_SHIFT * RED_MAX;
+    i64 gP = (m->P + 1023) / 1024; if (gP < 1) gP = 1; if (gP > RED_MAX) gP = RED_MAX;
+    a.nshift = (int)gP;
+    a.omega = m->use_omega_scalar ? nullptr : m->omega;
+    a.omega_scalar = m->omega_scalar_dev;
+    a.w_in = w;
+    a.red_w = m->red + RED_W * RED_MAX;
+    a.part = m->dense_part;
+    a.done_flag = done_flag;
+    const int grid = m->dense_nblk;
+    switch (mode) {
+    case DS_DOT: a.out = m->u_n; return ds_launch_mode<DS_DOT>(m, a, grid, smem);
+    case DS_DOT_W: a.out = m->w_n; m->nred_w = grid; return ds_launch_mode<DS_DOT_W>(m, a, grid, smem);
+    case DS_TDOT: return ds_launch_mode<DS_TDOT>(m, a, grid, smem);
+    default: a.out = nullptr; m->nred_w = grid; return ds_launch_mode<DS_FUSED>(m, a, grid, smem);
+    }
+}
+
 __global__ void k_colsum_parts(const double* __restrict__ part, int nblk, i64 p, double* __restrict__ out) {
     for (i64 j = (i64)blockIdx.x * blockDim.x + threadIdx.x; j < p; j += (i64)gridDim.x * blockDim.x) {
         double t = 0.0;
@@ -96,6 +317,7 @@ static int dense_dot_grid(bb_mat* m) {
 
 int bb_dense_dot(bb_mat* m, int mode, const int* done_flag) {
     bb_ctx* ctx = m->ctx;
+    if (m->dense_stream) return bb_dense_stream(m, mode == 0 ? DS_DOT : DS_DOT_W, nullptr, done_flag);
     const double* red_shift = m->red + RED_SHIFT * RED_MAX;
     i64 gP = (m->P + 1023) / 1024; if (gP < 1) gP = 1; if (gP > RED_MAX) gP = RED_MAX;
     int nshift = (int)gP;
@@ -116,17 +338,21 @@ int bb_dense_dot(bb_mat* m, int mode, const int* done_flag) {
 int bb_dense_tdot(bb_mat* m, const double* w, const int* done_flag) {
     bb_ctx* ctx = m->ctx;
     if (m->p == 0) return BB_OK;
+    if (m->dense_stream) return bb_dense_stream(m, DS_TDOT, w, done_flag);
     dim3 grid(m->dense_nblk, (unsigned)((m->p + DT_THREADS * DT_COLS - 1) / (DT_THREADS * DT_COLS)));
     k_dense_tdot<false><<<grid, DT_THREADS, 0, ctx->stream>>>(m->Xd, m->n, m->p, w, m->dense_nblk, m->dense_part, nullptr, done_flag);
     BB_LAUNCHED(ctx);
     return BB_OK;
 }
 
+// the fused operator of the CG loop: one pass over X
+int bb_dense_fused(bb_mat* m, const int* done_flag) { return bb_dense_stream(m, DS_FUSED, nullptr, done_flag); }
+
 int bb_dense_fisher_diag(bb_mat* m, const double* weight_dev, double* d2, double* d1) {
     bb_ctx* ctx = m->ctx;
     if (m->p == 0) return BB_OK;
-    double* part_sq = nullptr;
-    BB_CUDA(cudaMalloc((void**)&part_sq, (size_t)m->dense_nblk * m->p * sizeof(double)));
+    double* part_sq = nullptr;       // persistent context scratch: no allocation per call
+    BB_TRY(bb_ctx_scratch(ctx, 1, (size_t)m->dense_nblk * m->p * sizeof(double), (void**)&part_sq));
     dim3 grid(m->dense_nblk, (unsigned)((m->p + DT_THREADS * DT_COLS - 1) / (DT_THREADS * DT_COLS)));
     k_dense_tdot<true><<<grid, DT_THREADS, 0, ctx->stream>>>(m->Xd, m->n, m->p, weight_dev, m->dense_nblk, m->dense_part, part_sq, nullptr);
     BB_LAUNCHED(ctx);
@@ -135,8 +361,6 @@ int bb_dense_fisher_diag(bb_mat* m, const double* weight_dev, double* d2, double
     BB_LAUNCHED(ctx);
     k_colsum_parts<<<g, 256, 0, ctx->stream>>>(part_sq, m->dense_nblk, m->p, d2);
     BB_LAUNCHED(ctx);
-    BB_CUDA(cudaStreamSynchronize(ctx->stream));
-    cudaFree(part_sq);
     return BB_OK;
 }
 
@@ -158,8 +382,9 @@ extern "C" int bb_dense_upload(bb_ctx* ctx, int64_t n, int64_t p, const double* 
     int rc = BB_OK;
     do {
 #define CKC(e) { cudaError_t e_ = (e); if (e_ != cudaSuccess) { bb_set_error("%s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(e_)); rc = BB_ERR_CUDA; break; } }
-        size_t nb = (size_t)(n * p > 0 ? n * p : 1) * sizeof(double);
+        size_t nb = (size_t)(n * p > 0 ? n * p : 1) * sizeof(double) + 64;    // the bulk copies round a chunk up to 16 bytes
         CKC(cudaMalloc((void**)&m->Xd, nb));
+        CKC(cudaMemsetAsync(m->Xd, 0, nb, ctx->stream));
         if (n * p > 0) CKC(cudaMemcpyAsync(m->Xd, X, (size_t)n * p * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         CKC(cudaMalloc((void**)&m->col_offset, (size_t)(p > 0 ? p : 1) * sizeof(double)));
         CKC(cudaMemsetAsync(m->col_offset, 0, (size_t)(p > 0 ? p : 1) * sizeof(double), ctx->stream));
@@ -168,6 +393,13 @@ extern "C" int bb_dense_upload(bb_ctx* ctx, int64_t n, int64_t p, const double* 
         i64 nblk = ctx->sm_count * 2;
         if (nblk > n) nblk = n > 0 ? n : 1;
         if (nblk > RED_MAX) nblk = RED_MAX;
+        m->dense_stream = bb_dense_stream_ok(m) ? 1 : 0;
+        if (m->dense_stream) {       // one partial row per persistent CTA of the streaming kernel
+            int R, ns; size_t sm;
+            ds_geometry(ctx, p, &R, &ns, &sm);
+            const i64 ngroups = (n + R - 1) / R;
+            nblk = ctx->sm_count < ngroups ? ctx->sm_count : (ngroups > 0 ? ngroups : 1);
+        }
         m->dense_nblk = (int)nblk;
         CKC(cudaMalloc((void**)&m->dense_part, (size_t)nblk * (p > 0 ? p : 1) * sizeof(double)));
         if ((rc = bb_mat_alloc_work(m)) != BB_OK) break;

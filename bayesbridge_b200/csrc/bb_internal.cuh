@@ -51,6 +51,7 @@ struct P2PState {
     unsigned long long seq;        // publications completed by this rank
     unsigned int blocks_done;      // publish: block counter
     unsigned int error;            // set when a wait timed out
+    unsigned long long seq2;       // two-shot exchanges (fused CG iteration, bb_pside.cu) completed by this rank
 };
 struct P2PView {
     double* const* peer_base;      // [nranks] mapped exchange buffers (device array)
@@ -76,6 +77,10 @@ struct bb_ctx {
     i64 opt_spmv_variant;  // 1 (default): sliced lane-per-fragment kernel with 16-bit in-slab indices; 0: tile + segmented-scan kernel
     i64 opt_cg_chunk;      // CG iterations enqueued between host checks (0 = adaptive)
     i64 opt_use_graph;     // capture the CG iteration chunk into a CUDA graph
+    i64 opt_cg_fused;      // 1 (default): the P-side of a CG iteration (+ its all-reduce) is one kernel (bb_pside.cu)
+    i64 opt_pside_ctas;    // grid of that kernel (0 = automatic)
+    i64 opt_pside_collect_max;  // slab partials per column the fused kernel sums itself (0 = default 8); above: k_tdot_collect
+    i64 opt_dense_stream;  // 1 (default): dense products through the one-pass TMA streaming kernel when a row pair fits in shared memory
     // communicator (NCCL via dlopen)
     void* nccl_handle;
     void* nccl_comm;
@@ -122,6 +127,7 @@ bool bb_p2p_allreduce(bb_ctx* c, double* dbuf, i64 count, const int* done_flag, 
 int bb_p2p_free(bb_ctx* c);
 i64 bb_p2p_capacity(bb_ctx* c);                               // doubles per exchange, 0 when not attached
 bool bb_p2p_view(bb_ctx* c, i64 count, P2PView* out);          // true when the exchange can carry `count` doubles
+bool bb_p2p_view2(bb_ctx* c, i64 count, P2PView* out);         // same for the two-shot exchange of the fused CG iteration
 int bb_p2p_reduce_into(bb_ctx* c, double* dst, i64 count);      // wait + rank-ordered sum of the last publication
 
 // ------------------------------------------------------------------------------------------
@@ -177,6 +183,7 @@ struct CgScalars {
     int    done;      // 0 running, 1 converged, 2 maxiter reached, 3 zero right-hand side
     int    maxiter;
     int    pad;
+    unsigned long long bar_base;   // grid-barrier count at the start of the next fused P-side launch (bb_pside.cu)
 };
 
 struct bb_mat {
@@ -206,15 +213,16 @@ struct bb_mat {
     CgScalars* cg;              // device
     CgScalars* cg_host;         // pinned
     int last_n_iter;
-    cudaGraphExec_t cg_graph; int cg_graph_launches; int cg_graph_scalar_mode;   // kernels per captured CG iteration
+    cudaGraphExec_t cg_graph; int cg_graph_launches; int cg_graph_scalar_mode; int cg_graph_fused;   // kernels per captured CG iteration
     int nred_w;                 // number of valid partials in red[RED_W]
     // dense Tdot partials [dense_nblk x p]
-    double* dense_part; int dense_nblk;
+    double* dense_part; int dense_nblk; int dense_stream;    // dense_stream: the one-pass streaming kernel serves this matrix
     // device-resident P-side Gibbs state (bb_state_*): local scales, running summaries of the scaled coefficients
     double *st_lscale, *st_mean, *st_square, *st_prior_sd, *st_sums;
     int st_k, st_ready; double st_slab; long long st_n_avg;
     // cached z = X' kappa for the logit model (kappa = n_success - n_trial/2 is constant)
     double* zk; int zk_valid;
+    unsigned long long* ps_bar;  // grid-barrier counter of the fused P-side kernel
 };
 
 enum { RED_MAX = 1024, RED_SLOTS = 12 };
@@ -234,14 +242,22 @@ int bb_op_prepare_flag(bb_mat* m, const double* vP, const double* scale, const i
 int bb_op_dot_flag(bb_mat* m, int mode, const int* done_flag);
 int bb_op_tdot_flag(bb_mat* m, const double* w, bool have_w_partials, const int* done_flag,
                     bool fuse_reduce_into_consumer = false);
+int bb_op_tdot_local(bb_mat* m, const double* w, const int* done_flag);   // product + collect into traw, no exchange
+int bb_op_collect_local(bb_mat* m, const int* done_flag);                // the collect alone
 int bb_mat_alloc_work(bb_mat* m);
 
 int bb_slab_free(SlabFmt* f);
-int bb_launch_spmv(bb_mat* m, SlabFmt* f, const double* gvec, const int* done_flag);
+int bb_launch_spmv(bb_mat* m, SlabFmt* f, const double* gvec, const int* done_flag, bool skip_overflow_add = false);
 // sliced format (bb_sell.cu)
 i64 bb_sell_max_width(bb_ctx* ctx);
 int bb_sell_build(bb_ctx* ctx, SlabFmt* f);          // from f->ptr / f->idx / f->val / f->slab_nnz1 (device arrays of the slab format)
-int bb_sell_launch(bb_ctx* ctx, SlabFmt* f, const double* gvec, const int* done_flag);
+int bb_sell_launch(bb_ctx* ctx, SlabFmt* f, const double* gvec, const int* done_flag, bool skip_overflow_add = false);
+// fused P-side of a CG iteration (bb_pside.cu)
+bool bb_pside_available(bb_mat* m);
+int bb_pside_prepare(bb_mat* m);     // outside graph capture: uploads the exchange view
+int bb_pside_enqueue(bb_mat* m);
+bool bb_pside_precollect(bb_mat* m);   // true: the caller launches the overflow fold + k_tdot_collect before the fused kernel
+int bb_dense_fused(bb_mat* m, const int* done_flag);   // one pass over X: omega.(X sv + shift) and its X' product
 void bb_sell_free(SlabFmt* f);
 
 // ------------------------------------------------------------------------------------------

@@ -1,7 +1,8 @@
 // One-shot all-reduce over NVLink peer memory (no NCCL on the hot path).
 //
 // Every rank owns one cudaMalloc'ed exchange buffer that the other ranks of the box map through CUDA IPC:
-//     [ flags: nranks x u64, padded to 256 B ][ slot 0: cap doubles ][ slot 1: cap doubles ]
+//     [ flags: 32 x u64 = 256 B ][ slot 0: cap doubles ][ slot 1: cap doubles ][ inbox: cap ][ result: cap ]
+// (inbox / result and flag words 8..23 belong to the two-shot exchange of the fused CG iteration, bb_pside.cu)
 // A reduction of `count` doubles is two kernels on the library stream:
 //   publish : copy the local partial vector into slot (seq & 1); the LAST block to finish makes the data visible
 //             system-wide and stores seq+1 into flags[my_rank] of EVERY peer (st.release.sys over NVLink);
@@ -47,7 +48,7 @@ extern "C" int bb_comm_p2p_export(bb_ctx* c, int64_t capacity, char* handle_out_
     p->cap = (capacity + 31) & ~(i64)31;
     p->nranks = c->nranks;
     p->rank = c->rank;
-    size_t bytes = (size_t)(32 + 2 * p->cap) * sizeof(double);
+    size_t bytes = (size_t)(32 + 4 * p->cap) * sizeof(double);
     BB_CUDA(cudaMalloc((void**)&p->own, bytes));
     BB_CUDA(cudaMemset(p->own, 0, bytes));
     BB_CUDA(cudaMalloc((void**)&p->state, sizeof(P2PState)));
@@ -106,6 +107,19 @@ i64 bb_p2p_capacity(bb_ctx* c) {
 bool bb_p2p_view(bb_ctx* c, i64 count, P2PView* out) {
     bb_p2p* p = (bb_p2p*)c->p2p;
     if (!p || !c->p2p_ready || (c->opt_allreduce_p2p == 0 && !c->comm_local) || count > p->cap) return false;
+    out->peer_base = p->peers_dev;
+    out->st = p->state;
+    out->cap = p->cap;
+    out->nranks = p->nranks;
+    out->rank = p->rank;
+    out->variant = (int)c->opt_p2p_variant;
+    return true;
+}
+
+// the two-shot exchange needs room for nranks chunks of ceil(count/nranks) (+ rounding) doubles
+bool bb_p2p_view2(bb_ctx* c, i64 count, P2PView* out) {
+    bb_p2p* p = (bb_p2p*)c->p2p;
+    if (!p || !c->p2p_ready || p->nranks > 8 || count + 4 * (i64)p->nranks > p->cap) return false;
     out->peer_base = p->peers_dev;
     out->st = p->state;
     out->cap = p->cap;

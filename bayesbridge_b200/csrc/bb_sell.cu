@@ -17,6 +17,10 @@
 //   * the slices of one (CTA, slab) section are split into 32 contiguous STRIPS of equal cost, one per warp, so a
 //     warp streams a contiguous byte range through a register ring (R rows in flight) with no dependent
 //     address loads; per entry the lane does: extract index, LDS.64 gather, DADD;
+//   * every slice starts with a HEADER row in the same stream: lane l's 8 bytes are {output slot of its fragment,
+//     number of data rows of the slice}.  The header therefore arrives through the same register ring as the
+//     indices -- no separate, dependent load per slice (with the slot in an array of its own, a warp walking short
+//     slices waited a full memory latency per slice: 25 % of all stall samples in the first ncu capture);
 //   * at the end of a slice every lane stores its sum to part[slot]; the first fragment of a virtual segment
 //     owns slot v = slab*n_seg + seg (the layout k_dot_finish / k_tdot_collect read), further fragments of a
 //     long segment own overflow slots that k_ovf_add folds in afterwards (rare);
@@ -151,7 +155,7 @@ __global__ void k_sell_slice_rows(const int* __restrict__ slab_slice0, const int
     int len = (q < slab_frag0[slab + 1]) ? frag_len[sorted_id[q]] : 0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
-    if (lane == 0) nrows[slice] = (len + 3) >> 2;
+    if (lane == 0) nrows[slice] = 1 + ((len + 3) >> 2);       // header row + data rows
 }
 
 // Fill one slice per warp.  Lane l owns fragment l of the slice.  With `permute` the entries of every fragment are
@@ -171,7 +175,7 @@ k_sell_fill(const int* __restrict__ slab_slice0, const int* __restrict__ slab_fr
             const int* __restrict__ sorted_id, const int* __restrict__ frag_src, const int* __restrict__ frag_len,
             const unsigned* __restrict__ frag_slot, const int* __restrict__ idx, const double* __restrict__ val, int W,
             const unsigned* __restrict__ sl_off, unsigned trash_slot, int permute,
-            unsigned* __restrict__ sl_slot, unsigned* __restrict__ words, double* __restrict__ vals) {
+            unsigned* __restrict__ words, double* __restrict__ vals) {
     extern __shared__ __align__(16) unsigned char fill_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int slice = blockIdx.x * SELL_FILL_WARPS + warp;
@@ -198,12 +202,70 @@ k_sell_fill(const int* __restrict__ slab_slice0, const int* __restrict__ slab_fr
         for (int b = 0; b < 16; ++b) if (S.bptr[lane][b] < S.bend[lane][b]) mask |= 1u << b;
     }
     __syncwarp();
-    const unsigned r0 = sl_off[slice];
+    const unsigned r0 = sl_off[slice] + 1u;                 // first data row (the header row precedes it)
     const int nrows = (int)(sl_off[slice + 1] - r0);
+    {   // header row: {output slot, data rows of the slice}
+        const size_t o32 = ((size_t)(r0 - 1u) * 32 + lane) * 2;
+        words[o32] = slot;
+        words[o32 + 1] = (unsigned)nrows;
+    }
+    // permute == 2: per-bank load of this lane's half-warp; lane hl is the book-keeper of bank hl
+    const int hl = lane & 15, hbase = lane & 16;
+    int load = 0;
+    if (permute == 2)
+        for (int l = 0; l < 16; ++l) load += (int)S.bend[hbase + l][hl] - (int)S.bptr[hbase + l][hl];
     for (int j = 0; j < 4 * nrows; ++j) {
         int pos = -1;
-        if (permute) {
-            unsigned used = 0;
+        unsigned used = 0;
+        if (permute == 2) {
+            // "Most loaded bank first": a conflict-free position is a matching between lanes and banks, and the number
+            // of positions a half-warp needs is bounded below by its fullest bank, so each position serves the banks
+            // in order of their remaining load; a bank goes to the lane with the fewest other banks still open.
+            bool assigned = (mask == 0u);
+            unsigned avail = 0;                 // as book-keeper of bank hl: lanes that could still take an entry from it
+            for (int l = 0; l < 16; ++l) {
+                const unsigned ml = __shfl_sync(0xffffffffu, mask, l, 16);
+                avail |= ((ml >> hl) & 1u) << l;
+            }
+            for (int pick = 0; pick < 16; ++pick) {
+                int key = (!((used >> hl) & 1u) && avail != 0u) ? ((load << 4) | hl) : -1;
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) key = max(key, __shfl_xor_sync(0xffffffffu, key, o, 16));
+                if (!__any_sync(0xffffffffu, key >= 0)) break;
+                const int bstar = key & 15;
+                int k2 = (key >= 0 && !assigned && ((mask >> bstar) & 1u)) ? ((__popc(mask & ~used) << 5) | hl) : 0x7fffffff;
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) k2 = min(k2, __shfl_xor_sync(0xffffffffu, k2, o, 16));
+                if (key >= 0) {
+                    const int kstar = k2 & 15;
+                    if (hl == kstar) {
+                        const int pp = S.bptr[lane][bstar];
+                        pos = S.ord[lane][pp];
+                        S.bptr[lane][bstar] = (unsigned short)(pp + 1);
+                        if (pp + 1 == S.bend[lane][bstar]) mask &= ~(1u << bstar);
+                        assigned = true;
+                    }
+                    used |= 1u << bstar;
+                    if (hl == bstar) load -= 1;
+                    avail &= ~(1u << kstar);
+                }
+            }
+            // lanes left over share a bank with another lane at this position (unavoidable here)
+            int forced = -1;
+            if (!assigned) {
+                const int r = (j + hl) & 15;
+                const unsigned mm = ((mask >> r) | (mask << (16 - r))) & 0xffffu;
+                forced = (__ffs(mm) - 1 + r) & 15;
+                const int pp = S.bptr[lane][forced];
+                pos = S.ord[lane][pp];
+                S.bptr[lane][forced] = (unsigned short)(pp + 1);
+                if (pp + 1 == S.bend[lane][forced]) mask &= ~(1u << forced);
+            }
+            for (int l = 0; l < 16; ++l) {
+                const int fb = __shfl_sync(0xffffffffu, forced, l, 16);
+                if (fb == hl) load -= 1;
+            }
+        } else if (permute) {
             for (int k = 0; k < 16; ++k) {
                 int chosen = -1;
                 if ((lane & 15) == k && mask != 0u) {
@@ -224,13 +286,13 @@ k_sell_fill(const int* __restrict__ slab_slice0, const int* __restrict__ slab_fr
         } else if (j < len) {
             pos = j;
         }
-        const unsigned e = (pos >= 0) ? (unsigned)S.el[lane][pos] : (unsigned)W;   // padded entry -> the zero behind the window
+        // padded entry -> one of the two zeros kept behind the window (banks 0 and 1): the one whose bank is free
+        const unsigned e = (pos >= 0) ? (unsigned)S.el[lane][pos] : (unsigned)W + (((used & 3u) == 1u) ? 1u : 0u);
         // row j>>2, lane, entry j&3 : 16-bit entries, 4 per lane and row
         const size_t o16 = ((size_t)(r0 + (unsigned)(j >> 2)) * 32 + lane) * 4 + (j & 3);
         reinterpret_cast<unsigned short*>(words)[o16] = (unsigned short)e;
         if (vals) vals[o16] = (pos >= 0) ? val[src + pos] : 0.0;
     }
-    sl_slot[(size_t)slice * 32 + lane] = slot;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -274,10 +336,8 @@ __device__ __forceinline__ void sell_load_row(SellRow<BINARY>& r, const uint2* _
 // per-warp state of the strip walk
 struct SellWalk {
     double a0, a1;            // the two accumulators of the current fragment
-    int rows_left;            // rows until the end of the current slice
-    int s, s1, sb;            // current slice, end of the strip, first slice of the length batch held in nr_batch
-    int nr_batch, nr_next;    // lane l: rows of slice sb + l / sb + 32 + l
-    unsigned slot_cur, slot_n1;
+    int rows_left;            // data rows until the end of the current slice (0: the next row is a header)
+    unsigned slot;            // output slot of this lane's fragment
 };
 
 // One batch of R rows: first issue the loads of the NEXT batch into `nxt` (they are only consumed one batch later,
@@ -286,37 +346,29 @@ template <bool BINARY, int R>
 __device__ __forceinline__ void sell_batch(SellRow<BINARY> (&cur)[R], SellRow<BINARY> (&nxt)[R],
                                            const uint2* __restrict__ rp, const double2* __restrict__ vp,
                                            unsigned r, unsigned r_end, unsigned sbase,
-                                           const unsigned* __restrict__ sl_off, const unsigned* __restrict__ sl_slot,
-                                           double* __restrict__ part, int lane, SellWalk& w) {
+                                           double* __restrict__ part, SellWalk& w) {
 #pragma unroll
     for (int k = 0; k < R; ++k)
         if (r + R + k < r_end) sell_load_row<BINARY>(nxt[k], rp, vp, R + k);
 #pragma unroll
     for (int k = 0; k < R; ++k) {
         if (r + k < r_end) {
-            const double g0 = sell_lds(sbase + ((cur[k].q.x & 0xffffu) << 3));
-            const double g1 = sell_lds(sbase + ((cur[k].q.x >> 16) << 3));
-            const double g2 = sell_lds(sbase + ((cur[k].q.y & 0xffffu) << 3));
-            const double g3 = sell_lds(sbase + ((cur[k].q.y >> 16) << 3));
-            if constexpr (BINARY) {
-                w.a0 += g0; w.a1 += g1; w.a0 += g2; w.a1 += g3;
+            if (w.rows_left == 0) {             // header row (warp-uniform: rows_left is the same in every lane)
+                w.slot = cur[k].q.x;
+                w.rows_left = __shfl_sync(0xffffffffu, (int)cur[k].q.y, 0);
             } else {
-                w.a0 += cur[k].va.x * g0; w.a1 += cur[k].va.y * g1; w.a0 += cur[k].vb.x * g2; w.a1 += cur[k].vb.y * g3;
-            }
-            if (--w.rows_left == 0) {
-                part[w.slot_cur] = w.a0 + w.a1;
-                w.a0 = 0.0; w.a1 = 0.0;
-                ++w.s;
-                w.slot_cur = w.slot_n1;
-                w.slot_n1 = (w.s + 1 < w.s1) ? sl_slot[(size_t)(w.s + 1) * 32 + lane] : 0u;
-                if (w.s < w.s1) {
-                    int j = w.s - w.sb;
-                    if (j == 32) {
-                        w.sb = w.s; j = 0;
-                        w.nr_batch = w.nr_next;
-                        w.nr_next = (int)(sl_off[min(w.sb + 32 + lane + 1, w.s1)] - sl_off[min(w.sb + 32 + lane, w.s1)]);
-                    }
-                    w.rows_left = __shfl_sync(0xffffffffu, w.nr_batch, j);
+                const double g0 = sell_lds(sbase + ((cur[k].q.x & 0xffffu) << 3));
+                const double g1 = sell_lds(sbase + ((cur[k].q.x >> 16) << 3));
+                const double g2 = sell_lds(sbase + ((cur[k].q.y & 0xffffu) << 3));
+                const double g3 = sell_lds(sbase + ((cur[k].q.y >> 16) << 3));
+                if constexpr (BINARY) {
+                    w.a0 += g0; w.a1 += g1; w.a0 += g2; w.a1 += g3;
+                } else {
+                    w.a0 += cur[k].va.x * g0; w.a1 += cur[k].va.y * g1; w.a0 += cur[k].vb.x * g2; w.a1 += cur[k].vb.y * g3;
+                }
+                if (--w.rows_left == 0) {
+                    part[w.slot] = w.a0 + w.a1;
+                    w.a0 = 0.0; w.a1 = 0.0;
                 }
             }
         }
@@ -325,8 +377,7 @@ __device__ __forceinline__ void sell_batch(SellRow<BINARY> (&cur)[R], SellRow<BI
 
 template <bool BINARY, int R>
 __global__ void __launch_bounds__(SELL_THREADS, 1)
-k_sell_spmv(const unsigned* __restrict__ sl_off, const unsigned* __restrict__ sl_slot,
-            const uint2* __restrict__ rows, const double* __restrict__ vals,
+k_sell_spmv(const uint2* __restrict__ rows, const double* __restrict__ vals,
             const int* __restrict__ cta_sec0, const int* __restrict__ sec_slab, const int* __restrict__ sec_wstart,
             const double* __restrict__ gvec, int W, i64 n_gather, int use_bulk,
             double* __restrict__ part, const int* __restrict__ done_flag)
@@ -352,9 +403,10 @@ k_sell_spmv(const unsigned* __restrict__ sl_off, const unsigned* __restrict__ sl
         const i64 gbase = (i64)slab * W;
         const i64 rem = n_gather - gbase;
         const int wlen = rem < (i64)W ? (int)rem : W;
-        // this warp's strip (contiguous slices) -- fetched before the barrier so that the loads overlap the staging
-        const int s0 = sec_wstart[sec * (SELL_WARPS + 1) + warp];
-        const int s1 = sec_wstart[sec * (SELL_WARPS + 1) + warp + 1];
+        // this warp's strip (a contiguous row range that starts at a slice header) -- fetched before the barrier so
+        // that the loads overlap the staging
+        unsigned r = (unsigned)sec_wstart[sec * (SELL_WARPS + 1) + warp];
+        const unsigned r_end = (unsigned)sec_wstart[sec * (SELL_WARPS + 1) + warp + 1];
         __syncthreads();                          // readers of the previous window are done; mbarrier init is visible
         if (use_bulk) {
             if (tid == 0) {
@@ -378,26 +430,15 @@ k_sell_spmv(const unsigned* __restrict__ sl_off, const unsigned* __restrict__ sl
             for (; i < wlen; i += SELL_THREADS) sell_smem[i] = src[i];
         }
         // strip prologue: issue the first loads while the window is in flight
-        unsigned r = 0, r_end = 0;
         SellWalk w;
-        w.a0 = 0.0; w.a1 = 0.0; w.rows_left = 0; w.s = s0; w.s1 = s1; w.sb = s0; w.nr_batch = 0; w.nr_next = 0;
-        w.slot_cur = 0u; w.slot_n1 = 0u;
+        w.a0 = 0.0; w.a1 = 0.0; w.rows_left = 0; w.slot = 0u;
         SellRow<BINARY> bufA[R], bufB[R];
-        const uint2* rp = rows;
+        const uint2* rp = rows + (size_t)r * 32 + lane;
         const double2* vp = reinterpret_cast<const double2*>(vals);
-        if (s0 < s1) {
-            r = sl_off[s0];
-            r_end = sl_off[s1];
-            rp = rows + (size_t)r * 32 + lane;
-            if constexpr (!BINARY) vp = reinterpret_cast<const double2*>(vals) + ((size_t)r * 32 + lane) * 2;
+        if constexpr (!BINARY) vp += ((size_t)r * 32 + lane) * 2;
 #pragma unroll
-            for (int k = 0; k < R; ++k)
-                if (r + k < r_end) sell_load_row<BINARY>(bufA[k], rp, vp, k);
-            w.nr_batch = (int)(sl_off[min(s0 + lane + 1, s1)] - sl_off[min(s0 + lane, s1)]);
-            w.nr_next = (int)(sl_off[min(s0 + 32 + lane + 1, s1)] - sl_off[min(s0 + 32 + lane, s1)]);
-            w.slot_cur = sl_slot[(size_t)s0 * 32 + lane];
-            w.slot_n1 = (s0 + 1 < s1) ? sl_slot[(size_t)(s0 + 1) * 32 + lane] : 0u;
-        }
+        for (int k = 0; k < R; ++k)
+            if (r + k < r_end) sell_load_row<BINARY>(bufA[k], rp, vp, k);
         if (use_bulk) {
             unsigned ok = 0;
             while (!ok) {
@@ -410,15 +451,12 @@ k_sell_spmv(const unsigned* __restrict__ sl_off, const unsigned* __restrict__ sl
         } else {
             __syncthreads();
         }
-        if (s0 < s1) {
-            w.rows_left = __shfl_sync(0xffffffffu, w.nr_batch, 0);
-            while (r < r_end) {
-                sell_batch<BINARY, R>(bufA, bufB, rp, vp, r, r_end, sbase, sl_off, sl_slot, part, lane, w);
-                r += R; rp += R * 32; if constexpr (!BINARY) vp += R * 64;
-                if (r >= r_end) break;
-                sell_batch<BINARY, R>(bufB, bufA, rp, vp, r, r_end, sbase, sl_off, sl_slot, part, lane, w);
-                r += R; rp += R * 32; if constexpr (!BINARY) vp += R * 64;
-            }
+        while (r < r_end) {
+            sell_batch<BINARY, R>(bufA, bufB, rp, vp, r, r_end, sbase, part, w);
+            r += R; rp += R * 32; if constexpr (!BINARY) vp += R * 64;
+            if (r >= r_end) break;
+            sell_batch<BINARY, R>(bufB, bufA, rp, vp, r, r_end, sbase, part, w);
+            r += R; rp += R * 32; if constexpr (!BINARY) vp += R * 64;
         }
     }
 }
@@ -618,7 +656,6 @@ int bb_sell_build(bb_ctx* ctx, SlabFmt* f) {
     }
     const size_t total_rows = off[(size_t)nslices];
     if (total_rows >= ((size_t)1 << 31)) { bb_set_error("sliced format: too many rows"); return BB_ERR_ARG; }
-    BB_CUDA(cudaMalloc((void**)&f->sl_slot, ((size_t)nslices * 32 + 1) * sizeof(unsigned)));
     BB_CUDA(cudaMalloc((void**)&f->sl_pairs, (total_rows * 64 + 4) * sizeof(unsigned)));
     if (f->val) BB_CUDA(cudaMalloc((void**)&f->sl_vals, (total_rows * 128 + 4) * sizeof(double)));
     if (nslices > 0) {
@@ -630,13 +667,13 @@ int bb_sell_build(bb_ctx* ctx, SlabFmt* f) {
         }
         k_sell_fill<<<(nslices + SELL_FILL_WARPS - 1) / SELL_FILL_WARPS, SELL_FILL_WARPS * 32, fill_smem, st>>>(
             f->sl_slab_slice0, d_slab_frag0, nslab, nslices, sorted_id, frag_src, frag_len, frag_slot, f->idx, f->val, W,
-            f->sl_off, trash_slot, ctx->opt_bank_permute != 0 ? 1 : 0, f->sl_slot, f->sl_pairs, f->sl_vals);
+            f->sl_off, trash_slot, (int)ctx->opt_bank_permute, f->sl_pairs, f->sl_vals);
         ctx->launches += 1;
     }
 
     // work partition: CTA ranges of equal cost, cut at slab boundaries into sections, every section into 32 warp strips
     const int ncta = std::max(1, std::min(ctx->sm_count, nslices));
-    auto cost = [&](i64 s) { return (i64)off[(size_t)s] + (i64)SELL_SLICE_COST * s; };
+    auto cost = [&](i64 s) { return (i64)off[(size_t)s] + (i64)(SELL_SLICE_COST - 1) * s; };   // off counts the header rows
     auto cut = [&](i64 lo, i64 hi, i64 target) {      // first s in [lo, hi] with cost(s) >= target
         while (lo < hi) { i64 mid = (lo + hi) >> 1; if (cost(mid) < target) lo = mid + 1; else hi = mid; }
         return lo;
@@ -655,7 +692,7 @@ int bb_sell_build(bb_ctx* ctx, SlabFmt* f) {
             const i64 ca = cost(cur), cb = cost(e);
             for (int w = 0; w <= SELL_WARPS; ++w) {
                 i64 sw = (w == 0) ? cur : (w == SELL_WARPS) ? e : cut(cur, e, ca + (cb - ca) * w / SELL_WARPS);
-                sec_wstart.push_back((int)sw);
+                sec_wstart.push_back((int)off[(size_t)sw]);       // strips are stored as ROW offsets
             }
             cur = e;
         }
@@ -677,7 +714,7 @@ int bb_sell_build(bb_ctx* ctx, SlabFmt* f) {
 
 static size_t sell_smem_bytes(const SlabFmt* f) { return (size_t)(f->W + 2) * sizeof(double) + 16; }
 
-int bb_sell_launch(bb_ctx* ctx, SlabFmt* f, const double* gvec, const int* done_flag) {
+int bb_sell_launch(bb_ctx* ctx, SlabFmt* f, const double* gvec, const int* done_flag, bool skip_overflow_add) {
     if (f->nslices == 0) return BB_OK;        // no nnz: part stays zero
     const size_t smem = sell_smem_bytes(f);
     if (smem > ctx->smem_optin) { bb_set_error("sliced spmv: shared memory %zu exceeds %zu", smem, ctx->smem_optin); return BB_ERR_ARG; }
@@ -696,12 +733,12 @@ int bb_sell_launch(bb_ctx* ctx, SlabFmt* f, const double* gvec, const int* done_
     const uint2* rows = reinterpret_cast<const uint2*>(f->sl_pairs);
     if (f->sl_vals == nullptr)
         k_sell_spmv<true, SELL_RING_BIN><<<f->sl_ncta, SELL_THREADS, smem, ctx->stream>>>(
-            f->sl_off, f->sl_slot, rows, nullptr, cta_sec0, sec_slab, sec_wstart, gvec, f->W, f->n_gather, use_bulk, f->part, done_flag);
+            rows, nullptr, cta_sec0, sec_slab, sec_wstart, gvec, f->W, f->n_gather, use_bulk, f->part, done_flag);
     else
         k_sell_spmv<false, SELL_RING_VAL><<<f->sl_ncta, SELL_THREADS, smem, ctx->stream>>>(
-            f->sl_off, f->sl_slot, rows, f->sl_vals, cta_sec0, sec_slab, sec_wstart, gvec, f->W, f->n_gather, use_bulk, f->part, done_flag);
+            rows, f->sl_vals, cta_sec0, sec_slab, sec_wstart, gvec, f->W, f->n_gather, use_bulk, f->part, done_flag);
     BB_LAUNCHED(ctx);
-    if (f->n_ovf_pieces > 0) {
+    if (f->n_ovf_pieces > 0 && !skip_overflow_add) {
         k_sell_ovf_add<<<(int)(((i64)f->n_ovf_pieces * 32 + 255) / 256), 256, 0, ctx->stream>>>(
             f->ovf_piece, f->ovf_first, f->n_ovf_pieces, (i64)f->nslab * f->n_seg, f->part, done_flag);
         BB_LAUNCHED(ctx);

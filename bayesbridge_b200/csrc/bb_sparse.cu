@@ -773,9 +773,9 @@ static int build_slab_format(bb_ctx* ctx, const int* cptr, const int* cidx, cons
 }
 
 // launch the SpMV + fix-up for one format; gvec has f->n_gather entries
-int bb_launch_spmv(bb_mat* m, SlabFmt* f, const double* gvec, const int* done_flag) {
+int bb_launch_spmv(bb_mat* m, SlabFmt* f, const double* gvec, const int* done_flag, bool skip_overflow_add) {
     bb_ctx* ctx = m->ctx;
-    if (f->variant == 1) return bb_sell_launch(ctx, f, gvec, done_flag);
+    if (f->variant == 1) return bb_sell_launch(ctx, f, gvec, done_flag, skip_overflow_add);
     // a format built without staging in mind may have slabs wider than shared memory
     const bool stage = f->staged && (i64)f->W <= max_stage_width(ctx);
     int wstage = stage ? f->W : 0;
@@ -882,6 +882,23 @@ int bb_op_tdot_flag(bb_mat* m, const double* w, bool have_w_partials, const int*
 }
 int bb_op_tdot(bb_mat* m, const double* w) { return bb_op_tdot_flag(m, w, false, nullptr, false); }
 
+// the local part only: traw = [sum w; X' w] of this shard (w partials already in red[RED_W]); the fused P-side kernel
+// exchanges it
+int bb_op_tdot_local(bb_mat* m, const double* w, const int* done_flag) {
+    if (!m->is_sparse) BB_TRY(bb_dense_tdot(m, w, done_flag));
+    else BB_TRY(bb_launch_spmv(m, &m->ftdot, w, done_flag));
+    return bb_op_collect_local(m, done_flag);
+}
+// traw = [sum of the w partials; column sums of the slab / row-block partials]
+int bb_op_collect_local(bb_mat* m, const int* done_flag) {
+    bb_ctx* ctx = m->ctx;
+    k_tdot_collect<<<grid_for(m->p, 32, 4096), 256, 0, ctx->stream>>>(
+        m->is_sparse ? m->ftdot.part : m->dense_part, m->is_sparse ? m->ftdot.nslab : m->dense_nblk, m->p,
+        m->red + RED_W * RED_MAX, m->nred_w, m->traw, done_flag, nullptr);
+    BB_LAUNCHED(ctx);
+    return BB_OK;
+}
+
 int bb_op_tdot_finish(bb_mat* m, double* tP) {
     bb_ctx* ctx = m->ctx;
     k_tdot_finish<<<P_grid(m->P), 256, 0, ctx->stream>>>(m->traw, m->p, m->add_intercept, m->col_offset, tP);
@@ -918,6 +935,8 @@ int bb_mat_alloc_work(bb_mat* m) {
     BB_CUDA(cudaMalloc((void**)&m->cg, sizeof(CgScalars)));
     BB_CUDA(cudaMemsetAsync(m->cg, 0, sizeof(CgScalars), m->ctx->stream));
     BB_CUDA(cudaMallocHost((void**)&m->cg_host, sizeof(CgScalars)));
+    BB_CUDA(cudaMalloc((void**)&m->ps_bar, sizeof(unsigned long long)));
+    BB_CUDA(cudaMemsetAsync(m->ps_bar, 0, sizeof(unsigned long long), m->ctx->stream));
     m->omega_scalar = 1.0;
     m->use_omega_scalar = 0;
     m->last_n_iter = 0;
@@ -935,7 +954,7 @@ extern "C" int bb_mat_free(bb_mat* m) {
                     m->omega, m->n_trial, m->n_success, m->eta, m->w_n, m->u_n, m->eps_n, m->dense_part, m->zk, m->omega_scalar_dev, m->p2p_view_dev,
                     m->st_lscale, m->st_mean, m->st_square, m->st_prior_sd, m->st_sums,
                     m->v_P, m->sv_base, m->traw, m->t_P, m->x, m->r, m->pvec, m->q, m->b, m->s, m->D, m->pps, m->z, m->x0,
-                    m->eps_P, m->out_P, m->red, m->cg};
+                    m->eps_P, m->out_P, m->red, m->cg, m->ps_bar};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (m->cg_host) cudaFreeHost(m->cg_host);
     free(m);

@@ -26,7 +26,7 @@ ref_dot = ref_tdot = v = None
 for var in variants:
     ctx.set_option('spmv_variant', int(var[0]))
     ctx.set_option('spmv_bulk', 0 if 'nb' in var else 1)
-    ctx.set_option('bank_permute', 0 if 'np' in var else 1)
+    ctx.set_option('bank_permute', 0 if 'np' in var else (2 if 'p2' in var else 1))
     t0 = time.time()
     D = GpuSparseDesignMatrix(X, center_predictor=True, add_intercept=True, ctx=ctx, pattern_only=not valued)
     up = time.time() - t0

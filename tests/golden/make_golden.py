@@ -61,6 +61,27 @@ def golden_ks():
     np.savez_compressed(os.path.join(HERE, 'ks_ref.npz'), **out)
 
 
+def golden_ks_quantiles():
+    """two-sample KS at N = 1e6.  A million reference draws per grid cell cannot travel as a
+    fixture (36 cells x 8 MB), so each cell's reference sample is summarised by its 4001-point quantile table
+    (empirical quantiles at k/4000): the GPU test measures sup|F_device - F_reference| with F_reference interpolated
+    from the table (resolution 2.5e-4, below the two-sample critical distance 3.1e-3 at n = m = 1e6)."""
+    out = {}
+    N, Q = 1_000_000, 4001
+    probs = np.linspace(0.0, 1.0, Q)
+    grid = [(b, c) for b in (1, 2, 5) for c in (0., 0.01, 0.5, 2., 10., 50., 100.)]
+    out['pg_grid'] = np.array(grid)
+    pg = PolyaGammaDist(4242)
+    out['pg_quantiles'] = np.array([np.quantile(pg.rand_polyagamma(np.full(N, b, dtype=np.intc), np.full(N, c)), probs)
+                                    for b, c in grid])
+    tgrid = [(a, t) for a in (1 / 32, .25, .5) for t in (0.01, 1., 10., 100., 1e4)]
+    out['ts_grid'] = np.array(tgrid)
+    ts = ExpTiltedStableDist(4243)
+    out['ts_quantiles'] = np.array([np.quantile(ts.sample(a, np.full(N, t)), probs) for a, t in tgrid])
+    out['n_reference_draws'] = N
+    np.savez_compressed(os.path.join(HERE, 'ks_quantiles_ref.npz'), **out)
+
+
 def golden_design():
     out = {}
     X = sparse_problem(3, 60, 17, 0.3, False)
@@ -232,7 +253,7 @@ def golden_posterior():
 
 if __name__ == '__main__':
     only = sys.argv[1:]
-    todo = [golden_random, golden_ks, golden_design, golden_cg, golden_cg_c1, golden_summarizer, golden_chain, golden_posterior]
+    todo = [golden_random, golden_ks, golden_ks_quantiles, golden_design, golden_cg, golden_cg_c1, golden_summarizer, golden_chain, golden_posterior]
     for fn in todo:
         if not only or fn.__name__ in only:
             fn()

@@ -46,13 +46,17 @@ def test_products_match_reference_outputs(ctx):
 
 @pytest.mark.parametrize('n,p,density', [(300, 40, 0.2), (20000, 700, 0.02), (60000, 3000, 0.004)])
 @pytest.mark.parametrize('binary', [False, True])
-@pytest.mark.parametrize('slab,stage,variant', [(0, 1, 1), (64, 1, 1), (1024, 1, 1), (0, 0, 0), (0, 1, 0), (64, 1, 0), (1024, 1, 0), (1024, 0, 0)])
-def test_sparse_products_vs_oracle(ctx, n, p, density, binary, slab, stage, variant):
-    """variant 1 = sliced lane-per-fragment kernel (bb_sell.cu, the default), 0 = tile + segmented-scan kernel."""
+@pytest.mark.parametrize('slab,stage,variant,permute', [(0, 1, 1, 2), (64, 1, 1, 2), (1024, 1, 1, 2), (0, 1, 1, 1), (1024, 1, 1, 0),
+                                                        (0, 0, 0, 1), (0, 1, 0, 1), (64, 1, 0, 1), (1024, 1, 0, 1), (1024, 0, 0, 1)])
+def test_sparse_products_vs_oracle(ctx, n, p, density, binary, slab, stage, variant, permute):
+    """variant 1 = sliced lane-per-fragment kernel (bb_sell.cu, the default), 0 = tile + segmented-scan kernel;
+    permute = bank-aware entry order (2: most-loaded-bank-first matching, 1: greedy, 0: canonical order)."""
     Sparse, _ = _designs()
+    default_permute = ctx.get_option('bank_permute')
     ctx.set_option('slab_width', slab)
     ctx.set_option('spmv_stage', stage)
     ctx.set_option('spmv_variant', variant)
+    ctx.set_option('bank_permute', permute)
     try:
         X = random_sparse(n, p, density, seed=n + p, binary=binary)
         rng = np.random.default_rng(5)
@@ -69,6 +73,7 @@ def test_sparse_products_vs_oracle(ctx, n, p, density, binary, slab, stage, vari
         ctx.set_option('slab_width', 0)
         ctx.set_option('spmv_stage', 1)
         ctx.set_option('spmv_variant', 1)
+        ctx.set_option('bank_permute', default_permute)
 
 
 def test_products_are_bit_reproducible(ctx):
@@ -89,35 +94,44 @@ def test_bank_aware_order_changes_rounding_only(ctx):
     w = np.random.default_rng(2).standard_normal(60000)
     out = {}
     ctx.set_option('slab_width', 1024)
+    default_permute = ctx.get_option('bank_permute')
     try:
-        for perm in (1, 0):
+        for perm in (2, 1, 0):
             ctx.set_option('bank_permute', perm)
             D = Sparse(X, center_predictor=True, add_intercept=True, ctx=ctx, pattern_only=False)
             v = np.random.default_rng(3).standard_normal(D.shape[1])
             out[perm] = (D.dot(v), D.Tdot(w), D.export_csr() + D.export_csc())
     finally:
-        ctx.set_option('bank_permute', 1)
+        ctx.set_option('bank_permute', default_permute)
         ctx.set_option('slab_width', 0)
-    assert relerr(out[1][0], out[0][0]) < 1e-14 and relerr(out[1][1], out[0][1]) < 1e-14
-    for a, b in zip(out[1][2], out[0][2]):
-        assert np.array_equal(a, b)
+    for perm in (1, 2):
+        assert relerr(out[perm][0], out[0][0]) < 1e-14 and relerr(out[perm][1], out[0][1]) < 1e-14
+        for a, b in zip(out[perm][2], out[0][2]):
+            assert np.array_equal(a, b)
     C = X.tocsc()
     assert np.array_equal(out[1][2][4], C.indices) and np.array_equal(out[1][2][5], C.data)
 
 
-@pytest.mark.parametrize('n,p', [(200, 30), (5000, 1300)])
-def test_dense_products_vs_oracle(ctx, n, p):
+@pytest.mark.parametrize('n,p,stream', [(200, 30, 1), (5000, 1300, 1), (1001, 2049, 1), (3, 5, 1), (777, 4097, 1), (301, 9001, 1),
+                                        (200, 30, 0), (5000, 1300, 0)])
+def test_dense_products_vs_oracle(ctx, n, p, stream):
+    """stream = 1: the one-pass TMA streaming kernel (row groups in shared memory; odd p / ragged last group / p beyond
+    one column per thread; p = 9001 exceeds what the kernel holds and takes the two-pass kernels), 0: two-pass kernels."""
     _, Dense = _designs()
     rng = np.random.default_rng(n)
     X = rng.standard_normal((n, p))
-    for center in (False, True):
-        for icpt in (False, True):
-            D = Dense(X.copy(), center_predictor=center, add_intercept=icpt, ctx=ctx)
-            O = co.DesignOracle(X, center, icpt)
-            v, w, wt = rng.standard_normal(D.shape[1]), rng.standard_normal(n), rng.random(n)
-            assert relerr(D.dot(v), O.dot(v)) < 1e-12
-            assert relerr(D.Tdot(w), O.Tdot(w)) < 1e-12
-            assert relerr(D.compute_fisher_info(wt, diag_only=True), O.fisher_diag(wt)) < 1e-12
+    ctx.set_option('dense_stream', stream)
+    try:
+        for center in (False, True):
+            for icpt in (False, True):
+                D = Dense(X.copy(), center_predictor=center, add_intercept=icpt, ctx=ctx)
+                O = co.DesignOracle(X, center, icpt)
+                v, w, wt = rng.standard_normal(D.shape[1]), rng.standard_normal(n), rng.random(n)
+                assert relerr(D.dot(v), O.dot(v)) < 1e-12
+                assert relerr(D.Tdot(w), O.Tdot(w)) < 1e-12
+                assert relerr(D.compute_fisher_info(wt, diag_only=True), O.fisher_diag(wt)) < 1e-12
+    finally:
+        ctx.set_option('dense_stream', 1)
 
 
 def test_csr_upload_and_csc_construction_are_bit_exact(ctx):

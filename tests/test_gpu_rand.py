@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 from scipy.stats import ks_2samp
 
-from conftest import golden, import_reference
+from conftest import golden, import_reference, record_achieved
 from oracle import philox_port as pp
 
 pytestmark = pytest.mark.gpu
@@ -73,6 +73,38 @@ def test_ts_distribution_vs_reference_samples(ctx):
         # Laplace transform identity of the tilted stable law: E[exp(-s X)] = exp(t^a - (t+s)^a)
         s = t
         assert np.mean(np.exp(-s * x)) == pytest.approx(np.exp(t ** a - (t + s) ** a), rel=0.02)
+
+
+def _ks_distance_to_table(x, quantiles):
+    """sup |F_x - F_ref| with F_ref interpolated from the reference's quantile table (golden_ks_quantiles)."""
+    probs = np.linspace(0.0, 1.0, len(quantiles))
+    x = np.sort(x)
+    n = len(x)
+    F = np.interp(x, quantiles, probs)
+    i = np.arange(n)
+    return max(np.abs((i + 1) / n - F).max(), np.abs(i / n - F).max())
+
+
+# two-sample KS critical distance at n = m = 1e6, alpha = 1e-4: sqrt(-ln(alpha/2)/2) * sqrt(2/n) = 3.15e-3, plus the
+# resolution of the 4001-point quantile table (2.5e-4).  The reference against its own table gives 0.6e-3 ... 2.4e-3.
+KS_BOUND_1E6 = 3.4e-3
+
+
+def test_pg_and_ts_ks_at_one_million_draws(ctx):
+    """N = 1e6 draws per grid cell against 1e6 draws of the compiled reference sampler
+    (summarised as quantile tables, tests/golden/make_golden.py::golden_ks_quantiles)."""
+    pg, ts = _samplers(ctx, 77)
+    g = golden('ks_quantiles_ref.npz')
+    N = 1_000_000
+    assert int(g['n_reference_draws']) == N
+    for (b, c), q in zip(g['pg_grid'], g['pg_quantiles']):
+        d = _ks_distance_to_table(pg.rand_polyagamma(np.full(N, int(b), dtype=np.int32), np.full(N, c)), q)
+        record_achieved('ks_1e6_polya_gamma', (int(b), float(c)), d, KS_BOUND_1E6)
+        assert d < KS_BOUND_1E6, ('pg', b, c, d)
+    for (a, t), q in zip(g['ts_grid'], g['ts_quantiles']):
+        d = _ks_distance_to_table(ts.sample(float(a), np.full(N, t)), q)
+        record_achieved('ks_1e6_tilted_stable', (float(a), float(t)), d, KS_BOUND_1E6)
+        assert d < KS_BOUND_1E6, ('ts', a, t, d)
 
 
 def test_pg_vs_live_reference_large_sample(ctx):
