@@ -48,6 +48,8 @@ SIGNATURES = {
     'bb_dot': (c_int, [c_void_p, P_dbl, P_dbl]),
     'bb_tdot': (c_int, [c_void_p, P_dbl, P_dbl]),
     'bb_fisher_diag': (c_int, [c_void_p, P_dbl, P_dbl]),
+    'bb_fisher_full': (c_int, [c_void_p, P_dbl, P_dbl, P_dbl]),
+    'bb_cholesky_sample': (c_int, [c_void_p, P_dbl, P_dbl, P_dbl, P_dbl, P_dbl, P_dbl]),
     'bb_set_outcome': (c_int, [c_void_p, P_dbl, P_dbl]),
     'bb_set_obs_prec': (c_int, [c_void_p, P_dbl]),
     'bb_set_obs_prec_scalar': (c_int, [c_void_p, c_dbl]),

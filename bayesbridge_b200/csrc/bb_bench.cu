@@ -31,8 +31,10 @@ extern "C" int bb_time_kernel(bb_mat* m, const char* what, int reps, int do_flus
     else if (!strcmp(what, "spmv_dot")) kind = 3;     // the SpMV kernel alone (+ its fix-up)
     else if (!strcmp(what, "spmv_tdot")) kind = 4;
     else if (!strcmp(what, "exchange")) kind = 5;     // all-reduce of the (p+1)-vector (every rank must call)
-    BB_ARG(kind >= 0, "what must be dot | tdot | op | spmv_dot | spmv_tdot | exchange");
-    BB_ARG(kind < 3 || kind == 5 || m->is_sparse, "spmv_* needs a sparse matrix");
+    else if (!strcmp(what, "fused_op")) kind = 6;     // dense: omega.(X sv) and its X' product in ONE pass over X (+ collect)
+    BB_ARG(kind >= 0, "what must be dot | tdot | op | spmv_dot | spmv_tdot | exchange | fused_op");
+    BB_ARG(kind < 3 || kind >= 5 || m->is_sparse, "spmv_* needs a sparse matrix");
+    BB_ARG(kind != 6 || (!m->is_sparse && m->dense_stream), "fused_op needs a dense matrix served by the streaming kernel");
     if (kind == 5) {
         // back-to-back exchanges, timed as one region (the per-exchange latency is what matters in the CG loop)
         cudaEvent_t a, b;
@@ -74,6 +76,10 @@ extern "C" int bb_time_kernel(bb_mat* m, const char* what, int reps, int do_flus
             BB_TRY(bb_op_prepare(m, m->v_P, nullptr));
             BB_TRY(bb_op_dot(m, 1));
             BB_TRY(bb_op_tdot_flag(m, m->w_n, true, nullptr, false));
+        } else if (kind == 6) {
+            BB_TRY(bb_op_prepare(m, m->v_P, nullptr));
+            BB_TRY(bb_dense_fused(m, nullptr));
+            BB_TRY(bb_op_collect_local(m, nullptr));
         } else if (kind == 3) {
             BB_TRY(bb_launch_spmv(m, &m->fdot, m->sv + m->add_intercept, nullptr));   // the (16-byte aligned) vector dot gathers from
         } else {

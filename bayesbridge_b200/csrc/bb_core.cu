@@ -39,7 +39,7 @@ extern "C" int bb_init(int device, bb_ctx** out) {
     c->smem_optin = prop.sharedMemPerBlockOptin;
     c->opt_spmv_stage = 1;
     c->opt_slab_width = 0;
-    c->opt_bank_permute = 1;
+    c->opt_bank_permute = 2;     // most-loaded-bank-first matching (bb_sell.cu); 1: greedy; 0: canonical order
     c->opt_spmv_variant = 1;
     c->opt_spmv_bulk = 1;
     c->opt_cg_chunk = 0;

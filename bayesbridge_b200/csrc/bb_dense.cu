@@ -88,7 +88,8 @@ k_dense_tdot(const double* __restrict__ X, i64 n, i64 p, const double* __restric
 //   pass 2  acc_j += w_r X_rj  from the same shared-memory copy                        -- DS_TDOT, DS_FUSED
 // and at the end part[cta][j] = acc_j (summed over CTAs by the consumer in CTA order).  Algorithmic bytes of the fused
 // operator: 8 n p (+ vectors), SURVEY section 8d.
-constexpr int DS_THREADS = 1024;
+constexpr int DS_THREADS = 256;      // few threads with many columns each: the reductions per row stay cheap, TMA does the loading
+constexpr int DS_WARPS = DS_THREADS / 32;
 constexpr int DS_RMAX = 8;
 enum { DS_DOT = 0, DS_DOT_W = 1, DS_TDOT = 2, DS_FUSED = 3 };
 
@@ -115,21 +116,21 @@ __device__ __forceinline__ void ds_issue(const DenseStreamArgs& a, i64 g, unsign
     }
 }
 
-template <int KMAX, int MODE>
+// RR = rows per group (compile time, so the per-row work of a group is independent instruction streams)
+template <int KMAX, int MODE, int RR>
 __global__ void __launch_bounds__(DS_THREADS, 1)
 k_dense_stream(const DenseStreamArgs a) {
     if (a.done_flag != nullptr && *a.done_flag) return;
     extern __shared__ __align__(128) unsigned char ds_smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const i64 p = a.p;
-    const int R = a.R;
-    const size_t stage_elems = ((size_t)R * p + 1) & ~(size_t)1;
+    const size_t stage_elems = ((size_t)RR * p + 1) & ~(size_t)1;
     double* stage0 = reinterpret_cast<double*>(ds_smem);
-    double* red = stage0 + (size_t)a.nstage * stage_elems;                    // [32][R]
-    unsigned long long* mbar_p = reinterpret_cast<unsigned long long*>(red + 32 * DS_RMAX);
+    double* red = stage0 + (size_t)a.nstage * stage_elems;                    // [RR][DS_WARPS]
+    unsigned long long* mbar_p = reinterpret_cast<unsigned long long*>(red + DS_RMAX * DS_WARPS);
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(stage0);
     const unsigned mbar0 = (unsigned)__cvta_generic_to_shared(mbar_p);
-    const i64 ngroups = (a.n + R - 1) / R;
+    const i64 ngroups = (a.n + RR - 1) / RR;
     if (tid == 0) {
         for (int s = 0; s < a.nstage; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar0 + 8u * s));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -154,6 +155,18 @@ k_dense_stream(const DenseStreamArgs a) {
     int s = 0;
     for (i64 g = blockIdx.x; g < ngroups; g += gridDim.x) {
         const unsigned mb = mbar0 + 8u * s;
+        const i64 i0 = g * RR;
+        const int rows = (int)((a.n - i0 < RR) ? (a.n - i0) : RR);
+        // per-row scalars of this group: loaded before the wait so that their latency hides behind it
+        double scal[RR];
+#pragma unroll
+        for (int r = 0; r < RR; ++r) {
+            scal[r] = 0.0;
+            if (r < rows) {
+                if (MODE == DS_TDOT) scal[r] = a.w_in[i0 + r];
+                else if (MODE != DS_DOT) scal[r] = a.omega ? a.omega[i0 + r] : a.omega_scalar[0];
+            }
+        }
         {
             unsigned ok = 0;
             const unsigned ph = (phase_bits >> s) & 1u;
@@ -166,31 +179,43 @@ k_dense_stream(const DenseStreamArgs a) {
             phase_bits ^= 1u << s;
         }
         const double* xs = stage0 + (size_t)s * stage_elems;
-        const i64 i0 = g * R;
-        int rows = (int)((a.n - i0 < R) ? (a.n - i0) : R);
-        double wr[DS_RMAX];
+        double wr[RR];
         if (MODE != DS_TDOT) {
-            for (int r = 0; r < rows; ++r) {
-                const double* row = xs + (size_t)r * p;
-                double t = 0.0;
+            double t[RR];
 #pragma unroll
-                for (int k = 0; k < KMAX; ++k) {
-                    const i64 j = tid + (i64)k * DS_THREADS;
-                    if (j < p) t += row[j] * svr[k];
+            for (int r = 0; r < RR; ++r) t[r] = 0.0;
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) {
+                const i64 j = tid + (i64)k * DS_THREADS;
+                if (j < p) {
+#pragma unroll
+                    for (int r = 0; r < RR; ++r) t[r] += xs[(size_t)r * p + j] * svr[k];    // rows past the end read stale, finite data
                 }
-                t = warp_sum(t);
-                if (lane == 0) red[warp * DS_RMAX + r] = t;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                for (int r = 0; r < RR; ++r) t[r] += __shfl_xor_sync(0xffffffffu, t[r], o);
+            }
+            if (lane < RR) {
+                double mine = t[0];
+#pragma unroll
+                for (int r = 1; r < RR; ++r) if (lane == r) mine = t[r];
+                red[lane * DS_WARPS + warp] = mine;
             }
             __syncthreads();
 #pragma unroll
-            for (int r = 0; r < DS_RMAX; ++r) {
+            for (int r = 0; r < RR; ++r) {
+                double u = (lane < DS_WARPS) ? red[r * DS_WARPS + lane] : 0.0;
+#pragma unroll
+                for (int o = DS_WARPS / 2; o > 0; o >>= 1) u += __shfl_xor_sync(0xffffffffu, u, o);
+                u = __shfl_sync(0xffffffffu, u, 0) + shift;
                 wr[r] = 0.0;
                 if (r < rows) {
-                    const double u = warp_sum(red[lane * DS_RMAX + r]) + shift;
                     if (MODE == DS_DOT) {
                         if (tid == 0) a.out[i0 + r] = u;
                     } else {
-                        const double w = (a.omega ? a.omega[i0 + r] : a.omega_scalar[0]) * u;
+                        const double w = scal[r] * u;
                         wr[r] = w;
                         sw += w;
                         if (tid == 0 && a.out != nullptr) a.out[i0 + r] = w;
@@ -199,18 +224,16 @@ k_dense_stream(const DenseStreamArgs a) {
             }
         } else {
 #pragma unroll
-            for (int r = 0; r < DS_RMAX; ++r) wr[r] = (r < rows) ? a.w_in[i0 + r] : 0.0;
+            for (int r = 0; r < RR; ++r) wr[r] = scal[r];
         }
         if (MODE == DS_TDOT || MODE == DS_FUSED) {
 #pragma unroll
-            for (int r = 0; r < DS_RMAX; ++r) {
-                if (r < rows) {
-                    const double* row = xs + (size_t)r * p;
+            for (int k = 0; k < KMAX; ++k) {
+                const i64 j = tid + (i64)k * DS_THREADS;
+                if (j < p) {
 #pragma unroll
-                    for (int k = 0; k < KMAX; ++k) {
-                        const i64 j = tid + (i64)k * DS_THREADS;
-                        if (j < p) acc[k] += wr[r] * row[j];
-                    }
+                    for (int r = 0; r < RR; ++r)
+                        if (r < rows) acc[k] += wr[r] * xs[(size_t)r * p + j];
                 }
             }
         }
@@ -232,10 +255,10 @@ k_dense_stream(const DenseStreamArgs a) {
 // stage geometry: R rows (even, <= DS_RMAX) per group, nstage buffers; R = 0 when a row pair does not fit
 static void ds_geometry(bb_ctx* ctx, i64 p, int* R_out, int* nstage_out, size_t* smem_out) {
     *R_out = 0; *nstage_out = 0; *smem_out = 0;
-    if (p < 1 || p > (i64)8 * DS_THREADS) return;
-    const size_t fixed = 32 * DS_RMAX * sizeof(double) + 64;
+    if (p < 1 || p > (i64)32 * DS_THREADS) return;
+    const size_t fixed = DS_WARPS * DS_RMAX * sizeof(double) + 64;
     for (int nstage = 2; nstage >= 1; --nstage)
-        for (int R = DS_RMAX; R >= 2; R -= 2) {
+        for (int R = DS_RMAX; R >= 2; R /= 2) {
             const size_t stage = (((size_t)R * p + 1) & ~(size_t)1) * sizeof(double);
             const size_t need = nstage * stage + fixed;
             if (need <= ctx->smem_optin) { *R_out = R; *nstage_out = nstage; *smem_out = need; return; }
@@ -252,20 +275,28 @@ template <int MODE>
 static int ds_launch_mode(bb_mat* m, const DenseStreamArgs& a, int grid, size_t smem) {
     bb_ctx* ctx = m->ctx;
     const int kmax = (int)((m->p + DS_THREADS - 1) / DS_THREADS);
-#define DS_CASE(K)                                                                                                    \
+#define DS_LAUNCH(K, RRV)                                                                                             \
     {                                                                                                                 \
         static bool attr = false;                                                                                     \
         if (!attr) {                                                                                                  \
-            BB_CUDA(cudaFuncSetAttribute(k_dense_stream<K, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin)); \
+            BB_CUDA(cudaFuncSetAttribute(k_dense_stream<K, MODE, RRV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin)); \
             attr = true;                                                                                              \
         }                                                                                                             \
-        k_dense_stream<K, MODE><<<grid, DS_THREADS, smem, ctx->stream>>>(a);                                         \
+        k_dense_stream<K, MODE, RRV><<<grid, DS_THREADS, smem, ctx->stream>>>(a);                                    \
     }
-    if (kmax <= 1) DS_CASE(1)
-    else if (kmax <= 2) DS_CASE(2)
-    else if (kmax <= 4) DS_CASE(4)
-    else DS_CASE(8)
+#define DS_CASE(K)                                                                                                    \
+    {                                                                                                                 \
+        if (a.R == 8) DS_LAUNCH(K, 8) else if (a.R == 4) DS_LAUNCH(K, 4) else DS_LAUNCH(K, 2)                          \
+    }
+    if (kmax <= 4) DS_CASE(4)
+    else if (kmax <= 8) DS_CASE(8)
+    else if (kmax <= 12) DS_CASE(12)
+    else if (kmax <= 16) DS_CASE(16)
+    else if (kmax <= 20) DS_CASE(20)
+    else if (kmax <= 24) DS_CASE(24)
+    else DS_CASE(32)
 #undef DS_CASE
+#undef DS_LAUNCH
     BB_LAUNCHED(ctx);
     return BB_OK;
 }

@@ -37,13 +37,20 @@ warnings.simplefilter('ignore')
 
 N_BLOCKS = 50
 WORKLOADS = {
-    # name: (n, p, mean density)
+    # name: (n, p, mean density)            binary sparse X, logit outcome (BASELINE configs 1, 3, 4)
     'C4': (1_000_000, 100_000, 0.001),
     'C3': (100_000, 20_000, 0.005),
     'C1': (10_000, 1_000, 0.01),
     'C4shard8': (125_000, 100_000, 0.001),     # one rank's share of C4 at N = 8 (profiling aid)
     'C4quarter': (250_000, 100_000, 0.001),    # two such shares (N = 2 reproduces the N = 8 per-rank load)
+    # dense fp64 X, linear outcome (BASELINE config 2); density 1.0 marks the dense family
+    'C2': (50_000, 5_000, 1.0),
+    'C2small': (5_000, 500, 1.0),
 }
+
+
+def is_dense(workload):
+    return WORKLOADS[workload][2] >= 1.0
 
 
 # ---- synthetic data (shared by both arms) ------------------------------------------------------
@@ -78,7 +85,23 @@ def generate_block(block, n, p, freq, seed=0):
     return X, y
 
 
+def generate_dense_rows(blocks, n, p, seed=0):
+    """BASELINE config 2: X = standard normal n x p fp64, y = X beta + N(0, 1); generated per row
+    block so that the matrix is the same for every number of ranks."""
+    Xs, ys = [], []
+    beta = true_coef(p)
+    for b in blocks:
+        lo, hi = n * b // N_BLOCKS, n * (b + 1) // N_BLOCKS
+        rng = np.random.default_rng([seed, 1000 + b])
+        Xb = rng.standard_normal((hi - lo, p))
+        Xs.append(Xb)
+        ys.append(Xb @ beta + rng.standard_normal(hi - lo))
+    return np.ascontiguousarray(np.vstack(Xs)), np.concatenate(ys)
+
+
 def generate_rows(blocks, n, p, density):
+    if density >= 1.0:
+        return generate_dense_rows(blocks, n, p)
     freq = column_frequencies(p, density)
     parts = [generate_block(b, n, p, freq) for b in blocks]
     X = sp.vstack([q[0] for q in parts], format='csr')
@@ -176,7 +199,7 @@ def reference_run(workload, steps, warmup, sample_blocks=None, init_state=None, 
     frac = X.shape[0] / n
     if ref is not None:
         kind = 'reference'
-        model = ref.RegressionModel(y, X, family='logit')
+        model = ref.RegressionModel(y, X, family='linear' if is_dense(workload) else 'logit')
         bridge = ref.BayesBridge(model, ref.RegressionCoefPrior(bridge_exponent=.5))
         kw = dict(n_burnin=0, coef_sampler_type='cg', seed=0, params_to_save=('global_scale',))
         if init_state is not None:
@@ -197,28 +220,41 @@ def reference_run(workload, steps, warmup, sample_blocks=None, init_state=None, 
         from oracle import cg_oracle as co
         from oracle.rand_port import PolyaGammaPort, TiltedStablePort
         t0 = time.time()
+        if is_dense(workload):
+            raise RuntimeError('oracle/_ref is not built and the numpy port only covers the logit family')
         coefs, n_cg_arr = co.gibbs_cg_oracle('logit', (y.astype(float), np.ones(len(y))), X, warmup + steps, 0, 0.5,
                                              float('inf'), float('inf'), 0.1, np.ones(p), PolyaGammaPort,
                                              TiltedStablePort, True)
         dt = (time.time() - t0) * steps / max(warmup + steps, 1)
         n_cg = float(n_cg_arr.mean())
     its = steps / dt
-    what = ('the full %s matrix (%d x %d, nnz %d)' % (workload, X.shape[0], p, X.nnz) if sample_blocks is None else
+    nnz_x = int(X.nnz) if sp.issparse(X) else int(X.size)
+    what = ('the full %s matrix (%d x %d, nnz %d)' % (workload, X.shape[0], p, nnz_x) if sample_blocks is None else
             'rows 0..%d of %s (%d of %d row blocks, %.0f%% of the rows; NOT scaled to the full problem)'
             % (X.shape[0] - 1, workload, sample_blocks, N_BLOCKS, 100 * frac))
     desc = {
-        'kind': kind, 'cores': 1,
-        'sample': '%s; %d timed Gibbs iterations after %d warm-up%s; scipy SpMV and the Cython PG / tilted-stable '
+        'kind': kind, 'cores': (os.cpu_count() if is_dense(workload) else 1),
+        'sample': '%s; %d timed Gibbs iterations after %d warm-up%s; %s and the Cython PG / tilted-stable '
                   'samplers are single-threaded (host has %d cores)'
                   % (what, steps, warmup, '' if init_state is None else ', chain started from the state the GPU chain reached',
+                     'numpy BLAS gemv uses all cores; the rest of the sampler' if is_dense(workload) else 'scipy SpMV',
                      os.cpu_count()),
-        'full_size': sample_blocks is None, 'mean_n_cg_iter': n_cg, 'sample_nnz': int(X.nnz),
+        'full_size': sample_blocks is None, 'mean_n_cg_iter': n_cg, 'sample_nnz': nnz_x,
         'seconds_per_iteration': dt / steps, 'generate_seconds': t_gen,
     }
     return its, desc
 
 
 # ---- main ---------------------------------------------------------------------------------------
+def kernel_version():
+    """Identifies the source of the roofline kernels (a DRAM-traffic capture is only quoted for the version it was taken on)."""
+    import hashlib
+    h = hashlib.sha1()
+    for f in ('bb_sell.cu', 'bb_dense.cu'):
+        h.update(open(os.path.join(ROOT, 'bayesbridge_b200', 'csrc', f), 'rb').read())
+    return h.hexdigest()[:12]
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -237,9 +273,14 @@ def main():
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     n, p, density = WORKLOADS[args.workload]
-    config = {'workload': args.workload, 'family': 'logit', 'n': n, 'p': p, 'mean_density': density,
-              'bridge_exponent': 0.5, 'coef_sampler_type': 'cg', 'format': 'binary CSR + CSC, int32 indices, fp64 math',
-              'l2': 'inputs (2.4 GB) exceed L2; no flush'}
+    dense = is_dense(args.workload)
+    family = 'linear' if dense else 'logit'
+    x_bytes = 8.0 * n * p if dense else 2 * 4.0 * density * n * p
+    config = {'workload': args.workload, 'family': family, 'n': n, 'p': p, 'mean_density': density,
+              'bridge_exponent': 0.5, 'coef_sampler_type': 'cg',
+              'format': ('dense row-major fp64' if dense else 'binary CSR + CSC, int32 indices, fp64 math'),
+              'l2': ('X (%.2f GB) %s the 126 MB L2; the roofline kernel is timed with an L2 flush before every launch'
+                     % (x_bytes / 1e9, 'exceeds' if x_bytes > 126e6 else 'FITS in'))}
 
     if args.impl == 'reference':
         if rank != 0:
@@ -269,11 +310,13 @@ def main():
     blocks = range(N_BLOCKS * rank // world, N_BLOCKS * (rank + 1) // world)
     X, y = generate_rows(blocks, n, p, density)
     row_offset = n * blocks[0] // N_BLOCKS
-    nnz_local = int(X.nnz)
-    from bayesbridge_b200.design_matrix import GpuSparseDesignMatrix
-    design = GpuSparseDesignMatrix(X, center_predictor=True, add_intercept=True, ctx=ctx,
-                                   presharded=(world > 1), n_global=n, row_offset=row_offset)
-    model = bb.RegressionModel(y, design, family='logit')
+    nnz_local = 0 if dense else int(X.nnz)
+    from bayesbridge_b200.design_matrix import GpuSparseDesignMatrix, GpuDenseDesignMatrix
+    nnz_local = int(X.size) if dense else nnz_local
+    Design = GpuDenseDesignMatrix if dense else GpuSparseDesignMatrix
+    design = Design(X, center_predictor=True, add_intercept=True, ctx=ctx,
+                    presharded=(world > 1), n_global=n, row_offset=row_offset)
+    model = bb.RegressionModel(y, design, family=family)
     bridge = bb.BayesBridge(model, bb.RegressionCoefPrior(bridge_exponent=.5))
     P = design.shape[1]
 
@@ -286,18 +329,26 @@ def main():
     # chain initialisation + W warm-up steps (untimed)
     _, info = bridge.gibbs(n_iter=max(args.warmup, 1), n_burnin=0, coef_sampler_type='cg', seed=0,
                            params_to_save=('coef', 'global_scale', 'logp'))
-    # roofline of the dominant kernel, measured live with CUDA events on the library stream
-    roof = {}
-    for what in ('spmv_dot', 'spmv_tdot'):
-        roof[what] = design.time_kernel(what, reps=10, flush_l2=False)
+    # roofline of the dominant kernel, measured live with CUDA events on the library stream; every timed launch is
+    # preceded by an L2 flush (a 512 MB write), i.e. these are cold-cache times; the warm ones are reported beside them
+    roof, roof_warm = {}, {}
+    kernels = ('fused_op',) if dense else ('spmv_dot', 'spmv_tdot')
+    if dense:
+        try:
+            design.time_kernel('fused_op', reps=1, flush_l2=False)
+        except RuntimeError:          # p too wide for the one-pass streaming kernel: the two-pass products
+            kernels = ('op',)
+    for what in kernels:
+        roof[what] = design.time_kernel(what, reps=10, flush_l2=True)
+        roof_warm[what] = design.time_kernel(what, reps=10, flush_l2=False)
 
     # the same kernel on the 12 B/nnz layout (fp64 values + int32 indices) of the same matrix: the format
     # SURVEY section 8d's byte formulas are written for; measured here so both fractions are on record
     valued = {}
-    if world == 1:
+    if world == 1 and not dense and os.environ.get('BENCH_VALUED', '1') == '1':
         Dv = GpuSparseDesignMatrix(X, center_predictor=True, add_intercept=True, ctx=ctx, pattern_only=False)
         for what in ('spmv_dot', 'spmv_tdot'):
-            valued[what] = Dv.time_kernel(what, reps=10, flush_l2=False)
+            valued[what] = Dv.time_kernel(what, reps=10, flush_l2=True)
         del Dv
 
     sampler = ClockSampler(local_rank)
@@ -351,12 +402,20 @@ def main():
     n_cg = info2['_reg_coef_sampling_info']['n_cg_iter']
     value = K / (dev_ms / 1000.0)
     e2e = K / wall
-    # algorithmic bytes of one launch of the dominant kernel (pattern-only format:
-    # 4 B per nnz index + pointers + gathered and written vectors); per rank
+    # algorithmic bytes of one launch of the dominant kernel (per rank).  Sparse, pattern-only format:
+    # 4 B per nnz index + pointers + gathered and written vectors.  Dense: the one-pass fused operator reads X once.
     n_loc = design.shape[0]
-    b_dot = 4 * nnz_local + 4 * (n_loc + 1) + 8 * P + 8 * n_loc
-    b_tdot = 4 * nnz_local + 4 * (P + 1) + 8 * n_loc + 8 * P
-    dom = 'spmv_tdot' if roof['spmv_tdot'] >= roof['spmv_dot'] else 'spmv_dot'
+    if dense:
+        dom = kernels[0]
+        passes = 1 if dom == 'fused_op' else 2
+        alg = {dom: passes * 8 * n_loc * p + 8 * (2 * n_loc + 2 * P)}
+        kernel_name = 'k_dense_stream<FUSED> (one pass over X)' if dom == 'fused_op' else 'k_dense_stream<DOT_W> + <TDOT> (two passes)'
+    else:
+        alg = {'spmv_dot': 4 * nnz_local + 4 * (n_loc + 1) + 8 * P + 8 * n_loc,
+               'spmv_tdot': 4 * nnz_local + 4 * (P + 1) + 8 * n_loc + 8 * P}
+        dom = 'spmv_tdot' if roof['spmv_tdot'] >= roof['spmv_dot'] else 'spmv_dot'
+        variant = ctx.get_option('spmv_variant')
+        kernel_name = ('k_sell_spmv<binary> (%s)' if variant == 1 else 'k_seg_spmv (%s)') % dom
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
@@ -364,27 +423,25 @@ def main():
         pass
     peak = float(peaks.get('hbm_gbs', 6650.0))
     peak_src = 'measured (MEASURED_PEAKS.json hbm_gbs)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s'
-    ach = (b_tdot if dom == 'spmv_tdot' else b_dot) / (roof[dom] * 1e-3) / 1e9
-    # DRAM traffic of the same kernel from the committed `ncu --set full` capture (C4, one GPU): row 0 = dot, row 1 = Tdot
+    ach = alg[dom] / (roof[dom] * 1e-3) / 1e9
+    # DRAM traffic of the same kernel: from the `ncu --set full` capture of THIS kernel version committed under
+    # profiles/ (ncu cannot run inside the timed bench); matched by kernel, workload and rank count, else null
     traffic, traffic_src = None, None
     try:
-        if args.workload == 'C4' and world == 1:
-            import csv
-            rows = list(csv.reader(open(os.path.join(ROOT, 'profiles', 'r01_ncu_spmv_v6_c4.csv'))))
-            hdr, units = rows[0], rows[1]
-            row = rows[2 + (1 if dom == 'spmv_tdot' else 0)]
-            scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
-            traffic = 0.0
-            for name in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
-                i = hdr.index(name)
-                traffic += float(row[i].replace(',', '')) * scale[units[i]]
-            traffic_src = 'profiles/r01_ncu_spmv_v6_c4.csv (ncu --set full, same kernel and matrix)'
+        tr = json.load(open(os.path.join(ROOT, 'profiles', 'r02_traffic.json')))
+        ent = tr.get('%s/%s/n%d' % (args.workload, dom, world))
+        if ent and ent.get('kernel_version') == kernel_version():
+            traffic, traffic_src = float(ent['dram_bytes']), ent['source']
     except Exception:
         traffic, traffic_src = None, None
     line = {
         'metric': 'gibbs_iters_per_sec', 'value': value, 'unit': 'iter/s', 'n_gpus': world, 'steps': K,
         'warmup': args.warmup, 'ms_per_step': dev_ms / K, 'higher_is_better': True, 'scaling': 'strong',
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': dict(config, nnz=int(nnz_total)),
+        'cg_iteration': {'fused_p_side_kernel': bool(ctx.get_option('cg_fused')),
+                         'exchange': ('none (one rank)' if world == 1 else
+                                      ('two-shot peer-memory all-reduce inside the fused kernel' if ctx.get_option('cg_fused') and getattr(ctx, 'p2p_capacity', 0) > 0
+                                       else 'ncclAllReduce'))},
         'e2e': {'value': e2e, 'unit': 'iter/s', 'ms_per_step_wall': 1000 * wall / K,
                 # device-resident P-side state: per step only the coefficient draw (P doubles) and a few scalars
                 # come back; nothing P-length goes up (BB_RESIDENT_STATE=0: 4P+(P-1) doubles up, 2P-1 down)
@@ -395,15 +452,16 @@ def main():
         'mean_n_cg_iter': float(np.mean(n_cg)),
         'clocks': sampler.summary(),
         'roofline': {
-            'bound': 'hbm', 'kernel': 'k_seg_spmv (%s)' % dom, 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
+            'bound': 'hbm', 'kernel': kernel_name, 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
             'frac': ach / peak, 'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peak_src,
-            'algorithmic_bytes_per_launch': int(b_tdot if dom == 'spmv_tdot' else b_dot),
-            'ms_per_launch': roof[dom],
-            'other': {'spmv_dot_ms': roof['spmv_dot'], 'spmv_dot_GBs': b_dot / (roof['spmv_dot'] * 1e-3) / 1e9,
-                      'spmv_tdot_ms': roof['spmv_tdot'], 'spmv_tdot_GBs': b_tdot / (roof['spmv_tdot'] * 1e-3) / 1e9},
+            'algorithmic_bytes_per_launch': int(alg[dom]),
+            'ms_per_launch': roof[dom], 'timing': 'CUDA events on the library stream, L2 flushed before every launch (cold)',
+            'other': dict([(k + '_ms', v) for k, v in roof.items()] + [(k + '_GBs', alg[k] / (v * 1e-3) / 1e9) for k, v in roof.items()]
+                          + [(k + '_ms_warm', v) for k, v in roof_warm.items()]
+                          + [(k + '_frac_warm', alg[k] / (v * 1e-3) / 1e9 / peak) for k, v in roof_warm.items()]),
             'valued_format_12B_per_nnz': {
-                what: {'ms': ms, 'GBs': ((b_dot if what == 'spmv_dot' else b_tdot) + 8 * nnz_local) / (ms * 1e-3) / 1e9,
-                       'frac': ((b_dot if what == 'spmv_dot' else b_tdot) + 8 * nnz_local) / (ms * 1e-3) / 1e9 / peak}
+                what: {'ms': ms, 'GBs': (alg[what] + 8 * nnz_local) / (ms * 1e-3) / 1e9,
+                       'frac': (alg[what] + 8 * nnz_local) / (ms * 1e-3) / 1e9 / peak}
                 for what, ms in valued.items()},
         },
     }

@@ -99,6 +99,16 @@ int  bb_dot(bb_mat* mat, const double* v, double* out);
 int  bb_tdot(bb_mat* mat, const double* w, double* out);
 /* diag(X' diag(weight) X)[P], summed over shards */
 int  bb_fisher_diag(bb_mat* mat, const double* weight, double* out);
+/* X' diag(weight) X, P x P row-major (symmetric), summed over shards: compute_fisher_info(weight, diag_only=False),
+ * design_matrix/dense_matrix.py:54-58, sparse_matrix.py:131-162.  fp64 tensor-core (mma.sync m8n8k4) tile kernel;
+ * a sparse design is densified on the device first.  device_ms (nullable): milliseconds of the X'WX kernel alone. */
+int  bb_fisher_full(bb_mat* mat, const double* weight, double* out, double* device_ms);
+/* The direct ("cholesky") Gaussian draw of reg_coef_sampler/direct_gaussian_sampler.py:4-44 (generate_gaussian_with_weight):
+ * coef ~ N(Sigma z, Sigma), Sigma^-1 = X' diag(omega) X + diag(prior_prec_sqrt)^2, Jacobi-scaled, upper Cholesky factor,
+ * with the standard normal vector `gaussian_vec[P]` supplied by the caller (the reference draws it from numpy's global
+ * stream).  omega: host pointer or NULL for the resident precisions.  stats (nullable): [ms X'WX, ms factorisation]. */
+int  bb_cholesky_sample(bb_mat* mat, const double* omega, const double* prior_prec_sqrt, const double* z,
+                        const double* gaussian_vec, double* coef_out, double* stats);
 
 /* ---- resident observation-side vectors (avoid n-length PCIe traffic per Gibbs iteration) - */
 /* logit: n_trial, n_success;  linear: n_trial==NULL, n_success = y */
