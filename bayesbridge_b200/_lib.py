@@ -49,6 +49,7 @@ SIGNATURES = {
     'bb_tdot': (c_int, [c_void_p, P_dbl, P_dbl]),
     'bb_fisher_diag': (c_int, [c_void_p, P_dbl, P_dbl]),
     'bb_fisher_full': (c_int, [c_void_p, P_dbl, P_dbl, P_dbl]),
+    'bb_measure_fp64_mma': (c_int, [c_void_p, P_dbl]),
     'bb_cholesky_sample': (c_int, [c_void_p, P_dbl, P_dbl, P_dbl, P_dbl, P_dbl, P_dbl]),
     'bb_set_outcome': (c_int, [c_void_p, P_dbl, P_dbl]),
     'bb_set_obs_prec': (c_int, [c_void_p, P_dbl]),
@@ -181,6 +182,12 @@ class Context:
 
     def sync(self):
         check(load().bb_sync(self.handle))
+
+    def measure_fp64_mma_tflops(self):
+        """fp64 tensor-core throughput of this GPU (mma.sync m8n8k4 f64 from registers), TFLOP/s."""
+        v = c_dbl()
+        check(load().bb_measure_fp64_mma(self.handle, ctypes.byref(v)))
+        return v.value
 
     def init_comm_from_torch(self):
         """Attach an NCCL communicator spanning the ranks of the current torch.distributed job.

@@ -364,10 +364,20 @@ class BayesBridge():
 
     # ---- conditional updates ----------------------------------------------------------------------
     def update_regress_coef(self, coef, obs_prec, gscale, lscale, sampling_method, noise='device'):
-        """beta | omega, tau, lambda by the CG sampler (reference: bayesbridge.py:372-395)."""
-        if sampling_method != 'cg':
+        """beta | omega, tau, lambda by the CG sampler or the direct (Cholesky) draw (reference: bayesbridge.py:372-395)."""
+        if sampling_method not in ('cg', 'cholesky'):
             raise NotImplementedError()
         lib, mat = _lib.load(), self.model.design._mat
+        if sampling_method == 'cholesky':
+            design = self.model.design
+            if self.model.name == 'linear':
+                _lib.check(lib.bb_set_obs_prec_scalar(mat, float(obs_prec)))
+                z = design.Tdot(float(obs_prec) * _lib.as_f64(self.model.y))
+                omega = None
+            else:
+                z = design.Tdot(_lib.as_f64(self.model.n_success - self.model.n_trial / 2))   # omega * (kappa / omega)
+                omega = None if obs_prec is _RESIDENT else _lib.as_f64(obs_prec)
+            return self.reg_coef_sampler.sample_gaussian_posterior(None, design, omega, gscale, lscale, 'cholesky', z=z)
         philox = (self.rg.cg.seed, self.rg.cg._next_offset()) if noise == 'device' else None
         if self.model.name == 'linear':
             # omega = sigma^-2 * 1_n: the device keeps it as a scalar; z = omega X'y is formed there

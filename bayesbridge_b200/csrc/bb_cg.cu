@@ -488,7 +488,7 @@ extern "C" int bb_state_init(bb_mat* m, int n_unshrunk, const double* prior_sd_u
     BB_CUDA(cudaSetDevice(ctx->device));
     if (!m->st_lscale) {
         const size_t Pb = (size_t)(m->P + 1) * sizeof(double);
-        BB_CUDA(cudaMalloc((void**)&m->st_lscale, Pb));
+        BB_CUDA(cudaMalloc((void**)&m->st_lscale, Pb + 8 * sizeof(double)));      // + the three counters of the sharded draw
         BB_CUDA(cudaMalloc((void**)&m->st_mean, Pb));
         BB_CUDA(cudaMalloc((void**)&m->st_square, Pb));
         BB_CUDA(cudaMalloc((void**)&m->st_prior_sd, Pb));

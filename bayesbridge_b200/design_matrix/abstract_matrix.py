@@ -65,15 +65,17 @@ class AbstractDesignMatrix(abc.ABC):
         return out
 
     def compute_fisher_info(self, weight, diag_only=False):
-        """diag(X' W X) (sparse_matrix.py:164-177). The full matrix is only needed by the Cholesky
-        sampler, which the device classes do not offer (as the reference's cupy mode, gibbs_util.py:49-50)."""
-        if not diag_only:
-            raise NotImplementedError(
-                "Full Fisher information is not available for device-resident design matrices; "
-                "use coef_sampler_type='cg'.")
+        """X' W X: its diagonal (sparse_matrix.py:164-177) or the full P x P matrix (sparse_matrix.py:131-162,
+        dense_matrix.py:54-58) -- the latter by the fp64 tensor-core tile kernel of libbbgpu (bb_chol.cu); a sparse
+        design is densified on the device for it, so it is meant for the p <~ 1e4 the Cholesky sampler is for."""
         weight = _lib.as_f64(weight)
         if weight.shape != (self.shape[0],):
             raise ValueError("weight must have one entry per observation")
+        if not diag_only:
+            P = self.shape[1]
+            out = np.empty((P, P))
+            _lib.check(_lib.load().bb_fisher_full(self._mat, _lib.dptr(weight), _lib.dptr(out), None))
+            return out
         out = np.empty(self.shape[1])
         _lib.check(_lib.load().bb_fisher_diag(self._mat, _lib.dptr(weight), _lib.dptr(out)))
         return out

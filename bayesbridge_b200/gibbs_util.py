@@ -11,7 +11,7 @@ class SamplerOptions():
     def __init__(self, coef_sampler_type, global_scale_update='sample',
                  hmc_curvature_est_stabilized=False, noise='device'):
         """
-        coef_sampler_type : 'cg' (the device path); 'cholesky' / 'hmc' are rejected for device matrices
+        coef_sampler_type : 'cg' (the device path, default) or 'cholesky' (direct draw on the device); 'hmc' is rejected
         global_scale_update : 'sample' | 'optimize' | None
         noise : 'device' -- CG right-hand-side noise from on-device Philox streams (default);
                 'host'   -- drawn from np.random exactly like the reference and injected (parity mode)
@@ -35,8 +35,8 @@ class SamplerOptions():
 
     @staticmethod
     def pick_default_and_create(coef_sampler_type, options, model_name, design):
-        """Resolve the sampler (gibbs_util.py:33-84). Device matrices support 'cg' only, the rule the
-        reference applies to cupy matrices."""
+        """Resolve the sampler (gibbs_util.py:33-84).  Device matrices default to 'cg' (the reference's rule for its
+        accelerator mode) and also offer 'cholesky'; 'hmc' is not offered."""
         options = {} if options is None else dict(options)
         if 'coef_sampler_type' in options:
             if coef_sampler_type is not None:
@@ -45,14 +45,14 @@ class SamplerOptions():
             coef_sampler_type = options['coef_sampler_type']
         if coef_sampler_type not in (None, 'cholesky', 'cg', 'hmc'):
             raise ValueError("Unsupported sampler type.")
-        if coef_sampler_type not in (None, 'cg') and getattr(design, 'use_gpu', False):
-            raise ValueError("Only 'cg' sampler supported with device-resident design matrices.")
+        if coef_sampler_type not in (None, 'cg', 'cholesky') and getattr(design, 'use_gpu', False):
+            raise ValueError("Only the 'cg' and 'cholesky' samplers are supported with device-resident design matrices.")
         if model_name not in ('linear', 'logit'):
             raise ValueError("Only the linear and logit models are supported.")
         n_obs, n_pred = design.shape
         if n_pred > getattr(design, 'n_global', n_obs):
             warn("Sampler has not been optimized for 'small n' problem.")
-        options['coef_sampler_type'] = 'cg'
+        options['coef_sampler_type'] = 'cholesky' if coef_sampler_type == 'cholesky' else 'cg'
         return SamplerOptions(**options)
 
 

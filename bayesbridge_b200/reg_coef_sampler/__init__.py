@@ -3,5 +3,6 @@
 runs in libbbgpu.so (reference: reg_coef_sampler/cg_sampler.py)."""
 from .reg_coef_sampler import SparseRegressionCoefficientSampler
 from .cg_sampler import ConjugateGradientSampler
+from .direct_gaussian_sampler import generate_gaussian_with_weight
 
-__all__ = ['SparseRegressionCoefficientSampler', 'ConjugateGradientSampler']
+__all__ = ['SparseRegressionCoefficientSampler', 'ConjugateGradientSampler', 'generate_gaussian_with_weight']

@@ -9,6 +9,7 @@ import numpy as np
 import scipy.optimize
 
 from .cg_sampler import ConjugateGradientSampler
+from .direct_gaussian_sampler import generate_gaussian_with_weight
 from .reg_coef_posterior_summarizer import RegressionCoeffficientPosteriorSummarizer
 
 
@@ -16,8 +17,8 @@ class SparseRegressionCoefficientSampler():
 
     def __init__(self, n_coef, prior_sd_for_unshrunk, sampling_method,
                  stability_estimate_stabilized=False, regularizing_slab_size=float('inf')):
-        if sampling_method != 'cg':
-            raise ValueError("Only the 'cg' sampler is implemented for device-resident design matrices.")
+        if sampling_method not in ('cg', 'cholesky'):
+            raise ValueError("Only the 'cg' and 'cholesky' samplers are implemented for device-resident design matrices.")
         self.prior_sd_for_unshrunk = prior_sd_for_unshrunk
         self.n_unshrunk = len(prior_sd_for_unshrunk)
         self.regularizing_slab_size = regularizing_slab_size
@@ -50,10 +51,16 @@ class SparseRegressionCoefficientSampler():
             then formed there (for the logit model X'kappa, computed once and cached).
         obs_prec : array, or None to use the precision vector resident on the device.
         """
-        if method != 'cg':
-            raise NotImplementedError("Only method='cg' is available on the device.")
+        if method not in ('cg', 'cholesky'):
+            raise NotImplementedError("Only method='cg' and 'cholesky' are available on the device.")
         if z is None and y is not None:
             z = design.Tdot(obs_prec * y)
+        if method == 'cholesky':
+            # reg_coef_sampler.py:74-85: the direct draw needs no initial guess and leaves the summaries alone
+            prior_sd = np.concatenate((np.asarray(self.prior_sd_for_unshrunk, dtype=np.float64),
+                                       self.compute_prior_shrunk_scale(gscale, lscale)))
+            coef = generate_gaussian_with_weight(design, obs_prec, 1 / prior_sd, z)
+            return coef, {}
         k = self.n_unshrunk
         prior_prec_sqrt = np.empty(k + len(lscale))
         prior_prec_sqrt[:k] = 1 / np.asarray(self.prior_sd_for_unshrunk, dtype=np.float64)

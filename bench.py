@@ -179,7 +179,7 @@ def import_reference():
     return bayesbridge
 
 
-def reference_run(workload, steps, warmup, sample_blocks=None, init_state=None, data=None):
+def reference_run(workload, steps, warmup, sample_blocks=None, init_state=None, data=None, sampler='cg'):
     """The reference's own numpy/scipy/Cython sampler (oracle/_ref, the unmodified package built by
     oracle/build_ref.sh) through ITS public API, on the host cores of this box.
 
@@ -201,7 +201,7 @@ def reference_run(workload, steps, warmup, sample_blocks=None, init_state=None, 
         kind = 'reference'
         model = ref.RegressionModel(y, X, family='linear' if is_dense(workload) else 'logit')
         bridge = ref.BayesBridge(model, ref.RegressionCoefPrior(bridge_exponent=.5))
-        kw = dict(n_burnin=0, coef_sampler_type='cg', seed=0, params_to_save=('global_scale',))
+        kw = dict(n_burnin=0, coef_sampler_type=sampler, seed=0, params_to_save=('global_scale',))
         if init_state is not None:
             kw['init'] = init_state
         t0 = time.time()
@@ -213,7 +213,8 @@ def reference_run(workload, steps, warmup, sample_blocks=None, init_state=None, 
         else:
             _, info2 = bridge.gibbs(n_iter=steps, **kw)
             dt = info2['runtime']               # includes the (skipped or trivial) chain initialisation
-        n_cg = float(np.mean(info2['_reg_coef_sampling_info']['n_cg_iter'])) if steps > 0 else float('nan')
+        n_cg = (float(np.mean(info2['_reg_coef_sampling_info']['n_cg_iter']))
+                if steps > 0 and sampler == 'cg' else float('nan'))
     else:
         # the oracle port (numpy restatement) when the reference could not be built
         kind = 'port'
@@ -239,7 +240,7 @@ def reference_run(workload, steps, warmup, sample_blocks=None, init_state=None, 
                   % (what, steps, warmup, '' if init_state is None else ', chain started from the state the GPU chain reached',
                      'numpy BLAS gemv uses all cores; the rest of the sampler' if is_dense(workload) else 'scipy SpMV',
                      os.cpu_count()),
-        'full_size': sample_blocks is None, 'mean_n_cg_iter': n_cg, 'sample_nnz': nnz_x,
+        'full_size': sample_blocks is None, 'mean_n_cg_iter': (None if n_cg != n_cg else n_cg), 'sample_nnz': nnz_x,
         'seconds_per_iteration': dt / steps, 'generate_seconds': t_gen,
     }
     return its, desc
@@ -262,6 +263,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='C4', choices=sorted(WORKLOADS))
+    ap.add_argument('--sampler', default='cg', choices=['cg', 'cholesky'],
+                    help="coef_sampler_type; 'cholesky' is the comparator of BASELINE config 2 (dense workloads)")
     ap.add_argument('--ref-blocks', type=int, default=0,
                     help='time the CPU reference on the first K of the 50 row blocks only (0 = the full workload, the default)')
     ap.add_argument('--cpu-baseline-steps', type=int, default=2, help='full-size reference iterations of the cpu_baseline leg')
@@ -277,7 +280,7 @@ def main():
     family = 'linear' if dense else 'logit'
     x_bytes = 8.0 * n * p if dense else 2 * 4.0 * density * n * p
     config = {'workload': args.workload, 'family': family, 'n': n, 'p': p, 'mean_density': density,
-              'bridge_exponent': 0.5, 'coef_sampler_type': 'cg',
+              'bridge_exponent': 0.5, 'coef_sampler_type': args.sampler,
               'format': ('dense row-major fp64' if dense else 'binary CSR + CSC, int32 indices, fp64 math'),
               'l2': ('X (%.2f GB) %s the 126 MB L2; the roofline kernel is timed with an L2 flush before every launch'
                      % (x_bytes / 1e9, 'exceeds' if x_bytes > 126e6 else 'FITS in'))}
@@ -285,7 +288,7 @@ def main():
     if args.impl == 'reference':
         if rank != 0:
             return
-        value, desc = reference_run(args.workload, args.steps, max(args.warmup, 1), args.ref_blocks or None)
+        value, desc = reference_run(args.workload, args.steps, max(args.warmup, 1), args.ref_blocks or None, sampler=args.sampler)
         print(json.dumps({
             'impl': 'reference', 'metric': 'gibbs_iters_per_sec', 'value': value, 'unit': 'iter/s',
             'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1000.0 / value,
@@ -327,7 +330,7 @@ def main():
         ctx.sync()
 
     # chain initialisation + W warm-up steps (untimed)
-    _, info = bridge.gibbs(n_iter=max(args.warmup, 1), n_burnin=0, coef_sampler_type='cg', seed=0,
+    _, info = bridge.gibbs(n_iter=max(args.warmup, 1), n_burnin=0, coef_sampler_type=args.sampler, seed=0,
                            params_to_save=('coef', 'global_scale', 'logp'))
     # roofline of the dominant kernel, measured live with CUDA events on the library stream; every timed launch is
     # preceded by an L2 flush (a 512 MB write), i.e. these are cold-cache times; the warm ones are reported beside them
@@ -399,7 +402,8 @@ def main():
         return
 
     K = args.steps
-    n_cg = info2['_reg_coef_sampling_info']['n_cg_iter']
+    resident_state = os.environ.get('BB_RESIDENT_STATE', '1') != '0' and args.sampler == 'cg'
+    n_cg = info2['_reg_coef_sampling_info']['n_cg_iter'] if args.sampler == 'cg' else np.array([float('nan')])
     value = K / (dev_ms / 1000.0)
     e2e = K / wall
     # algorithmic bytes of one launch of the dominant kernel (per rank).  Sparse, pattern-only format:
@@ -434,6 +438,23 @@ def main():
             traffic, traffic_src = float(ent['dram_bytes']), ent['source']
     except Exception:
         traffic, traffic_src = None, None
+    roofline = None
+    if args.sampler == 'cholesky':
+        # the dominant kernel of the direct sampler is X'WX on the fp64 tensor cores: flops of the lower-triangle tiles
+        from bayesbridge_b200.reg_coef_sampler import generate_gaussian_with_weight
+        st_ = info2['_markov_chain_state']
+        om = np.full(n_loc, float(st_['obs_prec'])) if np.ndim(st_['obs_prec']) == 0 else np.asarray(st_['obs_prec'], dtype=float)
+        _, cst = generate_gaussian_with_weight(design, om, np.ones(P), np.zeros(P), return_stats=True)
+        nt = (p + 127) // 128
+        flops = 2.0 * n_loc * 128 * 128 * nt * (nt + 1) / 2
+        peak_t = ctx.measure_fp64_mma_tflops()
+        roofline = {'bound': 'tensor', 'kernel': 'k_fisher_syrk (X\'WX, mma.sync m8n8k4 f64; tcgen05 has no fp64 kind)',
+                    'achieved': flops / (cst['fisher_ms'] * 1e-3) / 1e12, 'peak': peak_t, 'unit': 'TFLOP/s',
+                    'frac': flops / (cst['fisher_ms'] * 1e-3) / 1e12 / peak_t, 'traffic': None,
+                    'peak_source': 'measured here: mma.sync m8n8k4 f64 back to back from registers (bb_measure_fp64_mma)',
+                    'algorithmic_flops_per_launch': flops, 'ms_per_launch': cst['fisher_ms'],
+                    'other': {'factorisation_ms (cuSOLVER potrf)': cst['factorisation_ms'], 'hbm_kernel': kernel_name,
+                              'hbm_frac': ach / peak}}
     line = {
         'metric': 'gibbs_iters_per_sec', 'value': value, 'unit': 'iter/s', 'n_gpus': world, 'steps': K,
         'warmup': args.warmup, 'ms_per_step': dev_ms / K, 'higher_is_better': True, 'scaling': 'strong',
@@ -445,13 +466,13 @@ def main():
         'e2e': {'value': e2e, 'unit': 'iter/s', 'ms_per_step_wall': 1000 * wall / K,
                 # device-resident P-side state: per step only the coefficient draw (P doubles) and a few scalars
                 # come back; nothing P-length goes up (BB_RESIDENT_STATE=0: 4P+(P-1) doubles up, 2P-1 down)
-                'h2d_bytes_per_step': 64 if os.environ.get('BB_RESIDENT_STATE', '1') != '0' else int(8 * (4 * P + (P - 1))),
-                'd2h_bytes_per_step': int(8 * P + 128) if os.environ.get('BB_RESIDENT_STATE', '1') != '0' else int(8 * (P + (P - 1)) + 64),
+                'h2d_bytes_per_step': (64 if resident_state else int(8 * (4 * P + (P - 1)))),
+                'd2h_bytes_per_step': (int(8 * P + 128) if resident_state else int(8 * (P + (P - 1)) + 64)),
                 'api': 'BayesBridge.gibbs_resume (public API; host numpy state in, samples out)'},
         'gpu_launches': int(launches),
-        'mean_n_cg_iter': float(np.mean(n_cg)),
+        'mean_n_cg_iter': (float(np.mean(n_cg)) if args.sampler == 'cg' else None),
         'clocks': sampler.summary(),
-        'roofline': {
+        'roofline': roofline if roofline is not None else {
             'bound': 'hbm', 'kernel': kernel_name, 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
             'frac': ach / peak, 'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peak_src,
             'algorithmic_bytes_per_launch': int(alg[dom]),
@@ -473,7 +494,8 @@ def main():
             init_state = {k: np.array(st[k], copy=True) if np.ndim(st[k]) else st[k]
                           for k in ('coef', 'obs_prec', 'local_scale', 'global_scale')}
             v, desc = reference_run(args.workload, args.cpu_baseline_steps, 0, args.ref_blocks or None,
-                                    init_state=init_state if not args.ref_blocks else None, data=None if args.ref_blocks else (X, y))
+                                    init_state=init_state if not args.ref_blocks else None, data=None if args.ref_blocks else (X, y),
+                                    sampler=args.sampler)
             line['cpu_baseline'] = dict(desc, value=v, unit='iter/s')
         except Exception as e:      # the baseline is reported, never required
             line['cpu_baseline'] = {'value': None, 'unit': 'iter/s', 'cores': 1, 'kind': 'reference',

@@ -172,8 +172,12 @@ int  bb_local_scale_resident(bb_mat* mat, double gscale, double char_exp, uint64
 
 /* ---- timing ----------------------------------------------------------------------------- */
 /* runs `reps` launches of one kernel class on resident data and returns mean device ms:
- * what = "dot" | "tdot" | "op" (one application of X' Omega X v) | "pg" | "fisher_diag" */
+ * what = "dot" | "tdot" | "op" (one application of X' Omega X v, two products) | "spmv_dot" | "spmv_tdot" (the sparse
+ * kernel alone) | "fused_op" (dense: the one-pass operator) | "exchange" (the all-reduce of a (p+1)-vector) */
 int  bb_time_kernel(bb_mat* mat, const char* what, int reps, int flush_l2, double* ms_out);
+/* measured fp64 tensor-core throughput (mma.sync m8n8k4 f64 issued back to back from registers), TFLOP/s: the roofline
+ * denominator of the X'WX kernel (MEASURED_PEAKS.json carries no fp64 figure) */
+int  bb_measure_fp64_mma(bb_ctx* ctx, double* tflops);
 
 #ifdef __cplusplus
 }

@@ -133,6 +133,26 @@ def cg_sample(design, obs_prec, prior_prec_sqrt, z, x0, s, maxiter, atol, eps1, 
     return s * x, {'n_iter': n_iter, 'converged': info == 0, 'b': b}
 
 
+def fisher_full(design, weight):
+    """compute_fisher_info(weight, diag_only=False): dense_matrix.py:54-58 on the materialised [1, X - c] image, which
+    is also what the sparse class's algebra (sparse_matrix.py:131-162) evaluates to."""
+    A = design.toarray()
+    return A.T.dot(weight[:, np.newaxis] * A)
+
+
+def cholesky_sample(design, obs_prec, prior_prec_sqrt, z, gaussian_vec):
+    """direct_gaussian_sampler.py:4-44 with the standard normal vector supplied by the caller."""
+    import scipy.linalg
+    G = fisher_full(design, obs_prec)
+    diag = prior_prec_sqrt ** 2 + np.diag(G)
+    J = 1 / np.sqrt(diag)
+    Prec = J[:, np.newaxis] * G * J[np.newaxis, :]
+    Prec += np.diag((J * prior_prec_sqrt) ** 2)
+    U = scipy.linalg.cholesky(Prec, lower=False)
+    mean = scipy.linalg.cho_solve((U, False), J * z)
+    return J * (mean + scipy.linalg.solve_triangular(U, gaussian_vec, lower=False))
+
+
 def exact_gaussian_mean(design, obs_prec, prior_prec_sqrt, rhs):
     """Dense solve of (X' Omega X + diag(pps^2)) beta = rhs, for small p."""
     A = design.toarray()

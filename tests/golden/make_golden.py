@@ -232,7 +232,43 @@ def golden_chain():
             out['logit_n_success'], out['logit_n_trial'] = outcome
         else:
             out['linear_y'] = outcome
+    # the 'cholesky' combo of the reference's regression test (test_gibb.py:12-13: logit, dense X)
+    outcome, X = test_gibb_data('logit', 'dense')
+    prior = ref.RegressionCoefPrior(sd_for_intercept=2., regularizing_slab_size=1., bridge_exponent=0.25)
+    br = ref.BayesBridge(ref.RegressionModel(outcome, X, 'logit'), prior)
+    s, info = br.gibbs(10, 0, init={'global_scale': 0.1, 'local_scale': np.ones(50)},
+                       coef_sampler_type='cholesky', seed=0, params_to_save='all')
+    out['logitchol_coef'], out['logitchol_gscale'] = s['coef'], s['global_scale']
     np.savez(os.path.join(HERE, 'chain_ref.npz'), **out)
+
+
+def golden_cholesky():
+    """Reference outputs of the direct sampler's pieces: compute_fisher_info(weight) (full matrix) of the dense and the
+    sparse class, and generate_gaussian_with_weight with numpy's global stream seeded (direct_gaussian_sampler.py)."""
+    from bayesbridge.reg_coef_sampler.direct_gaussian_sampler import generate_gaussian_with_weight
+    out = {}
+    rng = np.random.default_rng(21)
+    n, p = 400, 37
+    Xd = rng.standard_normal((n, p))
+    Xs = sparse_problem(5, n, p, 0.15, False)
+    out['Xd'], out['Xs_dense_image'] = Xd, Xs.toarray()
+    w = rng.random(n) * 0.25 + 0.01
+    out['weight'] = w
+    for c in (0, 1):
+        for i in (0, 1):
+            Dd = DenseDesignMatrix(Xd.copy(), center_predictor=bool(c), add_intercept=bool(i))
+            Ds = SparseDesignMatrix(Xs, use_mkl=False, center_predictor=bool(c), add_intercept=bool(i))
+            out['fisher_dense_%d%d' % (c, i)] = Dd.compute_fisher_info(w)
+            out['fisher_sparse_%d%d' % (c, i)] = Ds.compute_fisher_info(w)
+    P = p + 1
+    pps = np.concatenate(([0.5], 1 / (0.1 * rng.random(p) + 1e-2)))
+    z = rng.standard_normal(P)
+    out['pps'], out['z'] = pps, z
+    for name, D in (('dense', DenseDesignMatrix(Xd.copy(), center_predictor=True, add_intercept=True)),
+                    ('sparse', SparseDesignMatrix(Xs, use_mkl=False, center_predictor=True, add_intercept=True))):
+        np.random.seed(13)
+        out['draw_' + name] = generate_gaussian_with_weight(D, w, pps, z)
+    np.savez(os.path.join(HERE, 'cholesky_ref.npz'), **out)
 
 
 def golden_posterior():
@@ -253,7 +289,8 @@ def golden_posterior():
 
 if __name__ == '__main__':
     only = sys.argv[1:]
-    todo = [golden_random, golden_ks, golden_ks_quantiles, golden_design, golden_cg, golden_cg_c1, golden_summarizer, golden_chain, golden_posterior]
+    todo = [golden_random, golden_ks, golden_ks_quantiles, golden_design, golden_cg, golden_cg_c1, golden_summarizer, golden_chain,
+            golden_cholesky, golden_posterior]
     for fn in todo:
         if not only or fn.__name__ in only:
             fn()

@@ -240,3 +240,99 @@ def test_full_size_cg_solves_the_system_c3(ctx):
     assert np.linalg.norm(s * resid) <= 2e-10 * np.sqrt(P)       # the stopping rule acts on the preconditioned residual
     again, info2 = S.sample(D, omega, pps, z, np.zeros(P), 'prior', sd, maxiter=2000, atol=1e-10 * np.sqrt(P), seed=5)
     assert np.array_equal(again, coef) and info2['n_iter'] == info['n_iter']          # bit-reproducible
+
+
+# ---- the comparator of BASELINE config 2: full Fisher information and the direct (Cholesky) draw -------------------
+def test_full_fisher_information_matches_reference(ctx):
+    """compute_fisher_info(weight, diag_only=False) -- the fp64 tensor-core X'WX kernel + intercept / centring algebra --
+    against outputs of the reference's dense and sparse classes, all (centre, intercept) combinations."""
+    from bayesbridge_b200.design_matrix import GpuSparseDesignMatrix, GpuDenseDesignMatrix
+    g = golden('cholesky_ref.npz')
+    w = g['weight']
+    for name, X, Cls in (('dense', g['Xd'], GpuDenseDesignMatrix), ('sparse', sp.csr_matrix(g['Xs_dense_image']), GpuSparseDesignMatrix)):
+        for c in (0, 1):
+            for i in (0, 1):
+                D = Cls(X.copy(), center_predictor=bool(c), add_intercept=bool(i), ctx=ctx)
+                got, ref = D.compute_fisher_info(w), g['fisher_%s_%d%d' % (name, c, i)]
+                err = float(np.abs(got - ref).max() / np.abs(ref).max())
+                record_achieved('full_fisher_vs_reference', (name, c, i), err, 1e-12)
+                assert got.shape == ref.shape and err <= 1e-12, (name, c, i, err)
+                assert np.abs(got - got.T).max() <= 1e-13 * np.abs(got).max()
+
+
+@pytest.mark.parametrize('n,p', [(3000, 517), (20000, 1300)])
+def test_full_fisher_information_vs_oracle_larger(ctx, n, p):
+    """Tile edges (p not a multiple of 128), several tiles per dimension, n not a multiple of the 16-row stage."""
+    from bayesbridge_b200.design_matrix import GpuDenseDesignMatrix
+    rng = np.random.default_rng(p)
+    X = rng.standard_normal((n + 3, p))
+    w = rng.random(n + 3)
+    D = GpuDenseDesignMatrix(X.copy(), center_predictor=True, add_intercept=True, ctx=ctx)
+    ref = co.fisher_full(co.DesignOracle(X, True, True), w)
+    got = D.compute_fisher_info(w)
+    err = float(np.abs(got - ref).max() / np.abs(ref).max())
+    record_achieved('full_fisher_vs_oracle', (n, p), err, 1e-12)
+    assert err <= 1e-12
+
+
+def test_cholesky_draw_matches_reference(ctx):
+    """generate_gaussian_with_weight with numpy's global stream seeded like the reference run that produced the fixture
+    (direct_gaussian_sampler.py:4-44); the draw is a deterministic function of (omega, prior, z, g): <= 1e-10."""
+    from bayesbridge_b200.design_matrix import GpuSparseDesignMatrix, GpuDenseDesignMatrix
+    from bayesbridge_b200.reg_coef_sampler import generate_gaussian_with_weight
+    g = golden('cholesky_ref.npz')
+    for name, X, Cls in (('dense', g['Xd'], GpuDenseDesignMatrix), ('sparse', sp.csr_matrix(g['Xs_dense_image']), GpuSparseDesignMatrix)):
+        D = Cls(X.copy(), center_predictor=True, add_intercept=True, ctx=ctx)
+        np.random.seed(13)
+        draw = generate_gaussian_with_weight(D, g['weight'], g['pps'], g['z'])
+        err = relerr(draw, g['draw_' + name])
+        record_achieved('cholesky_draw_vs_reference', name, err, 1e-10)
+        assert err <= 1e-10, (name, err)
+
+
+def test_cg_and_cholesky_draw_agree_on_a_config2_shaped_problem(ctx):
+    """"cg vs cholesky" (BASELINE config 2, scaled to 4000 x 700): with the same right-hand side the tightly converged CG
+    solution equals the Cholesky sampler's mean, i.e. both draw from the same Gaussian."""
+    from bayesbridge_b200.design_matrix import GpuDenseDesignMatrix
+    from bayesbridge_b200.reg_coef_sampler import ConjugateGradientSampler, generate_gaussian_with_weight
+    rng = np.random.default_rng(4)
+    n, p = 4000, 700
+    X = rng.standard_normal((n, p))
+    D = GpuDenseDesignMatrix(X.copy(), center_predictor=True, add_intercept=True, ctx=ctx)
+    O = co.DesignOracle(X, True, True)
+    P = p + 1
+    omega = np.full(n, 0.7)
+    pps = np.concatenate(([0.5], 1 / (0.1 * rng.random(p) + 1e-2)))
+    z = rng.standard_normal(P)
+    gv = rng.standard_normal(P)
+
+    class Fixed:            # rand_gen stand-in handing out the fixed Gaussian vector
+        class np_random:
+            @staticmethod
+            def randn(k):
+                return gv.copy()
+    chol = generate_gaussian_with_weight(D, omega, pps, z, rand_gen=Fixed)
+    ref = co.cholesky_sample(O, omega, pps, z, gv)
+    err = relerr(chol, ref)
+    record_achieved('cholesky_draw_vs_oracle', (n, p), err, 1e-10)
+    assert err <= 1e-10
+    # CG with zero noise solves Phi beta = z: the mean of the Cholesky draw (gaussian_vec = 0)
+    zero = np.zeros(P)
+
+    class Zero:
+        class np_random:
+            @staticmethod
+            def randn(k):
+                return zero.copy()
+    mean = generate_gaussian_with_weight(D, omega, pps, z, rand_gen=Zero)
+    import ctypes
+    from bayesbridge_b200 import _lib
+    coef = np.empty(P)
+    ni, info = ctypes.c_int(), ctypes.c_int()
+    s = ConjugateGradientSampler(1).choose_preconditioner(pps, None, D, 'prior', np.ones(P))
+    _lib.check(_lib.load().bb_cg_sample(D._mat, _lib.dptr(omega), _lib.dptr(pps), _lib.dptr(z), _lib.dptr(zero), _lib.dptr(s),
+                                        1e-12 * np.sqrt(P), 2000, 0, _lib.dptr(np.zeros(n)), _lib.dptr(zero), 0, 0, _lib.dptr(coef),
+                                        ctypes.byref(ni), ctypes.byref(info), None))
+    err = relerr(coef, mean)
+    record_achieved('cg_mean_vs_cholesky_mean', (n, p), err, 1e-8, n_iter=ni.value)
+    assert info.value == 0 and err <= 1e-8

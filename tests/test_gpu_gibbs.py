@@ -52,6 +52,30 @@ def test_compat_chain_reproduces_reference(ctx, family):
     assert np.max(np.abs(n_cg - g[family + '_n_cg'])) <= 2     # the stopping test sits at the tolerance boundary
 
 
+def test_compat_cholesky_chain_reproduces_reference(ctx):
+    """The 'cholesky' combo of the reference's regression test (test_gibb.py:12-13: logit, dense X, 10 iterations, with
+    and without a restart in the middle) through the device's direct sampler."""
+    bb = _bb()
+    outcome, X, g = _test_gibb_problem('logit')
+    X = X.toarray()
+    prior = bb.RegressionCoefPrior(sd_for_intercept=2., regularizing_slab_size=1., bridge_exponent=0.25)
+    init = {'global_scale': 0.1, 'local_scale': np.ones(50)}
+
+    def bridge():
+        b = bb.BayesBridge(bb.RegressionModel(outcome, X, 'logit', ctx=ctx), prior)
+        b.rg.pg, b.rg.ts = PolyaGammaPort(), TiltedStablePort()
+        return b
+    samples, info = bridge().gibbs(10, 0, init=init, coef_sampler_type='cholesky', seed=0, params_to_save='all')
+    assert info['coef_sampler_type'] == 'cholesky'
+    saved = np.load(os.path.join(GOLDEN, 'ref_saved', 'logit_cholesky_samples.npy'))
+    assert np.allclose(samples['coef'][:, -1], saved, rtol=.001, atol=10e-6)       # the reference's own criterion
+    assert np.allclose(samples['coef'], g['logitchol_coef'], rtol=0, atol=1e-8)    # the reference chain run here
+    assert np.allclose(samples['global_scale'], g['logitchol_gscale'], rtol=1e-9)
+    s1, i1 = bridge().gibbs(5, 0, init=init, coef_sampler_type='cholesky', seed=0, params_to_save='all')
+    s2, _ = bridge().gibbs_resume(i1, 5, merge=True, prev_samples=s1)
+    assert np.allclose(s2['coef'], g['logitchol_coef'], rtol=0, atol=1e-8)
+
+
 def test_compat_chain_resume_equals_uninterrupted(ctx):
     bridge, g = _compat_bridge('logit', ctx)
     init = {'global_scale': 0.1, 'local_scale': np.ones(50)}
