@@ -50,6 +50,9 @@ SIGNATURES = {
     'bb_fisher_diag': (c_int, [c_void_p, P_dbl, P_dbl]),
     'bb_fisher_full': (c_int, [c_void_p, P_dbl, P_dbl, P_dbl]),
     'bb_measure_fp64_mma': (c_int, [c_void_p, P_dbl]),
+    'bb_column_moments': (c_int, [c_void_p, P_dbl, P_dbl]),
+    'bb_set_column_offset': (c_int, [c_void_p, P_dbl]),
+    'bb_loglik_and_gradient': (c_int, [c_void_p, P_dbl, c_dbl, c_int, P_dbl, P_dbl]),
     'bb_cholesky_sample': (c_int, [c_void_p, P_dbl, P_dbl, P_dbl, P_dbl, P_dbl, P_dbl]),
     'bb_set_outcome': (c_int, [c_void_p, P_dbl, P_dbl]),
     'bb_set_obs_prec': (c_int, [c_void_p, P_dbl]),

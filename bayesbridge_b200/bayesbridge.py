@@ -48,6 +48,7 @@ class BayesBridge():
         # the outcome, the cached X'kappa and the P-side state live on the DESIGN's device handle, and a design may be
         # shared by several models / bridges (several outcomes on one X): remember whose outcome is resident
         self.model.design._outcome_owner = id(self)
+        self.model.design._outcome_model = id(self.model)
 
     def _ensure_outcome(self):
         """Re-push this bridge's outcome if another bridge bound to the same design pushed its own since

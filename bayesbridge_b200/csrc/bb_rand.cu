@@ -459,6 +459,59 @@ extern "C" int bb_linear_rss(bb_mat* m, const double* coef, double* rss) {
 }
 
 
+// ---- log-likelihood and its gradient with everything n-length resident (chain initialisation) ----
+// logit  (logistic_model.py:49-55): ll = sum n_success eta - n_trial log(1 + e^eta) ; grad = X'(n_success - n_trial sigmoid(eta))
+// linear (linear_model.py:13-24):   ll = -prec/2 sum (y - eta)^2 (the n/2 log prec term is the host's) ; grad = prec X'(y - eta)
+__global__ void k_loglik_resid(i64 n, const double* __restrict__ n_trial, const double* __restrict__ y_or_success, int is_linear,
+                               double prec, const double* __restrict__ eta, double* __restrict__ w, double* __restrict__ red) {
+    __shared__ double sm[33];
+    double acc = 0.0;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        const double e = eta[i];
+        if (is_linear) {
+            const double r = y_or_success[i] - e;
+            acc += r * r;
+            w[i] = prec * r;
+        } else {
+            const double nt = n_trial[i], ns = y_or_success[i];
+            acc += ns * e - nt * (fmax(e, 0.0) + log1p(exp(-fabs(e))));       // np.logaddexp(0, eta)
+            w[i] = ns - nt / (1.0 + exp(-e));
+        }
+    }
+    acc = block_sum(acc, sm);
+    if (threadIdx.x == 0) red[blockIdx.x] = acc;
+}
+
+extern "C" int bb_loglik_and_gradient(bb_mat* m, const double* coef, double obs_prec, int loglik_only,
+                                      double* loglik, double* grad) {
+    BB_ARG(m && coef && loglik && (loglik_only || grad), "mat/coef/loglik/grad");
+    if (!m->has_outcome) { bb_set_error("bb_loglik_and_gradient needs bb_set_outcome"); return BB_ERR_STATE; }
+    bb_ctx* ctx = m->ctx;
+    cudaStream_t st = ctx->stream;
+    BB_CUDA(cudaSetDevice(ctx->device));
+    BBTimer timer_(ctx);
+    BB_TRY(linear_predictor(m, coef));
+    const int g = N_grid(m->n);
+    k_loglik_resid<<<g, 256, 0, st>>>(m->n, m->n_trial, m->n_success, m->is_linear, obs_prec, m->eta, m->w_n, m->red + RED_LL * RED_MAX);
+    ctx->launches++;
+    double* sc = m->red + RED_MISC * RED_MAX;                      // one double of scratch for the scalar
+    k_finish_scalar<<<1, 32, 0, st>>>(m->red + RED_LL * RED_MAX, g, sc);
+    ctx->launches++;
+    BB_TRY(bb_allreduce_dev(ctx, sc, 1));
+    double ll = 0.0;
+    BB_CUDA(cudaMemcpyAsync(&ll, sc, sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (!loglik_only) {
+        BB_TRY(bb_op_tdot(m, m->w_n));
+        BB_TRY(bb_op_tdot_finish(m, m->t_P));
+        BB_CUDA(cudaMemcpyAsync(grad, m->t_P, (size_t)m->P * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    timer_.end();
+    BB_CUDA(cudaStreamSynchronize(st));
+    timer_.commit();
+    *loglik = m->is_linear ? -0.5 * obs_prec * ll : ll;
+    return BB_OK;
+}
+
 // ---- local scales on the device (bayesbridge.py:458-478 with the state of bb_state_*) --------------------------
 // lambda_j = sqrt(0.5 / TS(alpha/2, (beta_j / tau)^2)); counts[0] = #(tilt <= 0), [1] = #(lambda == 0), [2] = #(lambda == inf)
 // Rank r of a row-sharded job draws only the scales [lo, hi) (the streams are keyed by the global coefficient index, so

@@ -1156,3 +1156,45 @@ extern "C" int bb_fisher_diag(bb_mat* m, const double* weight, double* out) {
     timer_.commit();
     return BB_OK;
 }
+
+
+// ---- column moments from the resident CSC image (construction: abstract_matrix.py:93-107 remove_intercept_indicator) ----
+__global__ void k_fill_ones(double* __restrict__ a, i64 n) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) a[i] = 1.0;
+}
+
+// sum_out[j] = sum_i x_ij, sumsq_out[j] = sum_i x_ij^2 over the LOCAL rows (the caller adds the shards)
+extern "C" int bb_column_moments(bb_mat* m, double* sum_out, double* sumsq_out) {
+    BB_ARG(m && sum_out && sumsq_out, "mat/sum/sumsq");
+    BB_ARG(m->is_sparse, "bb_column_moments: sparse designs only");
+    bb_ctx* ctx = m->ctx;
+    cudaStream_t st = ctx->stream;
+    BB_CUDA(cudaSetDevice(ctx->device));
+    BBTimer timer_(ctx);
+    if (m->p > 0) {
+        k_fill_ones<<<N_grid(m->n), 256, 0, st>>>(m->eps_n, m->n);
+        BB_LAUNCHED(ctx);
+        const i64 threads = m->p * 32;
+        k_fisher_diag_csc<<<(int)((threads + 255) / 256), 256, 0, st>>>(m->csc_ptr, m->csc_idx, m->csc_val, m->p, m->eps_n, m->q, m->b);
+        BB_LAUNCHED(ctx);
+        BB_CUDA(cudaMemcpyAsync(sumsq_out, m->q, (size_t)m->p * sizeof(double), cudaMemcpyDeviceToHost, st));
+        BB_CUDA(cudaMemcpyAsync(sum_out, m->b, (size_t)m->p * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    timer_.end();
+    BB_CUDA(cudaStreamSynchronize(st));
+    timer_.commit();
+    return BB_OK;
+}
+
+// (re)sets the centring offsets of a resident design: offset == NULL -> not centred
+extern "C" int bb_set_column_offset(bb_mat* m, const double* offset) {
+    BB_ARG(m != nullptr, "mat");
+    bb_ctx* ctx = m->ctx;
+    BB_CUDA(cudaSetDevice(ctx->device));
+    if (offset && m->p > 0) BB_CUDA(cudaMemcpyAsync(m->col_offset, offset, (size_t)m->p * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    else BB_CUDA(cudaMemsetAsync(m->col_offset, 0, (size_t)(m->p > 0 ? m->p : 1) * sizeof(double), ctx->stream));
+    BB_CUDA(cudaStreamSynchronize(ctx->stream));
+    m->centered = offset ? 1 : 0;
+    m->zk_valid = 0;
+    return BB_OK;
+}

@@ -33,25 +33,57 @@ class GpuSparseDesignMatrix(AbstractDesignMatrix):
         self.use_mkl = False
         sharded = self.ctx.nranks > 1
 
-        if sharded and presharded:
-            n_glob = int(n_global)
-            X, col_mean = self.remove_intercept_indicator_sharded(X, self.ctx, n_glob)
-            X_local = X.tocsr()
+        # Row block of this rank.  The column moments that decide which columns are constant (abstract_matrix.py:93-107)
+        # and give the centring offsets are taken on the DEVICE from the CSC image the upload builds anyway
+        # (bb_column_moments), instead of two host passes over the matrix (X.mean, X.power(2).mean: seconds at nnz = 1e8);
+        # only when a constant column is found (rare: a hand-added intercept) is the matrix cut on the host and sent again.
+        import time
+        t0 = time.perf_counter()
+        X_csr = X.tocsr()
+        if sharded and not presharded:
+            n_glob = X_csr.shape[0]
+            lo, hi = self.shard_rows(n_glob, self.ctx)
+            X_local, row_offset = X_csr[lo:hi], lo
         else:
-            X = self.remove_intercept_indicator(X)
-            n_glob = X.shape[0]
-            col_mean = np.squeeze(np.array(X.mean(axis=0))).reshape(-1)
-            X_csr = X.tocsr()
-            if sharded:
-                lo, hi = self.shard_rows(n_glob, self.ctx)
-                X_local, row_offset = X_csr[lo:hi], lo
-            else:
-                X_local = X_csr
-        self.column_offset = col_mean if center_predictor else np.zeros(X.shape[1])
-        self.X_main = X_local          # host image, kept for toarray() / export checks
+            n_glob = int(n_global) if (sharded and presharded) else X_csr.shape[0]
+            X_local = X_csr
         self.n_global = n_glob
         self.row_offset = int(row_offset)
+        # columns without a single stored entry anywhere (rare features of a sparse binary design) are constant by
+        # construction: one counting pass finds them, so that the matrix is cut BEFORE it is uploaded
+        if X_local.shape[1] > 0:
+            present = np.bincount(X_local.indices, minlength=X_local.shape[1]).astype(np.float64)
+            if sharded:
+                present = self.ctx.allreduce_host(present)
+            if np.any(present == 0):
+                import warnings
+                warnings.warn(
+                    "Intercept column (or numerically indistinguishable from such) detected. "
+                    "Do not add intercept manually. Removing....")
+                X_local = X_local[:, present > 0].tocsr()
+        t_prep = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        self._mat = None
+        self._upload(X_local, pattern_only, n_glob)
+        mean, constant = self._device_column_moments(X_local.shape[1], n_glob)
+        if np.any(constant):
+            import warnings
+            warnings.warn(
+                "Intercept column (or numerically indistinguishable from such) detected. "
+                "Do not add intercept manually. Removing....")
+            keep = np.logical_not(constant)
+            X_local, mean = X_local[:, keep].tocsr(), mean[keep]
+            _lib.check(_lib.load().bb_mat_free(self._mat))
+            self._mat = None
+            self._upload(X_local, pattern_only, n_glob)
+        self.column_offset = mean if center_predictor else np.zeros(X_local.shape[1])
+        if center_predictor:
+            _lib.check(_lib.load().bb_set_column_offset(self._mat, _lib.dptr(_lib.as_f64(self.column_offset))))
+        self.X_main = X_local          # host image, kept for toarray() / export checks
+        self.build_seconds = {'host_prepare': t_prep, 'upload_and_moments': time.perf_counter() - t0}
+        self._check_shards_agree()
 
+    def _upload(self, X_local, pattern_only, n_glob):
         indptr = np.ascontiguousarray(X_local.indptr)
         indices = np.ascontiguousarray(X_local.indices)
         if indptr.dtype != np.int32 or indices.dtype != np.int32:
@@ -62,14 +94,24 @@ class GpuSparseDesignMatrix(AbstractDesignMatrix):
         if pattern_only == 'auto':
             pattern_only = bool(data.size > 0 and np.all(data == 1.0))
         self.is_binary = bool(pattern_only)
-        offset = _lib.as_f64(self.column_offset) if center_predictor else None
         handle = ctypes.c_void_p()
         _lib.check(_lib.load().bb_csr_upload(
             self.ctx.handle, X_local.shape[0], X_local.shape[1], X_local.nnz,
             _lib.iptr(indptr), _lib.iptr(indices), None if self.is_binary else _lib.dptr(data),
-            _lib.dptr(offset), int(self.intercept_added), self.row_offset, n_glob, ctypes.byref(handle)))
+            None, int(self.intercept_added), self.row_offset, n_glob, ctypes.byref(handle)))
         self._mat = handle
-        self._check_shards_agree()
+
+    def _device_column_moments(self, p, n_glob):
+        """(column means, constant-column mask) from the device's column sums / sums of squares, summed over the shards."""
+        s1, s2 = np.zeros(p), np.zeros(p)
+        _lib.check(_lib.load().bb_column_moments(self._mat, _lib.dptr(s1), _lib.dptr(s2)))
+        if self.ctx.nranks > 1:
+            tot = self.ctx.allreduce_host(np.concatenate((s1, s2)))
+            s1, s2 = tot[:p], tot[p:]
+        mean, sq_mean = s1 / n_glob, s2 / n_glob
+        constant = (sq_mean - mean ** 2) < n_glob * 2.0 ** -52
+        return mean, constant
+
 
     @property
     def shape(self):

@@ -21,10 +21,16 @@ class LinearModel(AbstractModel):
 
     def compute_loglik_and_gradient(self, beta, obs_prec, loglik_only=False):
         """Log-likelihood up to the 2 pi constant and its gradient X'(y - X beta) * obs_prec (linear_model.py:13-24)."""
+        if getattr(self.design, '_mat', None) is not None:
+            ll, grad = self._device_loglik_and_gradient(beta, float(obs_prec), loglik_only)
+            return self.n_obs_global * math.log(obs_prec) / 2 + ll, grad
         resid = self.y - self.design.dot(beta)
         loglik = self.n_obs_global * math.log(obs_prec) / 2 - obs_prec * self._gsum(np.sum(resid ** 2)) / 2
         grad = None if loglik_only else obs_prec * self.design.Tdot(resid)
         return loglik, grad
+
+    def _outcome_arrays(self):
+        return None, self.y
 
     def get_hessian_matvec_operator(self, beta, obs_prec):
         """v -> -obs_prec X'X v, two device products per application (linear_model.py:29-31)."""

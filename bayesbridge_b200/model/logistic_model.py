@@ -29,7 +29,13 @@ class LogisticModel(AbstractModel):
         self.design = design
         self.name = 'logit'
 
+    def _outcome_arrays(self):
+        return self.n_trial, self.n_success
+
     def compute_loglik_and_gradient(self, beta, loglik_only=False):
+        """logistic_model.py:49-55.  With a device-resident design the whole evaluation runs there."""
+        if getattr(self.design, '_mat', None) is not None:
+            return self._device_loglik_and_gradient(beta, 1.0, loglik_only)
         eta = self.design.dot(beta)
         loglik = self._gsum(np.sum(self.n_success * eta - self.n_trial * np.logaddexp(0, eta)))
         if loglik_only:

@@ -110,6 +110,13 @@ int  bb_fisher_full(bb_mat* mat, const double* weight, double* out, double* devi
 int  bb_cholesky_sample(bb_mat* mat, const double* omega, const double* prior_prec_sqrt, const double* z,
                         const double* gaussian_vec, double* coef_out, double* stats);
 
+/* Column sums and sums of squares over the LOCAL rows, from the resident CSC image: the moments the constructor needs for
+ * remove_intercept_indicator and for the centring offsets (design_matrix/abstract_matrix.py:93-107, sparse_matrix.py:38-45)
+ * without two host passes over the matrix. */
+int  bb_column_moments(bb_mat* mat, double* sum_out, double* sumsq_out);
+/* (re)sets the centring offsets (column means) of a resident design; NULL = not centred */
+int  bb_set_column_offset(bb_mat* mat, const double* offset);
+
 /* ---- resident observation-side vectors (avoid n-length PCIe traffic per Gibbs iteration) - */
 /* logit: n_trial, n_success;  linear: n_trial==NULL, n_success = y */
 int  bb_set_outcome(bb_mat* mat, const double* n_trial, const double* n_success);
@@ -169,6 +176,13 @@ int  bb_cg_sample_resident(bb_mat* mat, const double* omega, double gscale, doub
  * lscale_out may be NULL */
 int  bb_local_scale_resident(bb_mat* mat, double gscale, double char_exp, uint64_t seed, uint64_t offset,
                              int* counts_out, double* lscale_out);
+
+/* Log-likelihood and gradient with the outcome resident (bb_set_outcome): only P-length vectors cross PCIe.
+ * logit : model/logistic_model.py:49-55   ll = sum n_success eta - n_trial log(1+e^eta), grad = X'(n_success - n_trial sigmoid(eta))
+ * linear: model/linear_model.py:13-24     ll = -obs_prec/2 ||y - X coef||^2 (the n/2 log obs_prec term is added by the caller),
+ *                                         grad = obs_prec X'(y - X coef)
+ * Used by the L-BFGS mode search that initialises a chain (reg_coef_sampler.py:281-327).  Sums run over all shards. */
+int  bb_loglik_and_gradient(bb_mat* mat, const double* coef, double obs_prec, int loglik_only, double* loglik, double* grad);
 
 /* ---- timing ----------------------------------------------------------------------------- */
 /* runs `reps` launches of one kernel class on resident data and returns mean device ms:

@@ -248,3 +248,61 @@ def test_full_size_properties_c3(ctx):
     wt = rng.random(n)
     uncentred = Sparse(X, center_predictor=False, add_intercept=True, ctx=ctx)
     assert relerr(uncentred.compute_fisher_info(wt, diag_only=True), uncentred.Tdot(wt)) < 1e-13
+
+
+def test_loglik_and_gradient_on_the_device(ctx):
+    """bb_loglik_and_gradient (chain initialisation, reg_coef_sampler.py:281-327 -> logistic_model.py:49-55,
+    linear_model.py:13-24): value and gradient vs the numpy formulas on the oracle design, sparse and dense."""
+    import bayesbridge_b200 as bb
+    Sparse, Dense = _designs()
+    rng = np.random.default_rng(12)
+    n, p = 6000, 90
+    Xs = random_sparse(n, p, 0.05, seed=4, binary=True)
+    Xd = rng.standard_normal((n, p))
+    for X, Cls in ((Xs, Sparse), (Xd, Dense)):
+        D = Cls(X.copy(), center_predictor=True, add_intercept=True, ctx=ctx)
+        O = co.DesignOracle(X, True, True)
+        beta = rng.standard_normal(p + 1) * 0.3
+        eta = O.dot(beta)
+        # logit
+        n_trial = rng.integers(1, 4, n).astype(float)
+        n_success = rng.binomial(n_trial.astype(int), 1 / (1 + np.exp(-eta))).astype(float)
+        model = bb.RegressionModel((n_success, n_trial), D, family='logit')
+        ll, grad = model.compute_loglik_and_gradient(beta)
+        ll_ref = np.sum(n_success * eta - n_trial * np.logaddexp(0, eta))
+        grad_ref = O.Tdot(n_success - n_trial / (1 + np.exp(-eta)))
+        assert abs(ll - ll_ref) <= 1e-12 * abs(ll_ref) and relerr(grad, grad_ref) < 1e-12
+        ll2, g2 = model.compute_loglik_and_gradient(beta, loglik_only=True)
+        assert ll2 == ll and g2 is None
+        # linear, on the same design: the outcome resident on the device handle is switched to this model's
+        y = eta + rng.standard_normal(n)
+        lin = bb.RegressionModel(y, D, family='linear')
+        prec = 0.7
+        ll, grad = lin.compute_loglik_and_gradient(beta, prec)
+        ll_ref = n * np.log(prec) / 2 - prec * np.sum((y - eta) ** 2) / 2
+        assert abs(ll - ll_ref) <= 1e-12 * abs(ll_ref) and relerr(grad, prec * O.Tdot(y - eta)) < 1e-12
+        # and back: the first model re-pushes its outcome
+        ll3, _ = model.compute_loglik_and_gradient(beta + 0.0, loglik_only=True)
+        assert abs(ll3 - np.sum(n_success * eta - n_trial * np.logaddexp(0, eta))) <= 1e-12 * abs(ll3)
+
+
+def test_empty_and_constant_columns_are_dropped(ctx):
+    """remove_intercept_indicator (abstract_matrix.py:93-107) with the moments taken on the device: an empty column and
+    a column of ones both go, with the reference's warning; the centring offsets equal the host means."""
+    Sparse, _ = _designs()
+    X = random_sparse(500, 12, 0.2, seed=1, hot_column=False).tolil()
+    X[:, 3] = 0.0
+    X[:, 7] = 1.0
+    X = X.tocsr()
+    X.eliminate_zeros()
+    import warnings
+    with warnings.catch_warnings(record=True) as rec:
+        warnings.simplefilter('always')
+        D = Sparse(X, center_predictor=True, add_intercept=True, ctx=ctx)
+    assert any('Intercept column' in str(r.message) for r in rec)
+    keep = [j for j in range(12) if j not in (3, 7)]
+    assert D.shape == (500, 11)
+    assert np.allclose(D.column_offset, np.asarray(X[:, keep].mean(axis=0)).ravel(), rtol=1e-14, atol=0)
+    O = co.DesignOracle(X[:, keep], True, True)
+    v = np.random.default_rng(0).standard_normal(11)
+    assert relerr(D.dot(v), O.dot(v)) < 1e-13
