@@ -2,9 +2,10 @@
 and Polya-Gamma draws running as sm_100a CUDA kernels (libbbgpu.so). Same public names as the
 reference's `bayesbridge` package."""
 from .bayesbridge import BayesBridge
+from .batched import BatchedBayesBridge
 from .gibbs_util import SamplerOptions
 from .prior import RegressionCoefPrior
 from .model import RegressionModel
 from ._lib import Context
 
-__all__ = ['BayesBridge', 'SamplerOptions', 'RegressionCoefPrior', 'RegressionModel', 'Context']
+__all__ = ['BayesBridge', 'BatchedBayesBridge', 'SamplerOptions', 'RegressionCoefPrior', 'RegressionModel', 'Context']

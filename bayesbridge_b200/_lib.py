@@ -52,6 +52,15 @@ SIGNATURES = {
     'bb_measure_fp64_mma': (c_int, [c_void_p, P_dbl]),
     'bb_column_moments': (c_int, [c_void_p, P_dbl, P_dbl]),
     'bb_set_column_offset': (c_int, [c_void_p, P_dbl]),
+    'bb_batch_init': (c_int, [c_void_p, c_int]),
+    'bb_batch_free': (c_int, [c_void_p]),
+    'bb_batch_set_obs_prec': (c_int, [c_void_p, P_dbl]),
+    'bb_batch_get_obs_prec': (c_int, [c_void_p, P_dbl]),
+    'bb_dot_batched': (c_int, [c_void_p, P_dbl, P_dbl]),
+    'bb_tdot_batched': (c_int, [c_void_p, P_dbl, P_dbl]),
+    'bb_cg_sample_batched': (c_int, [c_void_p, P_dbl, P_dbl, P_dbl, P_dbl, P_dbl, c_dbl, c_int, c_int, P_dbl, P_dbl,
+                                     ctypes.POINTER(c_u64), ctypes.POINTER(c_u64), P_dbl, P_int, P_int]),
+    'bb_pg_from_coef_batched': (c_int, [c_void_p, P_dbl, ctypes.POINTER(c_u64), ctypes.POINTER(c_u64), P_dbl]),
     'bb_loglik_and_gradient': (c_int, [c_void_p, P_dbl, c_dbl, c_int, P_dbl, P_dbl]),
     'bb_cholesky_sample': (c_int, [c_void_p, P_dbl, P_dbl, P_dbl, P_dbl, P_dbl, P_dbl]),
     'bb_set_outcome': (c_int, [c_void_p, P_dbl, P_dbl]),

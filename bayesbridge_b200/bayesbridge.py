@@ -214,6 +214,7 @@ class BayesBridge():
 
         coef, obs_prec, lscale, gscale, init, initial_optim_info = \
             self.initialize_chain(init, self.prior.bridge_exp)
+        init_runtime = time.time() - start_time          # chain initialisation (mode search) split out of 'runtime'
         self._loglik_cache = None
 
         samples, sampling_info = {}, {}
@@ -278,6 +279,7 @@ class BayesBridge():
             'coef_sampler_type': options.coef_sampler_type,
             'saved_params': params_to_save,
             'runtime': runtime,
+            'init_runtime': init_runtime,
             'options': options.get_info(),
             '_init_optim_info': initial_optim_info,
             '_reg_coef_sampling_info': sampling_info,

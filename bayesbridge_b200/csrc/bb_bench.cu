@@ -1,6 +1,8 @@
 // Device-side timing of one kernel class on resident data (CUDA events on the launching stream).
 #include "bb_internal.cuh"
 
+int bb_batch_time_op(bb_mat* m);
+
 __global__ void k_flush(double* buf, i64 n, double v) {
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) buf[i] = v;
 }
@@ -31,6 +33,7 @@ extern "C" int bb_time_kernel(bb_mat* m, const char* what, int reps, int do_flus
     else if (!strcmp(what, "spmv_dot")) kind = 3;     // the SpMV kernel alone (+ its fix-up)
     else if (!strcmp(what, "spmv_tdot")) kind = 4;
     else if (!strcmp(what, "exchange")) kind = 5;     // all-reduce of the (p+1)-vector (every rank must call)
+    else if (!strcmp(what, "batch_op")) kind = 7;     // dense, batched chains: X V, Omega o, X'(.) for all chains (bb_batch_init first)
     else if (!strcmp(what, "fused_op")) kind = 6;     // dense: omega.(X sv) and its X' product in ONE pass over X (+ collect)
     BB_ARG(kind >= 0, "what must be dot | tdot | op | spmv_dot | spmv_tdot | exchange | fused_op");
     BB_ARG(kind < 3 || kind >= 5 || m->is_sparse, "spmv_* needs a sparse matrix");
@@ -76,6 +79,8 @@ extern "C" int bb_time_kernel(bb_mat* m, const char* what, int reps, int do_flus
             BB_TRY(bb_op_prepare(m, m->v_P, nullptr));
             BB_TRY(bb_op_dot(m, 1));
             BB_TRY(bb_op_tdot_flag(m, m->w_n, true, nullptr, false));
+        } else if (kind == 7) {
+            BB_TRY(bb_batch_time_op(m));
         } else if (kind == 6) {
             BB_TRY(bb_op_prepare(m, m->v_P, nullptr));
             BB_TRY(bb_dense_fused(m, nullptr));

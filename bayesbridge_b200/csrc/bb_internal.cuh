@@ -223,6 +223,7 @@ struct bb_mat {
     // cached z = X' kappa for the logit model (kappa = n_success - n_trial/2 is constant)
     double* zk; int zk_valid;
     unsigned long long* ps_bar;  // grid-barrier counter of the fused P-side kernel
+    void* batch;                 // batched multi-chain work space (bb_batch.cu), or NULL
 };
 
 enum { RED_MAX = 1024, RED_SLOTS = 12 };

@@ -459,6 +459,62 @@ extern "C" int bb_linear_rss(bb_mat* m, const double* coef, double* rss) {
 }
 
 
+// ---- batched chains (bb_batch.cu): omega[i][c] ~ PG(n_trial_i, eta[i][c]) on chain c's own stream, log-likelihood per chain ----
+constexpr int PGB_BC = 16;
+__global__ void __launch_bounds__(256)
+k_pg_loglik_batched(i64 n, const double* __restrict__ n_trial, const double* __restrict__ n_success, const double* __restrict__ eta_b,
+                    int C, const uint64_t* __restrict__ seeds, const uint64_t* __restrict__ offsets, i64 row_offset,
+                    double* __restrict__ omega_b, double* __restrict__ red /*[grid][16]*/) {
+    __shared__ double sm[8][PGB_BC];
+    const i64 idx = (i64)blockIdx.x * 256 + threadIdx.x;
+    const i64 i = idx >> 4;
+    const int c = (int)(idx & 15), lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double ll = 0.0;
+    if (i < n) {
+        double om = 0.0;
+        if (c < C) {
+            RandStream rs;
+            rs.init(seeds[c], offsets[c], (uint64_t)(row_offset + i), STREAM_PG);
+            const double e = eta_b[idx], nt = n_trial[i];
+            om = pg_draw(rs, (int)nt, e);
+            const double lae = (e > 0.0) ? e + log1p(exp(-e)) : log1p(exp(e));
+            ll = n_success[i] * e - nt * lae;
+        }
+        omega_b[idx] = om;
+    }
+    ll += __shfl_xor_sync(0xffffffffu, ll, 16);            // the two rows of a warp
+    if (lane < 16) sm[warp][lane] = ll;
+    __syncthreads();
+    if (threadIdx.x < PGB_BC) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += sm[w][threadIdx.x];
+        red[(i64)blockIdx.x * PGB_BC + threadIdx.x] = t;
+    }
+}
+__global__ void k_pg_ll_finish_batched(const double* __restrict__ red, i64 nblk, double* __restrict__ ll_b) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int c = warp; c < PGB_BC; c += nw) {
+        double t = 0.0;
+        for (i64 k = lane; k < nblk; k += 32) t += red[k * PGB_BC + c];
+        t = warp_sum(t);
+        if (lane == 0) ll_b[c] = t;
+    }
+}
+int bb_batch_pg_launch(bb_mat* m, const double* eta_b, int C, const uint64_t* seeds_dev, const uint64_t* offsets_dev,
+                       double* omega_b, double* red_scratch, double* ll_b) {
+    bb_ctx* ctx = m->ctx;
+    const i64 nblk = (m->n * PGB_BC + 255) / 256;
+    if (nblk > 0) {
+        k_pg_loglik_batched<<<(unsigned)nblk, 256, 0, ctx->stream>>>(m->n, m->n_trial, m->n_success, eta_b, C, seeds_dev, offsets_dev,
+                                                                    m->row_offset, omega_b, red_scratch);
+        BB_LAUNCHED(ctx);
+    }
+    k_pg_ll_finish_batched<<<1, 512, 0, ctx->stream>>>(red_scratch, nblk, ll_b);
+    BB_LAUNCHED(ctx);
+    return BB_OK;
+}
+
 // ---- log-likelihood and its gradient with everything n-length resident (chain initialisation) ----
 // logit  (logistic_model.py:49-55): ll = sum n_success eta - n_trial log(1 + e^eta) ; grad = X'(n_success - n_trial sigmoid(eta))
 // linear (linear_model.py:13-24):   ll = -prec/2 sum (y - eta)^2 (the n/2 log prec term is the host's) ; grad = prec X'(y - eta)

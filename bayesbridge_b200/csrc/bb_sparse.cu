@@ -943,10 +943,13 @@ int bb_mat_alloc_work(bb_mat* m) {
     return BB_OK;
 }
 
+extern "C" int bb_batch_free(bb_mat* m);
+
 extern "C" int bb_mat_free(bb_mat* m) {
     if (!m) return BB_OK;
     cudaSetDevice(m->ctx->device);
     cudaStreamSynchronize(m->ctx->stream);
+    bb_batch_free(m);
     if (m->cg_graph) cudaGraphExecDestroy(m->cg_graph);
     bb_slab_free(&m->fdot);
     bb_slab_free(&m->ftdot);

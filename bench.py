@@ -46,7 +46,11 @@ WORKLOADS = {
     # dense fp64 X, linear outcome (BASELINE config 2); density 1.0 marks the dense family
     'C2': (50_000, 5_000, 1.0),
     'C2small': (5_000, 500, 1.0),
+    # dense fp64 X, logit outcome, 16 independent chains advanced in lock-step (BASELINE config 5)
+    'C5': (200_000, 2_000, 1.0),
+    'C5small': (20_000, 400, 1.0),
 }
+N_CHAINS = {'C5': 16, 'C5small': 16}
 
 
 def is_dense(workload):
@@ -85,7 +89,7 @@ def generate_block(block, n, p, freq, seed=0):
     return X, y
 
 
-def generate_dense_rows(blocks, n, p, seed=0):
+def generate_dense_rows(blocks, n, p, seed=0, logit=False):
     """BASELINE config 2: X = standard normal n x p fp64, y = X beta + N(0, 1); generated per row
     block so that the matrix is the same for every number of ranks."""
     Xs, ys = [], []
@@ -95,13 +99,16 @@ def generate_dense_rows(blocks, n, p, seed=0):
         rng = np.random.default_rng([seed, 1000 + b])
         Xb = rng.standard_normal((hi - lo, p))
         Xs.append(Xb)
-        ys.append(Xb @ beta + rng.standard_normal(hi - lo))
+        if logit:
+            ys.append(rng.binomial(1, 1 / (1 + np.exp(-(-1.0 + Xb @ beta)))).astype(np.float64))
+        else:
+            ys.append(Xb @ beta + rng.standard_normal(hi - lo))
     return np.ascontiguousarray(np.vstack(Xs)), np.concatenate(ys)
 
 
-def generate_rows(blocks, n, p, density):
+def generate_rows(blocks, n, p, density, logit_dense=False):
     if density >= 1.0:
-        return generate_dense_rows(blocks, n, p)
+        return generate_dense_rows(blocks, n, p, logit=logit_dense)
     freq = column_frequencies(p, density)
     parts = [generate_block(b, n, p, freq) for b in blocks]
     X = sp.vstack([q[0] for q in parts], format='csr')
@@ -194,12 +201,12 @@ def reference_run(workload, steps, warmup, sample_blocks=None, init_state=None, 
     ref = import_reference()
     blocks = range(N_BLOCKS) if sample_blocks is None else range(sample_blocks)
     t_gen = time.time()
-    X, y = data if data is not None else generate_rows(blocks, n, p, density)
+    X, y = data if data is not None else generate_rows(blocks, n, p, density, logit_dense=workload in N_CHAINS)
     t_gen = time.time() - t_gen
     frac = X.shape[0] / n
     if ref is not None:
         kind = 'reference'
-        model = ref.RegressionModel(y, X, family='linear' if is_dense(workload) else 'logit')
+        model = ref.RegressionModel(y, X, family='linear' if (is_dense(workload) and workload not in N_CHAINS) else 'logit')
         bridge = ref.BayesBridge(model, ref.RegressionCoefPrior(bridge_exponent=.5))
         kw = dict(n_burnin=0, coef_sampler_type=sampler, seed=0, params_to_save=('global_scale',))
         if init_state is not None:
@@ -277,10 +284,11 @@ def main():
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     n, p, density = WORKLOADS[args.workload]
     dense = is_dense(args.workload)
-    family = 'linear' if dense else 'logit'
+    n_chains = N_CHAINS.get(args.workload, 1)
+    family = 'linear' if (dense and n_chains == 1) else 'logit'
     x_bytes = 8.0 * n * p if dense else 2 * 4.0 * density * n * p
     config = {'workload': args.workload, 'family': family, 'n': n, 'p': p, 'mean_density': density,
-              'bridge_exponent': 0.5, 'coef_sampler_type': args.sampler,
+              'bridge_exponent': 0.5, 'coef_sampler_type': args.sampler, 'n_chains': n_chains,
               'format': ('dense row-major fp64' if dense else 'binary CSR + CSC, int32 indices, fp64 math'),
               'l2': ('X (%.2f GB) %s the 126 MB L2; the roofline kernel is timed with an L2 flush before every launch'
                      % (x_bytes / 1e9, 'exceeds' if x_bytes > 126e6 else 'FITS in'))}
@@ -311,14 +319,16 @@ def main():
 
     # this rank's row blocks
     blocks = range(N_BLOCKS * rank // world, N_BLOCKS * (rank + 1) // world)
-    X, y = generate_rows(blocks, n, p, density)
+    X, y = generate_rows(blocks, n, p, density, logit_dense=n_chains > 1)
     row_offset = n * blocks[0] // N_BLOCKS
+    t_build = time.perf_counter()
     nnz_local = 0 if dense else int(X.nnz)
     from bayesbridge_b200.design_matrix import GpuSparseDesignMatrix, GpuDenseDesignMatrix
     nnz_local = int(X.size) if dense else nnz_local
     Design = GpuDenseDesignMatrix if dense else GpuSparseDesignMatrix
     design = Design(X, center_predictor=True, add_intercept=True, ctx=ctx,
                     presharded=(world > 1), n_global=n, row_offset=row_offset)
+    t_build = time.perf_counter() - t_build
     model = bb.RegressionModel(y, design, family=family)
     bridge = bb.BayesBridge(model, bb.RegressionCoefPrior(bridge_exponent=.5))
     P = design.shape[1]
@@ -329,14 +339,21 @@ def main():
         torch.cuda.synchronize()
         ctx.sync()
 
-    # chain initialisation + W warm-up steps (untimed)
-    _, info = bridge.gibbs(n_iter=max(args.warmup, 1), n_burnin=0, coef_sampler_type=args.sampler, seed=0,
-                           params_to_save=('coef', 'global_scale', 'logp'))
+    batch = None
+    if n_chains > 1:
+        batch = bb.BatchedBayesBridge(model, bb.RegressionCoefPrior(bridge_exponent=.5), n_chains)
+        info = {}
+    else:
+        # chain initialisation + W warm-up steps (untimed)
+        _, info = bridge.gibbs(n_iter=max(args.warmup, 1), n_burnin=0, coef_sampler_type=args.sampler, seed=0,
+                               params_to_save=('coef', 'global_scale', 'logp'))
     # roofline of the dominant kernel, measured live with CUDA events on the library stream; every timed launch is
     # preceded by an L2 flush (a 512 MB write), i.e. these are cold-cache times; the warm ones are reported beside them
     roof, roof_warm = {}, {}
     kernels = ('fused_op',) if dense else ('spmv_dot', 'spmv_tdot')
-    if dense:
+    if batch is not None:
+        kernels = ('batch_op',)
+    elif dense:
         try:
             design.time_kernel('fused_op', reps=1, flush_l2=False)
         except RuntimeError:          # p too wide for the one-pass streaming kernel: the two-pass products
@@ -371,7 +388,24 @@ def main():
     t0 = time.perf_counter()
     if prof is not None:
         prof.enable()
-    samples, info2 = bridge.gibbs_resume(info, args.steps)
+    if batch is None:
+        samples, info2 = bridge.gibbs_resume(info, args.steps)
+    else:
+        # the batched sampler has no resume: one call runs W untimed + K timed lock-step iterations; the timed region
+        # (device-time accumulator, launch counter, wall clock) is opened by the callback at iteration W + 1
+        W = max(args.warmup, 1)
+        opened = {}
+
+        def open_timed_region(it):
+            if it == W + 1:
+                barrier()
+                ctx.reset_device_ms()
+                ctx.reset_launch_count()
+                opened['t0'] = time.perf_counter()
+        samples, info2 = batch.gibbs(W + args.steps, 0, seeds=list(range(n_chains)), on_iteration=open_timed_region,
+                                     params_to_save=('coef', 'global_scale', 'logp'))
+        t0 = opened['t0']
+        info = info2
     if prof is not None:
         prof.disable()
         import pstats
@@ -403,13 +437,21 @@ def main():
 
     K = args.steps
     resident_state = os.environ.get('BB_RESIDENT_STATE', '1') != '0' and args.sampler == 'cg'
-    n_cg = info2['_reg_coef_sampling_info']['n_cg_iter'] if args.sampler == 'cg' else np.array([float('nan')])
-    value = K / (dev_ms / 1000.0)
-    e2e = K / wall
+    if batch is not None:
+        n_cg = info2['n_cg_iter'][-K:]
+    else:
+        n_cg = info2['_reg_coef_sampling_info']['n_cg_iter'] if args.sampler == 'cg' else np.array([float('nan')])
+    # batched chains: a step advances every chain by one Gibbs iteration -> chain-iterations per second
+    value = n_chains * K / (dev_ms / 1000.0)
+    e2e = n_chains * K / wall
     # algorithmic bytes of one launch of the dominant kernel (per rank).  Sparse, pattern-only format:
     # 4 B per nnz index + pointers + gathered and written vectors.  Dense: the one-pass fused operator reads X once.
     n_loc = design.shape[0]
-    if dense:
+    if batch is not None:
+        dom = 'batch_op'
+        alg = {dom: 2 * 8 * n_loc * p + 8 * 16 * (3 * n_loc + 2 * P)}       # two passes over X + the [n][16] / [p][16] operands
+        kernel_name = 'k_batch_dot<1> + k_batch_tdot (X V and X\'(Omega o U) for 16 chains, mma.sync m8n8k4 f64; X read twice)'
+    elif dense:
         dom = kernels[0]
         passes = 1 if dom == 'fused_op' else 2
         alg = {dom: passes * 8 * n_loc * p + 8 * (2 * n_loc + 2 * P)}
@@ -466,10 +508,20 @@ def main():
         'e2e': {'value': e2e, 'unit': 'iter/s', 'ms_per_step_wall': 1000 * wall / K,
                 # device-resident P-side state: per step only the coefficient draw (P doubles) and a few scalars
                 # come back; nothing P-length goes up (BB_RESIDENT_STATE=0: 4P+(P-1) doubles up, 2P-1 down)
-                'h2d_bytes_per_step': (64 if resident_state else int(8 * (4 * P + (P - 1)))),
-                'd2h_bytes_per_step': (int(8 * P + 128) if resident_state else int(8 * (P + (P - 1)) + 64)),
-                'api': 'BayesBridge.gibbs_resume (public API; host numpy state in, samples out)'},
+                'h2d_bytes_per_step': (int(8 * n_chains * 4 * P + 32 * n_chains) if batch is not None else
+                                       (64 if resident_state else int(8 * (4 * P + (P - 1))))),
+                'd2h_bytes_per_step': (int(8 * n_chains * P + 16 * n_chains) if batch is not None else
+                                       (int(8 * P + 128) if resident_state else int(8 * (P + (P - 1)) + 64))),
+                'api': ('BatchedBayesBridge.gibbs (public API; %d chains in lock-step; value counts chain-iterations)' % n_chains
+                        if batch is not None else 'BayesBridge.gibbs_resume (public API; host numpy state in, samples out)')},
         'gpu_launches': int(launches),
+        # one-off costs outside the timed region: design construction (host CSR preparation, upload, CSC + kernel formats)
+        # and the chain initialisation (L-BFGS mode search with the likelihood evaluated on the device)
+        'setup': {'design_build_s': t_build, 'design_build_split_s': getattr(design, 'build_seconds', None),
+                  'chain_init_s': info.get('init_runtime'),
+                  'chain_init_optim': {k: (int(v) if isinstance(v, (int, np.integer)) else v)
+                                       for k, v in (info.get('_init_optim_info') or {}).items()
+                                       if k in ('n_iter', 'n_logp_eval', 'n_grad_eval', 'n_design_matvec', 'is_success')}},
         'mean_n_cg_iter': (float(np.mean(n_cg)) if args.sampler == 'cg' else None),
         'clocks': sampler.summary(),
         'roofline': roofline if roofline is not None else {
@@ -491,7 +543,9 @@ def main():
             # bounded sample of the same workload: the reference's sampler on the FULL matrix for a few iterations,
             # started from the state this chain has reached (so that it solves equally hard CG problems)
             st = info2['_markov_chain_state']
-            init_state = {k: np.array(st[k], copy=True) if np.ndim(st[k]) else st[k]
+            if batch is not None:           # the reference runs the chains one after the other: chain 0 stands for all
+                st = {k: st[k][0] for k in ('coef', 'obs_prec', 'local_scale', 'global_scale')}
+            init_state = {k: np.array(st[k], copy=True) if np.ndim(st[k]) else float(st[k])
                           for k in ('coef', 'obs_prec', 'local_scale', 'global_scale')}
             v, desc = reference_run(args.workload, args.cpu_baseline_steps, 0, args.ref_blocks or None,
                                     init_state=init_state if not args.ref_blocks else None, data=None if args.ref_blocks else (X, y),
@@ -500,6 +554,13 @@ def main():
         except Exception as e:      # the baseline is reported, never required
             line['cpu_baseline'] = {'value': None, 'unit': 'iter/s', 'cores': 1, 'kind': 'reference',
                                     'sample': 'failed: %r' % (e,)}
+    if batch is not None:
+        flops = 2 * (2.0 * n_loc * p * 16)
+        peak_t = ctx.measure_fp64_mma_tflops()
+        line['roofline']['other'].update({
+            'tensor_TFLOPs': flops / (roof[dom] * 1e-3) / 1e12, 'tensor_peak_TFLOPs (measured, mma.sync m8n8k4 f64)': peak_t,
+            'tensor_frac': flops / (roof[dom] * 1e-3) / 1e12 / peak_t,
+            'one_pass_equivalent_hbm_frac (8 n p bytes)': (8.0 * n_loc * p) / (roof[dom] * 1e-3) / 1e9 / peak})
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

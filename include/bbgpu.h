@@ -184,6 +184,26 @@ int  bb_local_scale_resident(bb_mat* mat, double gscale, double char_exp, uint64
  * Used by the L-BFGS mode search that initialises a chain (reg_coef_sampler.py:281-327).  Sums run over all shards. */
 int  bb_loglik_and_gradient(bb_mat* mat, const double* coef, double obs_prec, int loglik_only, double* loglik, double* grad);
 
+/* ---- batched multi-chain form (BASELINE config 5; SURVEY section 8b "batched form with leading chain dimension") -------
+ * C <= 16 independent chains on ONE dense design: the CG iterations of all chains run in lock-step, so that the two
+ * products of an operator application become X V (n x C) and X'(Omega o U) (p x C) on the fp64 tensor cores and X is read
+ * once for all chains.  Host arrays are chain-major: [C][n] for observation-side, [C][P] for coefficient-side vectors.
+ * Every chain keeps the semantics of bb_cg_sample (reg_coef_sampler/cg_sampler.py:20-94 + scipy's cg): own omega, prior,
+ * right-hand-side noise (injected, or Philox keyed by (seeds[c], offsets[c], global row)), own stopping decision. */
+int  bb_batch_init(bb_mat* mat, int n_chains);
+int  bb_batch_free(bb_mat* mat);
+int  bb_batch_set_obs_prec(bb_mat* mat, const double* omega);            /* [C][n] */
+int  bb_batch_get_obs_prec(bb_mat* mat, double* omega_out);              /* [C][n] */
+int  bb_dot_batched(bb_mat* mat, const double* v, double* out);          /* out[c] = X v[c]   ([C][P] -> [C][n]) */
+int  bb_tdot_batched(bb_mat* mat, const double* w, double* out);         /* out[c] = X' w[c]  ([C][n] -> [C][P]) */
+int  bb_cg_sample_batched(bb_mat* mat, const double* omega, const double* prior_prec_sqrt, const double* z,
+                          const double* x0, const double* precond_scale, double atol, int maxiter, int noise_mode,
+                          const double* eps1, const double* eps2, const uint64_t* seeds, const uint64_t* offsets,
+                          double* coef_out, int* n_iter, int* info);
+/* omega_c | beta_c for every chain (bayesbridge.py:397-410, polya_gamma.pyx:40-216) + the logistic log-likelihoods;
+ * coef: [C][P] or NULL for the coefficients of the last batched draw; the precisions stay resident for the next draw */
+int  bb_pg_from_coef_batched(bb_mat* mat, const double* coef, const uint64_t* seeds, const uint64_t* offsets, double* loglik);
+
 /* ---- timing ----------------------------------------------------------------------------- */
 /* runs `reps` launches of one kernel class on resident data and returns mean device ms:
  * what = "dot" | "tdot" | "op" (one application of X' Omega X v, two products) | "spmv_dot" | "spmv_tdot" (the sparse

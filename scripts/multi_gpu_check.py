@@ -78,6 +78,33 @@ for name, Xm, Cls in (('sparse', X, GpuSparseDesignMatrix), ('dense', Xd, GpuDen
     b, _ = S.sample(Du, omega, pps, z, x0, 'prior', sd, maxiter=500, atol=1e-11, noise='device', philox=(9, 3))
     check(name + ' cg device-noise sharded vs unsharded', rel(a, b), 1e-8)
 
+# batched multi-chain CG draw (bb_batch.cu), sharded vs unsharded: C chains in lock-step, exchange of C (p+1) doubles
+nn, pp = Xd.shape
+Ds = GpuDenseDesignMatrix(Xd.copy(), center_predictor=True, add_intercept=True, ctx=ctx)
+Du = GpuDenseDesignMatrix(Xd.copy(), center_predictor=True, add_intercept=True, ctx=solo)
+lo, hi = Ds.row_offset, Ds.row_offset + Ds.shape[0]
+Cb, P = 3, pp + 1
+rng = np.random.default_rng(7)
+om_b = rng.random((Cb, nn)) * 0.25 + 0.01
+pps_b = np.concatenate((np.full((Cb, 1), 0.5), 1 / (0.1 * rng.random((Cb, pp)) + 1e-3)), axis=1)
+z_b, x0_b = rng.standard_normal((Cb, P)), 0.01 * rng.standard_normal((Cb, P))
+s_b = np.array([ConjugateGradientSampler(1).choose_preconditioner(pps_b[c], None, Du, 'prior', np.ones(P)) for c in range(Cb)])
+e1_b, e2_b = rng.standard_normal((Cb, nn)), rng.standard_normal((Cb, P))
+import ctypes
+def run_batched(D, om, e1_):
+    lib = _lib.load()
+    _lib.check(lib.bb_batch_init(D._mat, Cb))
+    coef = np.empty((Cb, P)); ni, info = (ctypes.c_int * Cb)(), (ctypes.c_int * Cb)()
+    _lib.check(lib.bb_cg_sample_batched(D._mat, _lib.dptr(np.ascontiguousarray(om)), _lib.dptr(pps_b), _lib.dptr(z_b), _lib.dptr(x0_b),
+                                        _lib.dptr(s_b), 1e-11 * np.sqrt(P), 500, 0, _lib.dptr(np.ascontiguousarray(e1_)), _lib.dptr(e2_b),
+                                        None, None, _lib.dptr(coef), ni, info))
+    return coef, list(ni)
+cs, ns = run_batched(Ds, om_b[:, lo:hi], e1_b[:, lo:hi])
+cu, nu = run_batched(Du, om_b, e1_b)
+check(f'batched cg (n_iter {ns}/{nu}) sharded vs unsharded', rel(cs, cu), 1e-8)
+t = torch.from_numpy(cs.copy()).to(tdev); t0 = t.clone(); dist.broadcast(t0, 0)
+check('batched cg replicas identical', float((t - t0).abs().max()), 0.0)
+
 # full chain, sharded vs unsharded, device RNG: identical streams => same chain up to CG tolerance
 y = rs.binomial(1, 1 / (1 + np.exp(-(X @ np.concatenate((np.full(5, 1.5), np.zeros(p - 5))) - 1.0))))
 chains = []

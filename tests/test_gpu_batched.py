@@ -1,0 +1,129 @@
+"""GPU: the batched multi-chain path (BASELINE config 5; SURVEY section 8b "batched form"): C chains on one dense design,
+products X V / X'(Omega o U) on the fp64 tensor cores, CG iterations in lock-step.
+
+* products vs numpy, every chain;
+* the batched CG draw with injected noise: every chain vs the oracle's single-chain solve (identical n_iter, <= 1e-8 when
+  converged) and vs this library's single-chain solve; a chain's result does not depend on its batch mates (bit for bit);
+* the batched Gibbs sampler: chain c follows BayesBridge.gibbs(seed = s_c) (same streams, same state)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from conftest import record_achieved
+from oracle import cg_oracle as co
+
+pytestmark = pytest.mark.gpu
+
+
+def relerr(a, b):
+    return float(np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(b), 1e-300))
+
+
+def _design(ctx, n, p, seed=0):
+    from bayesbridge_b200.design_matrix import GpuDenseDesignMatrix
+    X = np.random.default_rng(seed).standard_normal((n, p))
+    return X, GpuDenseDesignMatrix(X.copy(), center_predictor=True, add_intercept=True, ctx=ctx)
+
+
+@pytest.mark.parametrize('n,p,C', [(1000, 64, 16), (4099, 517, 16), (300, 33, 5), (2000, 129, 1)])
+def test_batched_products_vs_numpy(ctx, n, p, C):
+    from bayesbridge_b200 import _lib
+    X, D = _design(ctx, n, p, seed=n)
+    O = co.DesignOracle(X, True, True)
+    lib = _lib.load()
+    _lib.check(lib.bb_batch_init(D._mat, C))
+    rng = np.random.default_rng(1)
+    V, W = rng.standard_normal((C, p + 1)), rng.standard_normal((C, n))
+    U, T = np.empty((C, n)), np.empty((C, p + 1))
+    _lib.check(lib.bb_dot_batched(D._mat, _lib.dptr(V), _lib.dptr(U)))
+    _lib.check(lib.bb_tdot_batched(D._mat, _lib.dptr(W), _lib.dptr(T)))
+    for c in range(C):
+        assert relerr(U[c], O.dot(V[c])) < 1e-13, c
+        assert relerr(T[c], O.Tdot(W[c])) < 1e-13, c
+
+
+def _cg_inputs(rng, n, P, C):
+    omega = rng.random((C, n)) * 0.25 + 0.01
+    pps = np.concatenate((np.full((C, 1), 0.5), 1 / (0.1 * rng.random((C, P - 1)) + 1e-3)), axis=1)
+    z, x0, sd = rng.standard_normal((C, P)), 0.01 * rng.standard_normal((C, P)), 0.5 + rng.random((C, P))
+    return omega, pps, z, x0, sd
+
+
+def _batched_cg(D, omega, pps, z, x0, s, atol, maxiter, e1, e2):
+    from bayesbridge_b200 import _lib
+    C, P = pps.shape
+    coef = np.empty((C, P))
+    n_it, info = (ctypes.c_int * C)(), (ctypes.c_int * C)()
+    _lib.check(_lib.load().bb_cg_sample_batched(
+        D._mat, _lib.dptr(np.ascontiguousarray(omega)), _lib.dptr(np.ascontiguousarray(pps)), _lib.dptr(np.ascontiguousarray(z)),
+        _lib.dptr(np.ascontiguousarray(x0)), _lib.dptr(np.ascontiguousarray(s)), float(atol), int(maxiter), _lib.BB_NOISE_INJECT,
+        _lib.dptr(np.ascontiguousarray(e1)), _lib.dptr(np.ascontiguousarray(e2)), None, None, _lib.dptr(coef), n_it, info))
+    return coef, list(n_it), list(info)
+
+
+def test_batched_cg_draw_vs_oracle_and_single_chain(ctx):
+    from bayesbridge_b200 import _lib
+    from bayesbridge_b200.reg_coef_sampler import ConjugateGradientSampler
+    n, p, C = 6000, 257, 16
+    X, D = _design(ctx, n, p, seed=3)
+    O = co.DesignOracle(X, True, True)
+    P = p + 1
+    rng = np.random.default_rng(5)
+    omega, pps, z, x0, sd = _cg_inputs(rng, n, P, C)
+    s = np.array([co.precond_scale_prior(pps[c], 1, sd[c]) for c in range(C)])
+    e1, e2 = rng.standard_normal((C, n)), rng.standard_normal((C, P))
+    _lib.check(_lib.load().bb_batch_init(D._mat, C))
+    for atol_unit, bound in ((1e-5, 1e-7), (1e-12, 1e-8)):
+        atol = atol_unit * np.sqrt(P)
+        coef, n_it, info = _batched_cg(D, omega, pps, z, x0, s, atol, 500, e1, e2)
+        for c in range(C):
+            ref, rinfo = co.cg_sample(O, omega[c], pps[c], z[c], x0[c], s[c], 500, atol, e1[c], e2[c])
+            err = relerr(coef[c], ref)
+            record_achieved('batched_cg_vs_oracle', (atol_unit, c), err, bound, n_iter=n_it[c], n_iter_oracle=rinfo['n_iter'])
+            assert info[c] == 0 and n_it[c] == rinfo['n_iter'], (c, n_it[c], rinfo['n_iter'])
+            assert err <= bound, (atol_unit, c, err)
+    # the single-chain path of this library on chain 3 (same injected noise)
+    c = 3
+    one = np.empty(P)
+    ni, inf = ctypes.c_int(), ctypes.c_int()
+    _lib.check(_lib.load().bb_cg_sample(D._mat, _lib.dptr(omega[c].copy()), _lib.dptr(pps[c].copy()), _lib.dptr(z[c].copy()),
+                                        _lib.dptr(x0[c].copy()), _lib.dptr(s[c].copy()), 1e-12 * np.sqrt(P), 500, 0,
+                                        _lib.dptr(e1[c].copy()), _lib.dptr(e2[c].copy()), 0, 0, _lib.dptr(one),
+                                        ctypes.byref(ni), ctypes.byref(inf), None))
+    assert relerr(coef[c], one) <= 1e-10 and ni.value == n_it[c]
+    # independence: chain c alone in a batch of one gives the same bits as inside the batch of 16
+    _lib.check(_lib.load().bb_batch_init(D._mat, 1))
+    alone, n1, _ = _batched_cg(D, omega[c:c + 1], pps[c:c + 1], z[c:c + 1], x0[c:c + 1], s[c:c + 1], 1e-12 * np.sqrt(P), 500,
+                               e1[c:c + 1], e2[c:c + 1])
+    assert np.array_equal(alone[0], coef[c]) and n1[0] == n_it[c]
+
+
+def test_batched_gibbs_follows_the_single_chain_sampler(ctx):
+    import bayesbridge_b200 as bb
+    n, p, C = 3000, 60, 4
+    X, D = _design(ctx, n, p, seed=8)
+    rng = np.random.default_rng(2)
+    beta = np.zeros(p); beta[:5] = 1.0
+    y = rng.binomial(1, 1 / (1 + np.exp(-(X @ beta - 0.3))))
+    model = bb.RegressionModel(y, D, family='logit')
+    prior = bb.RegressionCoefPrior(bridge_exponent=.5)
+    seeds = [11, 12, 13, 14]
+    batch = bb.BatchedBayesBridge(model, prior, C)
+    bs, binfo = batch.gibbs(6, 0, seeds=seeds, params_to_save=('coef', 'global_scale', 'logp'))
+    assert bs['coef'].shape == (p + 1, 6, C) and binfo['n_cg_iter'].shape == (6, C)
+    assert np.all(np.isfinite(bs['coef'])) and np.all(np.isfinite(bs['logp']))
+    for c in (0, 3):
+        single, sinfo = bb.BayesBridge(model, prior).gibbs(6, 0, seed=seeds[c], coef_sampler_type='cg',
+                                                           params_to_save=('coef', 'global_scale', 'logp'))
+        # same streams and state; the products differ in summation order, so the chains agree to CG-tolerance level
+        # until an accept/reject decision of a PG / tilted-stable draw flips (not within the first iterations)
+        e1 = relerr(bs['coef'][:, 0, c], single['coef'][:, 0])
+        e3 = relerr(bs['coef'][:, 2, c], single['coef'][:, 2])
+        record_achieved('batched_gibbs_vs_single_chain', (c, 'iteration 1'), e1, 1e-5)
+        record_achieved('batched_gibbs_vs_single_chain', (c, 'iteration 3'), e3, 1e-3)
+        assert e1 <= 1e-5 and e3 <= 1e-3
+        assert abs(bs['global_scale'][0, c] / single['global_scale'][0] - 1) < 1e-5
+        assert abs(int(binfo['n_cg_iter'][0, c]) - int(sinfo['_reg_coef_sampling_info']['n_cg_iter'][0])) <= 1
+    # chains with different seeds differ
+    assert relerr(bs['coef'][:, -1, 0], bs['coef'][:, -1, 1]) > 1e-3

@@ -174,8 +174,9 @@ def test_edge_cases(ctx):
         D.dot(np.ones(3))
     with pytest.raises(ValueError):
         D.Tdot(np.ones(3))
-    with pytest.raises(NotImplementedError):
-        D.compute_fisher_info(np.ones(9), diag_only=False)
+    full = D.compute_fisher_info(np.ones(9), diag_only=False)          # the full matrix (Cholesky comparator) on a tiny design
+    A = O.toarray()
+    assert np.allclose(full, A.T @ A, rtol=1e-13, atol=1e-13)
     # an all-zero matrix: every column is constant and is dropped (as the reference does) -> intercept only
     import warnings
     with warnings.catch_warnings():

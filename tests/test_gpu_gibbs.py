@@ -158,9 +158,10 @@ def test_api_contract(ctx):
     model = bb.RegressionModel(y, X, family='logit', ctx=ctx)
     assert model.design.use_gpu and model.design.is_sparse and not model.design.use_cupy
     bridge = bb.BayesBridge(model, bb.RegressionCoefPrior())
-    for bad in ('cholesky', 'hmc'):                      # as the reference does for cupy matrices
-        with pytest.raises(ValueError):
-            bridge.gibbs(n_iter=1, coef_sampler_type=bad)
+    with pytest.raises(ValueError):                      # as the reference does for cupy matrices
+        bridge.gibbs(n_iter=1, coef_sampler_type='hmc')
+    s, info = bridge.gibbs(n_iter=2, coef_sampler_type='cholesky', seed=1)     # the direct sampler, also on a sparse design
+    assert info['coef_sampler_type'] == 'cholesky' and np.all(np.isfinite(s['coef']))
     s, info = bridge.gibbs(n_iter=3, init={'coef': np.ones(model.n_pred)}, seed=1)   # gpu_tests/test_gibbs.py:32-44
     assert info['options']['coef_sampler_type'] == 'cg'
     assert s['coef'].shape == (41, 3) and s['logp'].shape == (3,)
