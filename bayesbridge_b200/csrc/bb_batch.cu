@@ -499,12 +499,11 @@ extern "C" int bb_batch_init(bb_mat* m, int n_chains) {
     BALLOC(w->cg, BC); BALLOC(w->done_count, 1); BALLOC(w->seeds, BC); BALLOC(w->offsets, BC); BALLOC(w->ll_b, BC);
 #undef BALLOC
     BB_CUDA(cudaMallocHost((void**)&w->cg_host, BC * sizeof(CgScalars)));
-    static bool attr = false;
-    if (!attr) {
+    static BBDeviceOnce attr = {{0, 0, 0, 0}};
+    if (attr.first(ctx->device)) {
         BB_CUDA(cudaFuncSetAttribute(k_batch_dot<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         BB_CUDA(cudaFuncSetAttribute(k_batch_dot<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         BB_CUDA(cudaFuncSetAttribute(k_batch_tdot, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        attr = true;
     }
     BB_CUDA(cudaStreamSynchronize(st));
     return BB_OK;

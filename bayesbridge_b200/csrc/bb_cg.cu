@@ -352,6 +352,16 @@ static int cg_core(bb_mat* m, double atol, int maxiter, int philox, uint64_t see
     return BB_OK;
 }
 
+// a peer that never published (lost rank, mismatched call sequence) raises the exchange's error flag instead of hanging
+// the GPU: surface it as soon as the solve returns
+static int check_exchange_health(bb_ctx* ctx) {
+    if (ctx->nranks <= 1 || !ctx->p2p_ready) return BB_OK;
+    int ready = 0, err = 0;
+    BB_TRY(bb_comm_p2p_status(ctx, &ready, &err));
+    if (err != 0) { bb_set_error("peer-memory exchange timed out waiting for a rank (the ranks must issue the same sequence of calls)"); return BB_ERR_STATE; }
+    return BB_OK;
+}
+
 extern "C" int bb_cg_sample(bb_mat* m, const double* omega, const double* prior_prec_sqrt,
                             const double* z, const double* x0, const double* precond_scale,
                             double atol, int maxiter, int noise_mode,
@@ -385,6 +395,7 @@ extern "C" int bb_cg_sample(bb_mat* m, const double* omega, const double* prior_
     timer_.end();
     BB_CUDA(cudaStreamSynchronize(st));
     timer_.commit();
+    BB_TRY(check_exchange_health(ctx));
     const int done = m->cg_host->done;
     m->last_n_iter = m->cg_host->iter;
     if (n_iter) *n_iter = m->cg_host->iter;
@@ -565,6 +576,7 @@ extern "C" int bb_cg_sample_resident(bb_mat* m, const double* omega, double gsca
     timer_.end();
     BB_CUDA(cudaStreamSynchronize(st));
     timer_.commit();
+    BB_TRY(check_exchange_health(ctx));
     m->st_n_avg += 1;
     const int done = m->cg_host->done;
     m->last_n_iter = m->cg_host->iter;

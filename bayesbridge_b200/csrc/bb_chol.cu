@@ -258,9 +258,9 @@ static int fisher_g0(bb_mat* m, const double* w_dev, FisherWork* fw) {
     }
     BB_CUDA(cudaMalloc((void**)&fw->G0, (size_t)(p * p > 0 ? p * p : 1) * sizeof(double)));
     if (p > 0) {
-        static bool attr = false;
+        static BBDeviceOnce attr = {{0, 0, 0, 0}};
         const size_t smem = (size_t)4 * FK * FS * sizeof(double);
-        if (!attr) { BB_CUDA(cudaFuncSetAttribute(k_fisher_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+        if (attr.first(ctx->device)) BB_CUDA(cudaFuncSetAttribute(k_fisher_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const i64 nt = (p + FT - 1) / FT;
         k_fisher_syrk<<<(unsigned)(nt * (nt + 1) / 2), F_THREADS, smem, st>>>(fw->Xdense, n, p, w_dev, fw->G0);
         BB_LAUNCHED(ctx);

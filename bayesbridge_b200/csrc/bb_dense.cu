@@ -277,10 +277,9 @@ static int ds_launch_mode(bb_mat* m, const DenseStreamArgs& a, int grid, size_t 
     const int kmax = (int)((m->p + DS_THREADS - 1) / DS_THREADS);
 #define DS_LAUNCH(K, RRV)                                                                                             \
     {                                                                                                                 \
-        static bool attr = false;                                                                                     \
-        if (!attr) {                                                                                                  \
+        static BBDeviceOnce attr = {{0, 0, 0, 0}};                                                                    \
+        if (attr.first(ctx->device)) {                                                                                \
             BB_CUDA(cudaFuncSetAttribute(k_dense_stream<K, MODE, RRV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin)); \
-            attr = true;                                                                                              \
         }                                                                                                             \
         k_dense_stream<K, MODE, RRV><<<grid, DS_THREADS, smem, ctx->stream>>>(a);                                    \
     }

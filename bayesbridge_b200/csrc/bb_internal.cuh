@@ -35,6 +35,18 @@ void bb_set_error(const char* fmt, ...);
         }                                                                                  \
     } while (0)
 
+// Function attributes (opt-in shared memory) are per device: a once-flag per device, not per process, so that a process
+// holding contexts on several devices sets them on each.
+struct BBDeviceOnce {
+    unsigned long long mask[4];
+    bool first(int device) {
+        const int w = (device >> 6) & 3, b = device & 63;
+        if ((mask[w] >> b) & 1ull) return false;
+        mask[w] |= 1ull << b;
+        return true;
+    }
+};
+
 // counts a kernel launch and checks the launch error
 #define BB_LAUNCHED(ctx)                                                                   \
     do {                                                                                   \
@@ -74,7 +86,9 @@ struct bb_ctx {
     i64 opt_bank_permute;  // 1: reorder nnz inside (segment x tile) pieces so that staged gathers avoid bank conflicts
     i64 opt_spmv_bulk;     // 1 (default): stage the window with cp.async.bulk + mbarrier; 0: cooperative copy loop
     i64 opt_sell_lmax;     // sliced format: fragment length cap (0 = automatic)
-    i64 opt_spmv_variant;  // 1 (default): sliced lane-per-fragment kernel with 16-bit in-slab indices; 0: tile + segmented-scan kernel
+    i64 opt_spmv_variant;  // 1 (default): sliced lane-per-fragment kernel with 16-bit in-slab indices; 0: tile + segmented-scan kernel;
+                           // 2: sub-warp-per-segment kernel on the canonical CSR / CSC image (gathers through L2)
+    i64 opt_rowwise_max_nnz;  // with variant 1: matrices with at most this many nnz use variant 2 instead
     i64 opt_cg_chunk;      // CG iterations enqueued between host checks (0 = adaptive)
     i64 opt_use_graph;     // capture the CG iteration chunk into a CUDA graph
     i64 opt_cg_fused;      // 1 (default): the P-side of a CG iteration (+ its all-reduce) is one kernel (bb_pside.cu)
@@ -158,7 +172,8 @@ struct SlabFmt {
     double* part;       // [nslab*n_seg (+ overflow slots + 1)] per-slab partial sums (output of the kernel)
     double* head_part;  // [ntiles]
     // ---- sliced format (spmv_variant 1, bb_sell.cu): fragments of <= SELL_LMAX nnz, one lane each ----
-    int   variant;            // 0: tile + segmented-scan kernel (k_seg_spmv); 1: sliced lane-per-fragment kernel (k_sell_spmv)
+    int   variant;            // 0: tile + segmented-scan kernel (k_seg_spmv); 1: sliced lane-per-fragment kernel (k_sell_spmv);
+                              // 2: sub-warp-per-segment kernel on the canonical arrays (k_csr_rowwise)
     int   nslices;            // slices of 32 fragments
     int   sl_lmax;            // fragment length cap chosen at build time (<= 256)
     unsigned* sl_off;         // [nslices+1] offset of a slice in index PAIRS per lane (slice length L = 2*(off[s+1]-off[s]))

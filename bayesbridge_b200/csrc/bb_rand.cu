@@ -111,12 +111,13 @@ __device__ double pg_draw(RandStream& rs, int shape, double tilt) {
 
 __global__ void k_pg_sample(i64 n, const int* __restrict__ shape, const double* __restrict__ shape_d,
                             const double* __restrict__ tilt, uint64_t seed, uint64_t offset, i64 index_offset,
-                            double* __restrict__ out) {
+                            double* __restrict__ out, int* __restrict__ bad_shape) {
     i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     RandStream rs;
     rs.init(seed, offset, (uint64_t)(index_offset + i), STREAM_PG);
     int b = shape ? shape[i] : (int)shape_d[i];
+    if (b < 0) { if (bad_shape) atomicOr(bad_shape, 1); out[i] = 0.0; return; }     // polya_gamma.pyx:55-61: validated here, not by a host loop
     out[i] = pg_draw(rs, b, tilt[i]);
 }
 
@@ -273,7 +274,6 @@ extern "C" int bb_pg_sample(bb_ctx* ctx, int64_t n, const int32_t* shape, const 
     BB_ARG(ctx && n >= 0, "ctx/n");
     if (n == 0) return BB_OK;
     BB_ARG(shape && tilt && out, "null pointer");
-    for (i64 i = 0; i < n; ++i) BB_ARG(shape[i] >= 0, "shape must be non-negative");
     BB_CUDA(cudaSetDevice(ctx->device));
     BBTimer timer_(ctx);
     cudaStream_t st = ctx->stream;
@@ -281,20 +281,25 @@ extern "C" int bb_pg_sample(bb_ctx* ctx, int64_t n, const int32_t* shape, const 
     BB_TRY(bb_ctx_scratch(ctx, 0, (size_t)n * sizeof(int), (void**)&d_shape));
     BB_TRY(bb_ctx_scratch(ctx, 1, (size_t)n * sizeof(double), (void**)&d_tilt));
     BB_TRY(bb_ctx_scratch(ctx, 2, (size_t)n * sizeof(double), (void**)&d_out));
-    int rc = BB_OK;
+    int* d_bad = nullptr;
+    BB_TRY(bb_ctx_scratch(ctx, 3, 64, (void**)&d_bad));
+    int rc = BB_OK, bad = 0;
     cudaError_t e;
-    e = cudaMemcpyAsync(d_shape, shape, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st);
+    e = cudaMemsetAsync(d_bad, 0, sizeof(int), st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_shape, shape, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_tilt, tilt, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) {
-        k_pg_sample<<<(int)((n + 127) / 128), 128, 0, st>>>(n, d_shape, nullptr, d_tilt, seed, offset, index_offset, d_out);
+        k_pg_sample<<<(int)((n + 127) / 128), 128, 0, st>>>(n, d_shape, nullptr, d_tilt, seed, offset, index_offset, d_out, d_bad);
         ctx->launches++;
         e = cudaPeekAtLastError();
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st);
     timer_.end();
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     timer_.commit();
     if (e != cudaSuccess) { bb_set_error("bb_pg_sample: %s", cudaGetErrorString(e)); rc = BB_ERR_CUDA; }
+    else if (bad) { bb_set_error("bb_pg_sample: invalid argument: shape must be non-negative"); rc = BB_ERR_ARG; }
     return rc;
 }
 

@@ -659,12 +659,10 @@ int bb_sell_build(bb_ctx* ctx, SlabFmt* f) {
     BB_CUDA(cudaMalloc((void**)&f->sl_pairs, (total_rows * 64 + 4) * sizeof(unsigned)));
     if (f->val) BB_CUDA(cudaMalloc((void**)&f->sl_vals, (total_rows * 128 + 4) * sizeof(double)));
     if (nslices > 0) {
-        static bool fill_attr = false;
+        static BBDeviceOnce fill_attr = {{0, 0, 0, 0}};
         const size_t fill_smem = sizeof(SellFillSmem) * SELL_FILL_WARPS;
-        if (!fill_attr) {
+        if (fill_attr.first(ctx->device))
             BB_CUDA(cudaFuncSetAttribute(k_sell_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fill_smem));
-            fill_attr = true;
-        }
         k_sell_fill<<<(nslices + SELL_FILL_WARPS - 1) / SELL_FILL_WARPS, SELL_FILL_WARPS * 32, fill_smem, st>>>(
             f->sl_slab_slice0, d_slab_frag0, nslab, nslices, sorted_id, frag_src, frag_len, frag_slot, f->idx, f->val, W,
             f->sl_off, trash_slot, (int)ctx->opt_bank_permute, f->sl_pairs, f->sl_vals);
@@ -718,12 +716,11 @@ int bb_sell_launch(bb_ctx* ctx, SlabFmt* f, const double* gvec, const int* done_
     if (f->nslices == 0) return BB_OK;        // no nnz: part stays zero
     const size_t smem = sell_smem_bytes(f);
     if (smem > ctx->smem_optin) { bb_set_error("sliced spmv: shared memory %zu exceeds %zu", smem, ctx->smem_optin); return BB_ERR_ARG; }
-    static bool attr_set = false;
-    if (!attr_set) {
+    static BBDeviceOnce attr_set = {{0, 0, 0, 0}};
+    if (attr_set.first(ctx->device)) {
         const int mx = (int)ctx->smem_optin;
         BB_CUDA(cudaFuncSetAttribute(k_sell_spmv<true, SELL_RING_BIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
         BB_CUDA(cudaFuncSetAttribute(k_sell_spmv<false, SELL_RING_VAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-        attr_set = true;
     }
     // TMA bulk staging needs a 16-byte aligned source (the window base is a multiple of W, W is a multiple of 32)
     const int use_bulk = (ctx->opt_spmv_bulk != 0 && (reinterpret_cast<uintptr_t>(gvec) & 15u) == 0 && (f->W & 1) == 0) ? 1 : 0;

@@ -598,6 +598,17 @@ static int build_slab_format(bb_ctx* ctx, const int* cptr, const int* cidx, cons
     memset(f, 0, sizeof(*f));
     f->staged = staged;
     cudaStream_t st = ctx->stream;
+    // sub-warp-per-segment kernel on the canonical image: forced by spmv_variant = 2, or picked for small, L2-resident
+    // problems (option rowwise_max_nnz: largest nnz it is used for; 0 = never)
+    if (ctx->opt_spmv_variant == 2 || (ctx->opt_spmv_variant == 1 && nnz <= ctx->opt_rowwise_max_nnz)) {
+        f->variant = 2;
+        f->nslab = 1; f->n_seg = n_seg; f->n_gather = n_gather; f->W = (int)(n_gather < ((i64)1 << 30) ? n_gather : ((i64)1 << 30)); f->nnz = nnz;
+        f->ptr = (int*)cptr; f->idx = (int*)cidx; f->val = (double*)cval;
+        f->owns_arrays = false;
+        BB_CUDA(cudaMalloc((void**)&f->part, (size_t)(n_seg > 0 ? n_seg : 1) * sizeof(double)));
+        BB_CUDA(cudaMemsetAsync(f->part, 0, (size_t)(n_seg > 0 ? n_seg : 1) * sizeof(double), st));
+        return BB_OK;
+    }
     // the sliced kernel (bb_sell.cu) always stages its window; the tile kernel also runs unstaged (one slab, gathers through L2)
     const bool sliced = staged && ctx->opt_spmv_variant == 1;
     i64 wmax = sliced ? bb_sell_max_width(ctx) : max_stage_width(ctx);
@@ -772,22 +783,70 @@ static int build_slab_format(bb_ctx* ctx, const int* cptr, const int* cidx, cons
     return BB_OK;
 }
 
+// ---- sub-warp-per-segment variant (spmv_variant 2) -----------------------------------------------------------------
+// For matrices whose index arrays and gather vector live in the 126 MB L2 (BASELINE configs 1 and 3) the persistent
+// staged kernels pay more for staging a window per CTA than for the product itself.  Here TPR lanes (2 ... 32, chosen
+// from the mean segment length) walk one row (dot, CSR) or column (Tdot, CSC) of the CANONICAL image, gathering through
+// L1/L2; the lanes' partial sums are added in a fixed shuffle tree.  One slab, no staging, no build cost.
+template <int TPR, bool BINARY>
+__global__ void __launch_bounds__(256)
+k_csr_rowwise(const int* __restrict__ ptr, const int* __restrict__ idx, const double* __restrict__ val, i64 n_seg,
+              const double* __restrict__ gvec, double* __restrict__ part, const int* __restrict__ done_flag) {
+    if (done_flag != nullptr && *done_flag) return;
+    const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    const i64 seg = t / TPR;
+    const int sub = (int)(t % TPR);
+    double acc = 0.0;
+    if (seg < n_seg) {
+        const int k1 = ptr[seg + 1];
+        for (int k = ptr[seg] + sub; k < k1; k += TPR) {
+            const double g = __ldg(gvec + idx[k]);
+            acc += BINARY ? g : val[k] * g;
+        }
+    }
+#pragma unroll
+    for (int o = TPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o, TPR);
+    if (sub == 0 && seg < n_seg) part[seg] = acc;
+}
+
+template <bool BINARY>
+static void launch_rowwise(const SlabFmt* f, const double* gvec, const int* done_flag, cudaStream_t st) {
+    const double mean_len = f->n_seg > 0 ? (double)f->nnz / (double)f->n_seg : 0.0;
+    int tpr = 2;
+    while (tpr < 32 && tpr * 4 < mean_len) tpr *= 2;            // ~4-8 nnz per lane
+    const i64 threads = f->n_seg * tpr;
+    const unsigned grid = (unsigned)((threads + 255) / 256);
+    switch (tpr) {
+    case 2: k_csr_rowwise<2, BINARY><<<grid, 256, 0, st>>>(f->ptr, f->idx, f->val, f->n_seg, gvec, f->part, done_flag); break;
+    case 4: k_csr_rowwise<4, BINARY><<<grid, 256, 0, st>>>(f->ptr, f->idx, f->val, f->n_seg, gvec, f->part, done_flag); break;
+    case 8: k_csr_rowwise<8, BINARY><<<grid, 256, 0, st>>>(f->ptr, f->idx, f->val, f->n_seg, gvec, f->part, done_flag); break;
+    case 16: k_csr_rowwise<16, BINARY><<<grid, 256, 0, st>>>(f->ptr, f->idx, f->val, f->n_seg, gvec, f->part, done_flag); break;
+    default: k_csr_rowwise<32, BINARY><<<grid, 256, 0, st>>>(f->ptr, f->idx, f->val, f->n_seg, gvec, f->part, done_flag); break;
+    }
+}
+
 // launch the SpMV + fix-up for one format; gvec has f->n_gather entries
 int bb_launch_spmv(bb_mat* m, SlabFmt* f, const double* gvec, const int* done_flag, bool skip_overflow_add) {
     bb_ctx* ctx = m->ctx;
     if (f->variant == 1) return bb_sell_launch(ctx, f, gvec, done_flag, skip_overflow_add);
+    if (f->variant == 2) {
+        if (f->n_seg == 0) return BB_OK;
+        if (f->val == nullptr) launch_rowwise<true>(f, gvec, done_flag, ctx->stream);
+        else launch_rowwise<false>(f, gvec, done_flag, ctx->stream);
+        BB_LAUNCHED(ctx);
+        return BB_OK;
+    }
     // a format built without staging in mind may have slabs wider than shared memory
     const bool stage = f->staged && (i64)f->W <= max_stage_width(ctx);
     int wstage = stage ? f->W : 0;
     size_t smem = (size_t)(wstage + SPMV_WARPS * (SPMV_TILE + 32)) * sizeof(double) + SPMV_WARPS * 8 * sizeof(unsigned);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static BBDeviceOnce attr_set = {{0, 0, 0, 0}};
+    if (attr_set.first(ctx->device)) {
         int mx = (int)ctx->smem_optin;
         BB_CUDA(cudaFuncSetAttribute(k_seg_spmv<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
         BB_CUDA(cudaFuncSetAttribute(k_seg_spmv<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
         BB_CUDA(cudaFuncSetAttribute(k_seg_spmv<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
         BB_CUDA(cudaFuncSetAttribute(k_seg_spmv<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-        attr_set = true;
     }
     if (smem > ctx->smem_optin) { bb_set_error("spmv shared memory %zu exceeds %zu", smem, ctx->smem_optin); return BB_ERR_ARG; }
     const bool binary = (f->val == nullptr);

@@ -46,10 +46,11 @@ def test_products_match_reference_outputs(ctx):
 
 @pytest.mark.parametrize('n,p,density', [(300, 40, 0.2), (20000, 700, 0.02), (60000, 3000, 0.004)])
 @pytest.mark.parametrize('binary', [False, True])
-@pytest.mark.parametrize('slab,stage,variant,permute', [(0, 1, 1, 2), (64, 1, 1, 2), (1024, 1, 1, 2), (0, 1, 1, 1), (1024, 1, 1, 0),
+@pytest.mark.parametrize('slab,stage,variant,permute', [(0, 1, 1, 2), (64, 1, 1, 2), (1024, 1, 1, 2), (0, 1, 1, 1), (1024, 1, 1, 0), (0, 1, 2, 2),
                                                         (0, 0, 0, 1), (0, 1, 0, 1), (64, 1, 0, 1), (1024, 1, 0, 1), (1024, 0, 0, 1)])
 def test_sparse_products_vs_oracle(ctx, n, p, density, binary, slab, stage, variant, permute):
-    """variant 1 = sliced lane-per-fragment kernel (bb_sell.cu, the default), 0 = tile + segmented-scan kernel;
+    """variant 1 = sliced lane-per-fragment kernel (bb_sell.cu, the default), 0 = tile + segmented-scan kernel,
+    2 = sub-warp-per-segment kernel on the canonical CSR / CSC image (small, L2-resident problems);
     permute = bank-aware entry order (2: most-loaded-bank-first matching, 1: greedy, 0: canonical order)."""
     Sparse, _ = _designs()
     default_permute = ctx.get_option('bank_permute')
