@@ -52,8 +52,13 @@ def import_reference():
 
 @pytest.fixture(scope='session')
 def ctx():
+    """The library's default context.  Problems below 2M nnz would by default take the small-problem SpMV variant
+    (sub-warp per segment, bb_sparse.cu); the parity tests are about the production kernels, so the switch is turned off
+    here and the small-problem variant is tested explicitly (spmv_variant = 2 cases, test_small_problem_variant_*)."""
     from bayesbridge_b200 import _lib
-    return _lib.Context.default()
+    c = _lib.Context.default()
+    c.set_option('rowwise_max_nnz', 0)
+    return c
 
 
 @pytest.fixture(autouse=True)

@@ -336,3 +336,26 @@ def test_cg_and_cholesky_draw_agree_on_a_config2_shaped_problem(ctx):
     err = relerr(coef, mean)
     record_achieved('cg_mean_vs_cholesky_mean', (n, p), err, 1e-8, n_iter=ni.value)
     assert info.value == 0 and err <= 1e-8
+
+
+def test_small_problem_variant_gives_the_same_draw(ctx):
+    """Default options on a config-1-sized problem pick the sub-warp-per-segment SpMV (k_csr_rowwise); the CG draw must
+    agree with the reference fixture exactly as the production kernels do."""
+    from bayesbridge_b200.design_matrix import GpuSparseDesignMatrix
+    from bayesbridge_b200.reg_coef_sampler import ConjugateGradientSampler
+    g = golden('cg_c1_ref.npz')
+    X = sp.csr_matrix((np.ones(len(g['indices'])), g['indices'], g['indptr']), shape=tuple(g['shape']))
+    ctx.set_option('rowwise_max_nnz', 1 << 21)
+    try:
+        D = GpuSparseDesignMatrix(X, center_predictor=True, add_intercept=True, ctx=ctx)
+    finally:
+        ctx.set_option('rowwise_max_nnz', 0)
+    P = D.shape[1]
+    omega, pps, z, x0, sd = (g[k] for k in ('omega', 'pps', 'z', 'x0', 'sd'))
+    k = 4                                                   # the tight rule
+    maxiter, atol_unit = g['rules'][k]
+    coef, info = ConjugateGradientSampler(1).sample(D, omega, pps, z, x0.copy(), 'prior', sd, maxiter=int(maxiter),
+                                                    atol=atol_unit * np.sqrt(P), seed=7)
+    err = relerr(coef, g['coef_%d' % k])
+    record_achieved('small_problem_variant_c1', 'tight', err, 1e-11, n_iter=info['n_iter'])
+    assert err <= 1e-11 and info['n_iter'] == int(g['niter_%d' % k])

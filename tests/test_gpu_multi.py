@@ -29,7 +29,9 @@ def _n_gpus():
 def _run(port, timeout, **env):
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
            '--master-addr', '127.0.0.1', '--master-port', str(port), os.path.join(ROOT, 'scripts', 'multi_gpu_check.py')]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT, env=dict(os.environ, **env))
+    # the small-problem SpMV variant is switched off so that the production kernels run on the check's small matrices
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT,
+                         env=dict(os.environ, BB_OPT_ROWWISE_MAX_NNZ='0', **env))
     print(out.stdout[-4000:])
     assert 'MULTI_GPU_CHECK PASS' in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
 
