@@ -209,13 +209,22 @@ def reference_run(workload, steps, warmup, sample_blocks=None, init_state=None, 
         model = ref.RegressionModel(y, X, family='linear' if (is_dense(workload) and workload not in N_CHAINS) else 'logit')
         bridge = ref.BayesBridge(model, ref.RegressionCoefPrior(bridge_exponent=.5))
         kw = dict(n_burnin=0, coef_sampler_type=sampler, seed=0, params_to_save=('global_scale',))
+        linear = is_dense(workload) and workload not in N_CHAINS
         if init_state is not None:
-            kw['init'] = init_state
+            # the reference's initialize_obs_precision takes len() of a given obs_prec (bayesbridge.py:355-360), which a
+            # linear model's scalar precision does not have: let it recompute the precision from the coefficients
+            kw['init'] = {k: v for k, v in init_state.items() if not (linear and k == 'obs_prec')}
         t0 = time.time()
         if warmup > 0:
             _, info = bridge.gibbs(n_iter=warmup, **kw)
             t1 = time.time()
-            _, info2 = bridge.gibbs_resume(info, steps)
+            if linear:
+                # ... and for the same reason its gibbs_resume fails for the linear model: restart from the reached state
+                st = info['_markov_chain_state']
+                kw2 = dict(kw, init={k: st[k] for k in ('coef', 'local_scale', 'global_scale')})
+                _, info2 = bridge.gibbs(n_iter=steps, **kw2)
+            else:
+                _, info2 = bridge.gibbs_resume(info, steps)
             dt = time.time() - t1
         else:
             _, info2 = bridge.gibbs(n_iter=steps, **kw)
