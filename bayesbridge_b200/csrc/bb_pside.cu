@@ -104,6 +104,12 @@ k_cg_pside(const PsideArgs a) {
         N = pv.nranks; me = pv.rank; peer = pv.peer_base; pst = pv.st; cap = pv.cap;
         Cw = (((L + N - 1) / N) + 1) & ~(i64)1;
         want = pst->seq2 + 1ull;
+        // an earlier exchange of this solve timed out (a rank is gone): stop the solve at once instead of spinning through
+        // every remaining iteration; the host raises as soon as the call returns (check_exchange_health)
+        if (pst->error != 0u) {
+            if (lead) st->done = 2;
+            return;
+        }
     }
     const i64 inbox_off = 32 + 2 * cap, result_off = 32 + 3 * cap;
 

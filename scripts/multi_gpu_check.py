@@ -105,6 +105,16 @@ check(f'batched cg (n_iter {ns}/{nu}) sharded vs unsharded', rel(cs, cu), 1e-8)
 t = torch.from_numpy(cs.copy()).to(tdev); t0 = t.clone(); dist.broadcast(t0, 0)
 check('batched cg replicas identical', float((t - t0).abs().max()), 0.0)
 
+# log-likelihood and gradient on the device (chain initialisation): sums over the shards
+y_ll = rs.binomial(1, 0.3, n).astype(float)
+beta_ll = np.random.default_rng(3).standard_normal(p + 1) * 0.1
+m_s = bb.RegressionModel(y_ll, X, family='logit', ctx=ctx)
+m_u = bb.RegressionModel(y_ll, X, family='logit', ctx=solo)
+ll_s, g_s = m_s.compute_loglik_and_gradient(beta_ll)
+ll_u, g_u = m_u.compute_loglik_and_gradient(beta_ll)
+check('loglik sharded vs unsharded', abs(ll_s - ll_u) / abs(ll_u), 1e-12)
+check('gradient sharded vs unsharded', rel(g_s, g_u), 1e-12)
+
 # full chain, sharded vs unsharded, device RNG: identical streams => same chain up to CG tolerance
 y = rs.binomial(1, 1 / (1 + np.exp(-(X @ np.concatenate((np.full(5, 1.5), np.zeros(p - 5))) - 1.0))))
 chains = []

@@ -149,6 +149,75 @@ def test_sharded_operator_algebra_gloo_world2():
     assert all(err < 1e-13 for _, err in res)
 
 
+def _twoshot_worker(rank, world, port, q):
+    """The protocol of the fused P-side kernel's exchange (csrc/bb_pside.cu), with gloo point-to-point messages in place of
+    NVLink stores: phase A pushes chunk c of the local vector into rank c's inbox slot, phase B adds the slots of the own
+    chunk in RANK ORDER and pushes the sum to everybody.  Also the sharded local-scale gather (pieces summed against zeros)."""
+    import torch
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'], os.environ['MASTER_PORT'] = '127.0.0.1', str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    L = 1003                                              # p + 1, not a multiple of the number of ranks
+    Cw = (((L + world - 1) // world) + 1) & ~1            # chunk width of bb_pside.cu
+    vecs = [np.random.default_rng(100 + r).standard_normal(L) * 10.0 ** np.random.default_rng(r).integers(-8, 8, L) for r in range(world)]
+    mine = vecs[rank]
+    inbox = np.zeros((world, Cw))
+    reqs = []
+    for c in range(world):                                # phase A
+        lo = c * Cw
+        chunk = np.zeros(Cw)
+        seg = mine[lo:min(lo + Cw, L)]
+        chunk[:len(seg)] = seg
+        if c == rank:
+            inbox[rank] = chunk
+        else:
+            reqs.append(dist.isend(torch.from_numpy(chunk.copy()), dst=c, tag=rank))
+    for sdr in range(world):
+        if sdr != rank:
+            buf = torch.zeros(Cw, dtype=torch.float64)
+            dist.recv(buf, src=sdr, tag=sdr)
+            inbox[sdr] = buf.numpy()
+    for r_ in reqs:
+        r_.wait()
+    acc = np.zeros(Cw)
+    for sdr in range(world):                              # phase B: rank order
+        acc = acc + inbox[sdr]
+    gathered = [torch.zeros(Cw, dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(gathered, torch.from_numpy(acc))
+    result = np.concatenate([g.numpy() for g in gathered])[:L]
+    expect = np.zeros(L)
+    for r in range(world):
+        expect = expect + vecs[r]                          # the same rank-ordered sum, computed locally
+    # sharded local-scale draw: every rank fills its own slice, zeros elsewhere, then a sum (exact: x + 0 == x)
+    ns = 777
+    lam = np.random.default_rng(5).random(ns)
+    lo, hi = ns * rank // world, ns * (rank + 1) // world
+    piece = np.zeros(ns)
+    piece[lo:hi] = lam[lo:hi]
+    t = torch.from_numpy(piece)
+    dist.all_reduce(t)
+    q.put((rank, bool(np.array_equal(result, expect)), bool(np.array_equal(t.numpy(), lam)), result.tobytes()))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_two_shot_exchange_protocol_gloo(world):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() + 7 * world) % 2000
+    procs = [ctx.Process(target=_twoshot_worker, args=(r, world, port, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for pr in procs:
+        pr.join(timeout=60)
+    assert sorted(r[0] for r in res) == list(range(world))
+    assert all(r[1] for r in res), 'the exchanged sum is the rank-ordered sum, bit for bit'
+    assert all(r[2] for r in res), 'pieces summed against zeros reproduce the vector exactly'
+    assert len({r[3] for r in res}) == 1, 'every rank holds identical bits'
+
+
 def test_bench_generator_is_block_deterministic():
     """bench.py builds C4 from 50 seeded row blocks so that every N sees the same matrix: a rank's rows must not
     depend on which other blocks the process generated."""
