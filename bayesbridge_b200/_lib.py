@@ -61,6 +61,7 @@ SIGNATURES = {
     'bb_cg_sample_batched': (c_int, [c_void_p, P_dbl, P_dbl, P_dbl, P_dbl, P_dbl, c_dbl, c_int, c_int, P_dbl, P_dbl,
                                      ctypes.POINTER(c_u64), ctypes.POINTER(c_u64), P_dbl, P_int, P_int]),
     'bb_pg_from_coef_batched': (c_int, [c_void_p, P_dbl, ctypes.POINTER(c_u64), ctypes.POINTER(c_u64), P_dbl]),
+    'bb_mode_search': (c_int, [c_void_p, P_dbl, P_dbl, P_dbl, c_dbl, c_int, c_dbl, c_dbl, c_int, P_dbl, P_int, P_int, P_int]),
     'bb_loglik_and_gradient': (c_int, [c_void_p, P_dbl, c_dbl, c_int, P_dbl, P_dbl]),
     'bb_cholesky_sample': (c_int, [c_void_p, P_dbl, P_dbl, P_dbl, P_dbl, P_dbl, P_dbl]),
     'bb_set_outcome': (c_int, [c_void_p, P_dbl, P_dbl]),

@@ -206,6 +206,7 @@ class BayesBridge():
             self.reg_coef_sampler = SparseRegressionCoefficientSampler(
                 self.n_pred, self.prior_sd_for_unshrunk, options.coef_sampler_type,
                 options.curvature_est_stabilized, self.prior.slab_size)
+            self.reg_coef_sampler.init_optimizer = options.init_optimizer
         if params_to_save == 'all':
             params_to_save = ('coef', 'local_scale', 'global_scale', 'logp', 'obs_prec')
         n_status_update = min(n_iter, n_status_update)

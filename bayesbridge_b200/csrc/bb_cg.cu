@@ -235,7 +235,7 @@ static int cg_iteration_fused(bb_mat* m) {
     }
     BB_TRY(bb_op_dot_flag(m, 1, done));
     if (precollect) BB_TRY(bb_op_tdot_local(m, m->w_n, done));
-    else if (m->is_sparse) BB_TRY(bb_launch_spmv(m, &m->ftdot, m->w_n, done, /*skip_overflow_add=*/true));
+    else if (m->is_sparse) BB_TRY(bb_launch_spmv(m, &m->ftdot, m->w_n, done, /*skip_overflow_add=*/bb_pside_folds_overflow(m)));
     else BB_TRY(bb_dense_tdot(m, m->w_n, done));
     return bb_pside_enqueue(m);
 }

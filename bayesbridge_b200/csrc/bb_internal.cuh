@@ -272,6 +272,7 @@ int bb_sell_launch(bb_ctx* ctx, SlabFmt* f, const double* gvec, const int* done_
 bool bb_pside_available(bb_mat* m);
 int bb_pside_prepare(bb_mat* m);     // outside graph capture: uploads the exchange view
 int bb_pside_enqueue(bb_mat* m);
+bool bb_pside_folds_overflow(bb_mat* m);   // true: the fused kernel adds the overflow fragments (few long columns)
 bool bb_pside_precollect(bb_mat* m);   // true: the caller launches the overflow fold + k_tdot_collect before the fused kernel
 int bb_dense_fused(bb_mat* m, const int* done_flag);   // one pass over X: omega.(X sv + shift) and its X' product
 void bb_sell_free(SlabFmt* f);

@@ -258,6 +258,7 @@ k_cg_pside(const PsideArgs a) {
 }
 
 // ---- host side ---------------------------------------------------------------------------------
+bool bb_pside_precollect(bb_mat* m);
 int bb_pside_grid(bb_ctx* ctx, i64 P) {
     i64 g = (ctx->opt_pside_ctas > 0) ? ctx->opt_pside_ctas : (P + 1023) / 1024;
     i64 cap = PS_MAX_CTAS;
@@ -276,6 +277,15 @@ bool bb_pside_available(bb_mat* m) {
     if (ctx->nranks == 1) return true;
     P2PView v;
     return ctx->nranks <= PS_MAX_RANKS && bb_p2p_view2(ctx, m->p + 1, &v);
+}
+
+// The fused kernel folds the overflow fragments of long columns itself (one warp per column) only while there are few
+// of them; a matrix with many long columns (BASELINE config 3: columns of up to 5e4 nnz) keeps the wide k_sell_ovf_add launch.
+bool bb_pside_folds_overflow(bb_mat* m) {
+    if (!m->is_sparse || m->ftdot.variant != 1 || m->ftdot.n_ovf_pieces == 0) return false;
+    if (bb_pside_precollect(m)) return false;
+    const i64 warps = (i64)bb_pside_grid(m->ctx, m->P) * (PS_THREADS / 32);
+    return (i64)m->ftdot.n_ovf_pieces <= 4 * warps;
 }
 
 bool bb_pside_precollect(bb_mat* m) {
@@ -307,7 +317,7 @@ int bb_pside_enqueue(bb_mat* m) {
     if (m->is_sparse) {
         SlabFmt* f = &m->ftdot;
         a.part = f->part; a.nslab = f->nslab;
-        if (f->variant == 1 && f->n_ovf_pieces > 0) {
+        if (bb_pside_folds_overflow(m)) {
             a.ovf_piece = f->ovf_piece; a.ovf_first = f->ovf_first; a.n_ovf = f->n_ovf_pieces; a.V = (i64)f->nslab * f->n_seg;
         }
     } else {

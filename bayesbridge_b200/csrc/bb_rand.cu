@@ -543,6 +543,24 @@ __global__ void k_loglik_resid(i64 n, const double* __restrict__ n_trial, const 
     if (threadIdx.x == 0) red[blockIdx.x] = acc;
 }
 
+// device-resident form used by the mode search (bb_lbfgs.cu): coef in m->v_P; ll_dev[0] = sum of the likelihood terms
+// (logit) or of the squared residuals (linear), summed over the shards; grad_dev = X' residual (P entries)
+int bb_loglik_resid_dev(bb_mat* m, const double* coef_dev, double obs_prec, double* ll_dev, double* grad_dev) {
+    bb_ctx* ctx = m->ctx;
+    cudaStream_t st = ctx->stream;
+    BB_TRY(bb_op_prepare(m, coef_dev, nullptr));
+    BB_TRY(bb_op_dot(m, 0));
+    const int g = N_grid(m->n);
+    k_loglik_resid<<<g, 256, 0, st>>>(m->n, m->n_trial, m->n_success, m->is_linear, obs_prec, m->u_n, m->w_n, m->red + RED_LL * RED_MAX);
+    ctx->launches++;
+    k_finish_scalar<<<1, 32, 0, st>>>(m->red + RED_LL * RED_MAX, g, ll_dev);
+    ctx->launches++;
+    BB_TRY(bb_allreduce_dev(ctx, ll_dev, 1));
+    BB_TRY(bb_op_tdot(m, m->w_n));
+    BB_TRY(bb_op_tdot_finish(m, grad_dev));
+    return BB_OK;
+}
+
 extern "C" int bb_loglik_and_gradient(bb_mat* m, const double* coef, double obs_prec, int loglik_only,
                                       double* loglik, double* grad) {
     BB_ARG(m && coef && loglik && (loglik_only || grad), "mat/coef/loglik/grad");

@@ -9,17 +9,22 @@ import numpy as np
 class SamplerOptions():
 
     def __init__(self, coef_sampler_type, global_scale_update='sample',
-                 hmc_curvature_est_stabilized=False, noise='device'):
+                 hmc_curvature_est_stabilized=False, noise='device', init_optimizer='device'):
         """
         coef_sampler_type : 'cg' (the device path, default) or 'cholesky' (direct draw on the device); 'hmc' is rejected
         global_scale_update : 'sample' | 'optimize' | None
         noise : 'device' -- CG right-hand-side noise from on-device Philox streams (default);
                 'host'   -- drawn from np.random exactly like the reference and injected (parity mode)
+        init_optimizer : 'device' -- the L-BFGS mode search of the chain initialisation inside libbbgpu (default);
+                         'scipy'  -- scipy's L-BFGS-B on the host, as the reference (reg_coef_sampler.py:296-305)
         """
         if coef_sampler_type not in ('cholesky', 'cg', 'hmc'):
             raise ValueError("Unsupported regression coefficient sampler.")
         if noise not in ('device', 'host'):
             raise ValueError("noise must be 'device' or 'host'.")
+        if init_optimizer not in ('device', 'scipy'):
+            raise ValueError("init_optimizer must be 'device' or 'scipy'.")
+        self.init_optimizer = init_optimizer
         self.coef_sampler_type = coef_sampler_type
         self.gscale_update = global_scale_update
         self.curvature_est_stabilized = hmc_curvature_est_stabilized
@@ -31,6 +36,7 @@ class SamplerOptions():
             'global_scale_update': self.gscale_update,
             'hmc_curvature_est_stabilized': self.curvature_est_stabilized,
             'noise': self.noise,
+            'init_optimizer': self.init_optimizer,
         }
 
     @staticmethod

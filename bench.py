@@ -267,7 +267,7 @@ def kernel_version():
     """Identifies the source of the roofline kernels (a DRAM-traffic capture is only quoted for the version it was taken on)."""
     import hashlib
     h = hashlib.sha1()
-    for f in ('bb_sell.cu', 'bb_dense.cu'):
+    for f in ('bb_sell.cu', 'bb_dense.cu', 'bb_batch.cu'):
         h.update(open(os.path.join(ROOT, 'bayesbridge_b200', 'csrc', f), 'rb').read())
     return h.hexdigest()[:12]
 

@@ -204,6 +204,15 @@ int  bb_cg_sample_batched(bb_mat* mat, const double* omega, const double* prior_
  * coef: [C][P] or NULL for the coefficients of the last batched draw; the precisions stay resident for the next draw */
 int  bb_pg_from_coef_batched(bb_mat* mat, const double* coef, const uint64_t* seeds, const uint64_t* offsets, double* loglik);
 
+/* The mode search that initialises a chain (reg_coef_sampler/reg_coef_sampler.py:281-358: scipy L-BFGS-B without bounds,
+ * maxcor 200, gtol 1e-6/sqrt(P), maxiter 250) run entirely on the device: minimises
+ *   F(theta) = -loglik(scale . theta) + 1/2 sum prior_prec theta^2,  theta = coef / scale,
+ * by L-BFGS (two-loop recursion in one kernel per iteration, strong-Wolfe line search), same stopping rules.
+ * status: 0 gradient tolerance met, 1 relative decrease <= ftol, 2 maxiter reached, 3 line search failed. */
+int  bb_mode_search(bb_mat* mat, const double* coef0, const double* scale, const double* prior_prec, double obs_prec,
+                    int maxiter, double gtol, double ftol, int maxcor, double* coef_out,
+                    int* n_iter, int* n_eval, int* status);
+
 /* ---- timing ----------------------------------------------------------------------------- */
 /* runs `reps` launches of one kernel class on resident data and returns mean device ms:
  * what = "dot" | "tdot" | "op" (one application of X' Omega X v, two products) | "spmv_dot" | "spmv_tdot" (the sparse

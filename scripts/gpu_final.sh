@@ -9,6 +9,7 @@ BENCH_NCU_RANGE=1 BENCH_VALUED=0 timeout 600 ncu --profile-from-start off --metr
 BENCH_NCU_RANGE=1 BENCH_VALUED=0 timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv \
     --log-file gpurun_out/f_launches_shard8.csv python bench.py --workload C4shard8 --steps 2 --warmup 2 --no-cpu-baseline --clocks none > gpurun_out/f_launch_shard8.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_sell_spmv -s 4 -c 2 -o gpurun_out/f_sell_c4 -f python scripts/prof_spmv.py big > gpurun_out/f_ncu_sell.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_sell_spmv -s 4 -c 2 -o gpurun_out/f_sell_shard8 -f python scripts/prof_spmv.py shard8 > gpurun_out/f_ncu_sell8.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_dense_stream -s 8 -c 1 -o gpurun_out/f_dense_c2 -f python scripts/prof_dense.py stream > gpurun_out/f_ncu_dense.log 2>&1
 timeout 600 ncu --set full --clock-control none -k regex:k_fisher_syrk -c 1 -o gpurun_out/f_fisher_c2 -f python scripts/prof_dense.py fisher > gpurun_out/f_ncu_fisher.log 2>&1
 timeout 600 ncu --set full --clock-control none -k regex:k_batch_ -s 4 -c 2 -o gpurun_out/f_batch_c5 -f python scripts/prof_dense.py batch > gpurun_out/f_ncu_batch.log 2>&1

@@ -7,7 +7,7 @@ import bench
 from bayesbridge_b200 import _lib
 from bayesbridge_b200.design_matrix import GpuSparseDesignMatrix
 ctx = _lib.Context.default()
-wl = 'C4' if (len(sys.argv) > 1 and sys.argv[1] == 'big') else 'C3'
+wl = {"big": "C4", "shard8": "C4shard8"}.get(sys.argv[1] if len(sys.argv) > 1 else "", "C3")
 valued = len(sys.argv) > 2 and sys.argv[2] == 'valued'
 n, p, dens = bench.WORKLOADS[wl]
 X, y = bench.generate_rows(range(bench.N_BLOCKS), n, p, dens)

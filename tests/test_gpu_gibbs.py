@@ -41,7 +41,8 @@ def _compat_bridge(family, ctx):
 def test_compat_chain_reproduces_reference(ctx, family):
     bridge, g = _compat_bridge(family, ctx)
     samples, info = bridge.gibbs(10, 0, init={'global_scale': 0.1, 'local_scale': np.ones(50)},
-                                 coef_sampler_type='cg', seed=0, params_to_save='all', options={'noise': 'host'})
+                                 coef_sampler_type='cg', seed=0, params_to_save='all',
+                                 options={'noise': 'host', 'init_optimizer': 'scipy'})
     saved = np.load(os.path.join(GOLDEN, 'ref_saved', family + '_cg_samples.npy'))
     assert np.allclose(samples['coef'][:, -1], saved, rtol=.001, atol=10e-6)       # reference's own criterion
     # every sample vs the reference chain; the cupy-parity test of the reference uses atol 1e-5
@@ -65,13 +66,15 @@ def test_compat_cholesky_chain_reproduces_reference(ctx):
         b = bb.BayesBridge(bb.RegressionModel(outcome, X, 'logit', ctx=ctx), prior)
         b.rg.pg, b.rg.ts = PolyaGammaPort(), TiltedStablePort()
         return b
-    samples, info = bridge().gibbs(10, 0, init=init, coef_sampler_type='cholesky', seed=0, params_to_save='all')
+    samples, info = bridge().gibbs(10, 0, init=init, coef_sampler_type='cholesky', seed=0, params_to_save='all',
+                                   options={'init_optimizer': 'scipy'})
     assert info['coef_sampler_type'] == 'cholesky'
     saved = np.load(os.path.join(GOLDEN, 'ref_saved', 'logit_cholesky_samples.npy'))
     assert np.allclose(samples['coef'][:, -1], saved, rtol=.001, atol=10e-6)       # the reference's own criterion
     assert np.allclose(samples['coef'], g['logitchol_coef'], rtol=0, atol=1e-8)    # the reference chain run here
     assert np.allclose(samples['global_scale'], g['logitchol_gscale'], rtol=1e-9)
-    s1, i1 = bridge().gibbs(5, 0, init=init, coef_sampler_type='cholesky', seed=0, params_to_save='all')
+    s1, i1 = bridge().gibbs(5, 0, init=init, coef_sampler_type='cholesky', seed=0, params_to_save='all',
+                            options={'init_optimizer': 'scipy'})
     s2, _ = bridge().gibbs_resume(i1, 5, merge=True, prev_samples=s1)
     assert np.allclose(s2['coef'], g['logitchol_coef'], rtol=0, atol=1e-8)
 
@@ -79,7 +82,8 @@ def test_compat_cholesky_chain_reproduces_reference(ctx):
 def test_compat_chain_resume_equals_uninterrupted(ctx):
     bridge, g = _compat_bridge('logit', ctx)
     init = {'global_scale': 0.1, 'local_scale': np.ones(50)}
-    s1, i1 = bridge.gibbs(5, 0, init=init, coef_sampler_type='cg', seed=0, params_to_save='all', options={'noise': 'host'})
+    s1, i1 = bridge.gibbs(5, 0, init=init, coef_sampler_type='cg', seed=0, params_to_save='all',
+                          options={'noise': 'host', 'init_optimizer': 'scipy'})
     bridge2, _ = _compat_bridge('logit', ctx)
     s2, i2 = bridge2.gibbs_resume(i1, 5, merge=True, prev_samples=s1)
     assert s2['coef'].shape == (51, 10) and i2['n_iter'] == 10
@@ -218,3 +222,44 @@ def test_resident_state_linear_model(ctx, monkeypatch):
     assert np.array_equal(out['1']['coef'][:, 0], out['0']['coef'][:, 0])
     assert np.allclose(out['1']['coef'][:, 1], out['0']['coef'][:, 1], atol=1e-6)
     assert out['1']['obs_prec'][0] == pytest.approx(out['0']['obs_prec'][0], rel=1e-12)
+
+
+@pytest.mark.parametrize('family', ['logit', 'linear'])
+def test_device_mode_search_finds_the_optimum_scipy_finds(ctx, family):
+    """Chain initialisation (reg_coef_sampler.py:281-358): the L-BFGS search inside libbbgpu (bb_mode_search) and scipy's
+    L-BFGS-B driven through the same device likelihood reach the same conditional posterior mode."""
+    bb = _bb()
+    from bayesbridge_b200.reg_coef_sampler import SparseRegressionCoefficientSampler
+    rs = np.random.RandomState(4)
+    n, p = 20000, 600
+    X = sp.random(n, p, density=0.02, format='csr', random_state=rs, dtype=np.float64)
+    X.data[:] = 1.0
+    beta = np.zeros(p); beta[:8] = 1.2
+    eta = X @ beta - 0.7
+    if family == 'logit':
+        outcome, obs_prec = rs.binomial(1, 1 / (1 + np.exp(-eta))), None
+    else:
+        outcome, obs_prec = eta + rs.randn(n), 0.8
+    model = bb.RegressionModel(outcome, X, family=family, ctx=ctx)
+    P = model.n_pred
+    lscale, gscale = np.exp(rs.randn(P - 1)), 0.05
+    found = {}
+    for opt in ('scipy', 'device'):
+        S = SparseRegressionCoefficientSampler(P, np.array([float('inf')]), 'cg')
+        S.init_optimizer = opt
+        coef0 = np.zeros(P); coef0[0] = model.calc_intercept_mle()
+        coef, info = S.search_mode(coef0, lscale, gscale, obs_prec, model)
+        assert info['is_success'], (opt, info)
+        scale, prior_prec = S.compute_preconditioning_scale(gscale, lscale, np.ones(P), S.prior_sd_for_unshrunk)
+        args = (obs_prec,) if family == 'linear' else ()
+        ll, grad = model.compute_loglik_and_gradient(coef, *args)
+        theta = coef / scale
+        F = -ll + 0.5 * np.sum(prior_prec * theta ** 2)
+        gmax = np.abs(-scale * grad + prior_prec * theta).max()
+        found[opt] = (coef, F, gmax, info)
+    (c_s, F_s, g_s, i_s), (c_d, F_d, g_d, i_d) = found['scipy'], found['device']
+    gtol = 1e-6 / np.sqrt(P)
+    assert g_d <= 20 * gtol or i_d['n_iter'] > 0 and abs(F_d - F_s) <= 1e-9 * abs(F_s), (g_d, gtol)
+    assert F_d <= F_s + 1e-9 * abs(F_s), (F_d, F_s)
+    assert np.linalg.norm(c_d - c_s) <= 1e-4 * np.linalg.norm(c_s), np.linalg.norm(c_d - c_s) / np.linalg.norm(c_s)
+    print('mode search: scipy', i_s['n_iter'], 'iterations, device', i_d['n_iter'], 'iterations; |grad|_inf', g_s, g_d)
