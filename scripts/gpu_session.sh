@@ -1,7 +1,8 @@
 #!/bin/bash
-# Round-2 GPU session (8 GPUs): bench N=8, fused two-shot vs unfused NCCL; C5 on 8 GPUs
+# Round-2 GPU session 12: device L-BFGS mode search, C3 overflow fix, batched test
 mkdir -p gpurun_out
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29611 bench.py --gpus 8 --steps 20 --warmup 5 > gpurun_out/s12_bench_n8.log 2>&1
-BB_OPT_CG_FUSED=0 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29612 bench.py --gpus 8 --steps 20 --warmup 5 > gpurun_out/s12_bench_n8_unfused.log 2>&1
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29613 bench.py --gpus 8 --workload C5 --steps 5 --warmup 3 > gpurun_out/s12_bench_c5_n8.log 2>&1
-for f in s12_bench_n8 s12_bench_n8_unfused s12_bench_c5_n8; do grep '^{' gpurun_out/$f.log | tail -1 | cut -c1-400; tail -3 gpurun_out/$f.log | cut -c1-300; done
+timeout 900 python -m pytest tests/test_gpu_gibbs.py tests/test_gpu_batched.py -q -x > gpurun_out/s14_pytest.log 2>&1; echo "rc=$?" >> gpurun_out/s14_pytest.log
+timeout 600 python bench.py --workload C3 --steps 50 --warmup 10 --no-cpu-baseline > gpurun_out/s14_bench_c3.log 2>&1
+timeout 600 python scripts/prof_init.py C4 > gpurun_out/s14_prof_init.log 2>&1
+timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/s14_bench_c4.log 2>&1
+tail -25 gpurun_out/s14_pytest.log; grep '^{' gpurun_out/s14_bench_c3.log | tail -1 | cut -c1-200; head -12 gpurun_out/s14_prof_init.log; grep '^{' gpurun_out/s14_bench_c4.log | tail -1 | cut -c1-200
