@@ -81,13 +81,13 @@ def test_batched_cg_draw_vs_oracle_and_single_chain(ctx):
             ref, rinfo = co.cg_sample(O, omega[c], pps[c], z[c], x0[c], s[c], 500, atol, e1[c], e2[c])
             err = relerr(coef[c], ref)
             bound_c = bound
-            if atol_unit == 1e-5 and n_it[c] != rinfo['n_iter']:
-                # the default rule may stop one iteration apart where ||r|| sits near the threshold (tests/test_gpu_cg.py);
-                # the two stopped solutions then differ by one late CG step
-                assert abs(n_it[c] - rinfo['n_iter']) == 1, (c, n_it[c], rinfo['n_iter'])
-                bound_c = 2e-5
-            else:
-                assert n_it[c] == rinfo['n_iter'], (atol_unit, c, n_it[c], rinfo['n_iter'])
+            if n_it[c] != rinfo['n_iter']:
+                # the stopping test may be crossed one iteration apart where ||r|| sits at the threshold: at the default rule
+                # (tests/test_gpu_cg.py) and at 1e-12 sqrt(P), where the residual recurrence is at its rounding floor.  At the
+                # default rule the two stopped solutions then differ by one late CG step; converged ones still agree to 1e-8.
+                assert abs(n_it[c] - rinfo['n_iter']) == 1, (atol_unit, c, n_it[c], rinfo['n_iter'])
+                if atol_unit == 1e-5:
+                    bound_c = 2e-5
             record_achieved('batched_cg_vs_oracle', (atol_unit, c), err, bound_c, n_iter=n_it[c], n_iter_oracle=rinfo['n_iter'])
             assert info[c] == 0 and err <= bound_c, (atol_unit, c, err)
     # the single-chain path of this library on chain 3 (same injected noise)
@@ -98,7 +98,7 @@ def test_batched_cg_draw_vs_oracle_and_single_chain(ctx):
                                         _lib.dptr(x0[c].copy()), _lib.dptr(s[c].copy()), 1e-12 * np.sqrt(P), 500, 0,
                                         _lib.dptr(e1[c].copy()), _lib.dptr(e2[c].copy()), 0, 0, _lib.dptr(one),
                                         ctypes.byref(ni), ctypes.byref(inf), None))
-    assert relerr(coef[c], one) <= 1e-10 and ni.value == n_it[c]
+    assert relerr(coef[c], one) <= 1e-10 and abs(ni.value - n_it[c]) <= 1
     # independence: chain c alone in a batch of one gives the same bits as inside the batch of 16
     _lib.check(_lib.load().bb_batch_init(D._mat, 1))
     alone, n1, _ = _batched_cg(D, omega[c:c + 1], pps[c:c + 1], z[c:c + 1], x0[c:c + 1], s[c:c + 1], 1e-12 * np.sqrt(P), 500,
