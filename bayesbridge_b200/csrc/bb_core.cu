@@ -47,6 +47,7 @@ extern "C" int bb_init(int device, bb_ctx** out) {
     c->opt_use_graph = 1;
     c->opt_cg_fused = 1;
     c->opt_pside_ctas = 0;
+    c->opt_pside_fold_ovf = -1;
     c->opt_dense_stream = 1;
     c->opt_allreduce_p2p = 1;
     c->opt_p2p_variant = 3;      // one system fence + relaxed flag stores, parallel flag polls (fastest measured at N=8)
@@ -95,6 +96,7 @@ static i64* option_slot(bb_ctx* c, const char* name) {
     if (!strcmp(name, "use_graph")) return &c->opt_use_graph;
     if (!strcmp(name, "cg_fused")) return &c->opt_cg_fused;
     if (!strcmp(name, "pside_ctas")) return &c->opt_pside_ctas;
+    if (!strcmp(name, "pside_fold_ovf")) return &c->opt_pside_fold_ovf;
     if (!strcmp(name, "pside_collect_max")) return &c->opt_pside_collect_max;
     if (!strcmp(name, "dense_stream")) return &c->opt_dense_stream;
     if (!strcmp(name, "allreduce_p2p")) return &c->opt_allreduce_p2p;

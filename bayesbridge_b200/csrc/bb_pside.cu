@@ -284,6 +284,8 @@ bool bb_pside_available(bb_mat* m) {
 bool bb_pside_folds_overflow(bb_mat* m) {
     if (!m->is_sparse || m->ftdot.variant != 1 || m->ftdot.n_ovf_pieces == 0) return false;
     if (bb_pside_precollect(m)) return false;
+    if (m->ctx->opt_pside_fold_ovf == 0) return false;
+    if (m->ctx->opt_pside_fold_ovf == 1) return true;
     const i64 warps = (i64)bb_pside_grid(m->ctx, m->P) * (PS_THREADS / 32);
     return (i64)m->ftdot.n_ovf_pieces <= 4 * warps;
 }

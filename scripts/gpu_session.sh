@@ -1,8 +1,10 @@
 #!/bin/bash
-# Round-2 GPU session 12: device L-BFGS mode search, C3 overflow fix, batched test
+# pside tuning on the N = 8 shard size (one GPU, no exchange) + batched test
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_gibbs.py tests/test_gpu_batched.py -q -x > gpurun_out/s14_pytest.log 2>&1; echo "rc=$?" >> gpurun_out/s14_pytest.log
-timeout 600 python bench.py --workload C3 --steps 50 --warmup 10 --no-cpu-baseline > gpurun_out/s14_bench_c3.log 2>&1
-timeout 600 python scripts/prof_init.py C4 > gpurun_out/s14_prof_init.log 2>&1
-timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/s14_bench_c4.log 2>&1
-tail -25 gpurun_out/s14_pytest.log; grep '^{' gpurun_out/s14_bench_c3.log | tail -1 | cut -c1-200; head -12 gpurun_out/s14_prof_init.log; grep '^{' gpurun_out/s14_bench_c4.log | tail -1 | cut -c1-200
+timeout 300 python -m pytest tests/test_gpu_batched.py -q > gpurun_out/s15_batched.log 2>&1; echo "rc=$?" >> gpurun_out/s15_batched.log
+for cfg in "0 -1" "64 -1" "32 -1" "16 -1" "0 0" "32 0"; do
+  set -- $cfg
+  BB_OPT_PSIDE_CTAS=$1 BB_OPT_PSIDE_FOLD_OVF=$2 BENCH_VALUED=0 timeout 300 python bench.py --workload C4shard8 --steps 30 --warmup 5 --no-cpu-baseline --clocks none > gpurun_out/s15_shard8_$1_$2.log 2>&1
+  echo "ctas=$1 fold=$2 $(grep '^{' gpurun_out/s15_shard8_$1_$2.log | tail -1 | python -c 'import sys,json; d=json.loads(sys.stdin.read()); print(d["ms_per_step"], d["value"], d["gpu_launches"])')"
+done
+tail -3 gpurun_out/s15_batched.log
