@@ -1,10 +1,7 @@
 #!/bin/bash
-# pside tuning on the N = 8 shard size (one GPU, no exchange) + batched test
+# full GPU suite + smoke with the final build
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_batched.py -q > gpurun_out/s15_batched.log 2>&1; echo "rc=$?" >> gpurun_out/s15_batched.log
-for cfg in "0 -1" "64 -1" "32 -1" "16 -1" "0 0" "32 0"; do
-  set -- $cfg
-  BB_OPT_PSIDE_CTAS=$1 BB_OPT_PSIDE_FOLD_OVF=$2 BENCH_VALUED=0 timeout 300 python bench.py --workload C4shard8 --steps 30 --warmup 5 --no-cpu-baseline --clocks none > gpurun_out/s15_shard8_$1_$2.log 2>&1
-  echo "ctas=$1 fold=$2 $(grep '^{' gpurun_out/s15_shard8_$1_$2.log | tail -1 | python -c 'import sys,json; d=json.loads(sys.stdin.read()); print(d["ms_per_step"], d["value"], d["gpu_launches"])')"
-done
-tail -3 gpurun_out/s15_batched.log
+rm -f gpurun_out/parity_achieved.jsonl
+timeout 2400 python -m pytest tests -m gpu -q -rs > gpurun_out/s16_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/s16_pytest.log
+timeout 300 python __graft_entry__.py smoke > gpurun_out/s16_smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/s16_smoke.log
+tail -6 gpurun_out/s16_pytest.log; tail -3 gpurun_out/s16_smoke.log
