@@ -67,6 +67,10 @@ extern "C" int bb_time_kernel(bb_mat* m, const char* what, int reps, int do_flus
     BB_CUDA(cudaEventCreate(&e0));
     BB_CUDA(cudaEventCreate(&e1));
     double total = 0.0;
+    // a kernel timed alone is launched WITHOUT programmatic dependent launch: its prologue must not slip in front of
+    // the start event (under the flush kernel), or the cold time would be flattered
+    struct PdlOff { bb_ctx* c; i64 saved; ~PdlOff() { c->opt_pdl = saved; } } pdl_off = {ctx, ctx->opt_pdl};
+    ctx->opt_pdl = 0;
     for (int r = -2; r < reps; ++r) {      // two untimed warm-ups
         if (do_flush) BB_TRY(flush_l2(ctx));
         BB_CUDA(cudaEventRecord(e0, st));

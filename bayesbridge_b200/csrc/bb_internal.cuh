@@ -96,6 +96,10 @@ struct bb_ctx {
     i64 opt_pside_fold_ovf;     // overflow fragments folded inside the fused kernel: -1 automatic (few of them), 0 never, 1 always
     i64 opt_pside_collect_max;  // slab partials per column the fused kernel sums itself (0 = default 8); above: k_tdot_collect
     i64 opt_dense_stream;  // 1 (default): dense products through the one-pass TMA streaming kernel when a row pair fits in shared memory
+    i64 opt_pdl;           // 1 (default): the kernels of a fused CG iteration are launched with programmatic dependent launch
+                           // (their launch and data-independent prologue overlap the tail of the previous kernel)
+    i64 opt_uniform_carveout;  // 1 (default 0: measured, no gain): every kernel of the CG iteration asks for the maximum shared-memory carve-out, so
+                               // that the SMs are never reconfigured (and drained) between the SpMV and the small kernels
     // communicator (NCCL via dlopen)
     void* nccl_handle;
     void* nccl_comm;
@@ -121,6 +125,39 @@ struct bb_ctx {
     double dev_ms;
     int timer_depth;
 };
+
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------
+// A kernel launched through bb_launch(..., pdl = true) may start while the previous kernel of the stream is still
+// running.  Rules every such kernel follows: (1) pdl_trigger() first (lets ITS successor be scheduled early);
+// (2) before pdl_wait() it touches only data no kernel ever writes during a solve (the matrix formats) and its own
+// shared memory; (3) pdl_wait() -- which returns once the previous kernel has completed and its writes are visible --
+// precedes every other access, including the `done` flag, and is executed on every path (so completion of a kernel
+// implies completion of all its predecessors).  Launched without the attribute both instructions are no-ops.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t bb_launch(bb_ctx* ctx, bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                    Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = ctx->stream;
+    cudaLaunchAttribute at[1];
+    if (pdl && ctx->opt_pdl != 0) {
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+    }
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+// every kernel of the CG iteration asks for the same (maximum) shared-memory carve-out: see opt_uniform_carveout
+template <typename K>
+static inline cudaError_t bb_prefer_max_smem(bb_ctx* ctx, K kernel) {
+    if (ctx->opt_uniform_carveout == 0) return cudaSuccess;
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+}
+#endif
 
 int bb_ctx_pinned(bb_ctx* ctx, size_t bytes, double** out);
 int bb_ctx_scratch(bb_ctx* ctx, int slot, size_t bytes, void** out);

@@ -81,6 +81,8 @@ __device__ __forceinline__ void ps_wait_flags(const unsigned long long* flags, i
 
 __global__ void __launch_bounds__(PS_THREADS)
 k_cg_pside(const PsideArgs a) {
+    pdl_trigger();
+    pdl_wait();           // everything this kernel reads was written by the kernels before it
     CgScalars* st = a.st;
     if (st->done) return;
     __shared__ double sm[33];
@@ -345,7 +347,9 @@ int bb_pside_enqueue(bb_mat* m) {
         if (m->p2p_view_valid == 0) { bb_set_error("fused CG iteration: bb_pside_prepare first"); return BB_ERR_STATE; }
         a.view = m->p2p_view_dev;
     }
-    k_cg_pside<<<bb_pside_grid(ctx, m->P), PS_THREADS, 0, ctx->stream>>>(a);
+    static BBDeviceOnce attr_set = {{0, 0, 0, 0}};
+    if (attr_set.first(ctx->device)) BB_CUDA(bb_prefer_max_smem(ctx, k_cg_pside));
+    BB_CUDA(bb_launch(ctx, true, k_cg_pside, dim3(bb_pside_grid(ctx, m->P)), dim3(PS_THREADS), 0, a));
     BB_LAUNCHED(ctx);
     return BB_OK;
 }

@@ -382,11 +382,12 @@ k_sell_spmv(const uint2* __restrict__ rows, const double* __restrict__ vals,
             const double* __restrict__ gvec, int W, i64 n_gather, int use_bulk,
             double* __restrict__ part, const int* __restrict__ done_flag)
 {
-    if (done_flag != nullptr && *done_flag) return;
+    // PDL (bb_internal.cuh): everything up to pdl_wait() reads only the matrix format and writes only shared memory
+    pdl_trigger();
     extern __shared__ __align__(128) double sell_smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int sec_lo = cta_sec0[blockIdx.x], sec_hi = cta_sec0[blockIdx.x + 1];
-    if (sec_lo >= sec_hi) return;
+    if (sec_lo >= sec_hi) { pdl_wait(); return; }
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(sell_smem);
     const unsigned mbar = sbase + (unsigned)(W + 2) * 8u;
     if (tid == 0) {
@@ -407,6 +408,21 @@ k_sell_spmv(const uint2* __restrict__ rows, const double* __restrict__ vals,
         // that the loads overlap the staging
         unsigned r = (unsigned)sec_wstart[sec * (SELL_WARPS + 1) + warp];
         const unsigned r_end = (unsigned)sec_wstart[sec * (SELL_WARPS + 1) + warp + 1];
+        // strip prologue: issue the first loads of the row stream (matrix format: independent of the previous kernel)
+        // before the window is requested, so that they overlap the tail of the previous kernel and the staging
+        SellWalk w;
+        w.a0 = 0.0; w.a1 = 0.0; w.rows_left = 0; w.slot = 0u;
+        SellRow<BINARY> bufA[R], bufB[R];
+        const uint2* rp = rows + (size_t)r * 32 + lane;
+        const double2* vp = reinterpret_cast<const double2*>(vals);
+        if constexpr (!BINARY) vp += ((size_t)r * 32 + lane) * 2;
+#pragma unroll
+        for (int k = 0; k < R; ++k)
+            if (r + k < r_end) sell_load_row<BINARY>(bufA[k], rp, vp, k);
+        if (sec == sec_lo) {
+            pdl_wait();                           // the gathered vector and the done flag come from the previous kernel
+            if (done_flag != nullptr && *done_flag) return;
+        }
         __syncthreads();                          // readers of the previous window are done; mbarrier init is visible
         if (use_bulk) {
             if (tid == 0) {
@@ -429,16 +445,6 @@ k_sell_spmv(const uint2* __restrict__ rows, const double* __restrict__ vals,
             }
             for (; i < wlen; i += SELL_THREADS) sell_smem[i] = src[i];
         }
-        // strip prologue: issue the first loads while the window is in flight
-        SellWalk w;
-        w.a0 = 0.0; w.a1 = 0.0; w.rows_left = 0; w.slot = 0u;
-        SellRow<BINARY> bufA[R], bufB[R];
-        const uint2* rp = rows + (size_t)r * 32 + lane;
-        const double2* vp = reinterpret_cast<const double2*>(vals);
-        if constexpr (!BINARY) vp += ((size_t)r * 32 + lane) * 2;
-#pragma unroll
-        for (int k = 0; k < R; ++k)
-            if (r + k < r_end) sell_load_row<BINARY>(bufA[k], rp, vp, k);
         if (use_bulk) {
             unsigned ok = 0;
             while (!ok) {
@@ -464,6 +470,8 @@ k_sell_spmv(const uint2* __restrict__ rows, const double* __restrict__ vals,
 // part[v] += overflow fragments of v, in fragment order (one warp per long virtual segment)
 __global__ void k_sell_ovf_add(const int* __restrict__ ovf_piece, const int* __restrict__ ovf_first, int n_pieces,
                                i64 V, double* __restrict__ part, const int* __restrict__ done_flag) {
+    pdl_trigger();
+    pdl_wait();
     if (done_flag != nullptr && *done_flag) return;
     const int i = (int)(((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (i >= n_pieces) return;
@@ -721,6 +729,9 @@ int bb_sell_launch(bb_ctx* ctx, SlabFmt* f, const double* gvec, const int* done_
         const int mx = (int)ctx->smem_optin;
         BB_CUDA(cudaFuncSetAttribute(k_sell_spmv<true, SELL_RING_BIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
         BB_CUDA(cudaFuncSetAttribute(k_sell_spmv<false, SELL_RING_VAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+        BB_CUDA(bb_prefer_max_smem(ctx, k_sell_spmv<true, SELL_RING_BIN>));
+        BB_CUDA(bb_prefer_max_smem(ctx, k_sell_spmv<false, SELL_RING_VAL>));
+        BB_CUDA(bb_prefer_max_smem(ctx, k_sell_ovf_add));
     }
     // TMA bulk staging needs a 16-byte aligned source (the window base is a multiple of W, W is a multiple of 32)
     const int use_bulk = (ctx->opt_spmv_bulk != 0 && (reinterpret_cast<uintptr_t>(gvec) & 15u) == 0 && (f->W & 1) == 0) ? 1 : 0;
@@ -729,15 +740,15 @@ int bb_sell_launch(bb_ctx* ctx, SlabFmt* f, const double* gvec, const int* done_
     const int* sec_wstart = sec_slab + f->sl_nsec;
     const uint2* rows = reinterpret_cast<const uint2*>(f->sl_pairs);
     if (f->sl_vals == nullptr)
-        k_sell_spmv<true, SELL_RING_BIN><<<f->sl_ncta, SELL_THREADS, smem, ctx->stream>>>(
-            rows, nullptr, cta_sec0, sec_slab, sec_wstart, gvec, f->W, f->n_gather, use_bulk, f->part, done_flag);
+        BB_CUDA(bb_launch(ctx, true, k_sell_spmv<true, SELL_RING_BIN>, dim3(f->sl_ncta), dim3(SELL_THREADS), smem,
+                          rows, nullptr, cta_sec0, sec_slab, sec_wstart, gvec, f->W, f->n_gather, use_bulk, f->part, done_flag));
     else
-        k_sell_spmv<false, SELL_RING_VAL><<<f->sl_ncta, SELL_THREADS, smem, ctx->stream>>>(
-            rows, f->sl_vals, cta_sec0, sec_slab, sec_wstart, gvec, f->W, f->n_gather, use_bulk, f->part, done_flag);
+        BB_CUDA(bb_launch(ctx, true, k_sell_spmv<false, SELL_RING_VAL>, dim3(f->sl_ncta), dim3(SELL_THREADS), smem,
+                          rows, f->sl_vals, cta_sec0, sec_slab, sec_wstart, gvec, f->W, f->n_gather, use_bulk, f->part, done_flag));
     BB_LAUNCHED(ctx);
     if (f->n_ovf_pieces > 0 && !skip_overflow_add) {
-        k_sell_ovf_add<<<(int)(((i64)f->n_ovf_pieces * 32 + 255) / 256), 256, 0, ctx->stream>>>(
-            f->ovf_piece, f->ovf_first, f->n_ovf_pieces, (i64)f->nslab * f->n_seg, f->part, done_flag);
+        BB_CUDA(bb_launch(ctx, true, k_sell_ovf_add, dim3((unsigned)(((i64)f->n_ovf_pieces * 32 + 255) / 256)), dim3(256), 0,
+                          f->ovf_piece, f->ovf_first, f->n_ovf_pieces, (i64)f->nslab * f->n_seg, f->part, done_flag));
         BB_LAUNCHED(ctx);
     }
     return BB_OK;

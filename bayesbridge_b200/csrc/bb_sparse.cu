@@ -430,6 +430,8 @@ __global__ void k_dot_finish(const double* __restrict__ part, int nslab, i64 n,
                              const double* __restrict__ omega, const double* __restrict__ omega_scalar,
                              double* __restrict__ out, double* __restrict__ u_out, double* __restrict__ red_w,
                              const int* __restrict__ done_flag) {
+    pdl_trigger();
+    pdl_wait();
     if (done_flag != nullptr && *done_flag) return;
     __shared__ double sm[33];
     const double shift = warp_sum_partials(red_shift, nshift);
@@ -470,6 +472,8 @@ __global__ void __launch_bounds__(256)
 k_tdot_collect(const double* __restrict__ part, int nslab, i64 p,
                const double* __restrict__ red_w, int nred, double* __restrict__ traw,
                const int* __restrict__ done_flag, const P2PView* __restrict__ pub_ptr) {
+    pdl_trigger();
+    pdl_wait();
     if (done_flag != nullptr && *done_flag) return;
     __shared__ double sm[8][33];
     P2PView pub;
@@ -792,14 +796,17 @@ template <int TPR, bool BINARY>
 __global__ void __launch_bounds__(256)
 k_csr_rowwise(const int* __restrict__ ptr, const int* __restrict__ idx, const double* __restrict__ val, i64 n_seg,
               const double* __restrict__ gvec, double* __restrict__ part, const int* __restrict__ done_flag) {
-    if (done_flag != nullptr && *done_flag) return;
+    pdl_trigger();
     const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     const i64 seg = t / TPR;
     const int sub = (int)(t % TPR);
+    int k0 = 0, k1 = 0;
+    if (seg < n_seg) { k0 = ptr[seg]; k1 = ptr[seg + 1]; }      // matrix format: readable before the previous kernel is done
+    pdl_wait();
+    if (done_flag != nullptr && *done_flag) return;
     double acc = 0.0;
     if (seg < n_seg) {
-        const int k1 = ptr[seg + 1];
-        for (int k = ptr[seg] + sub; k < k1; k += TPR) {
+        for (int k = k0 + sub; k < k1; k += TPR) {
             const double g = __ldg(gvec + idx[k]);
             acc += BINARY ? g : val[k] * g;
         }
@@ -810,19 +817,21 @@ k_csr_rowwise(const int* __restrict__ ptr, const int* __restrict__ idx, const do
 }
 
 template <bool BINARY>
-static void launch_rowwise(const SlabFmt* f, const double* gvec, const int* done_flag, cudaStream_t st) {
+static cudaError_t launch_rowwise(bb_ctx* ctx, const SlabFmt* f, const double* gvec, const int* done_flag) {
+    cudaError_t e = cudaSuccess;
     const double mean_len = f->n_seg > 0 ? (double)f->nnz / (double)f->n_seg : 0.0;
     int tpr = 2;
     while (tpr < 32 && tpr * 4 < mean_len) tpr *= 2;            // ~4-8 nnz per lane
     const i64 threads = f->n_seg * tpr;
     const unsigned grid = (unsigned)((threads + 255) / 256);
     switch (tpr) {
-    case 2: k_csr_rowwise<2, BINARY><<<grid, 256, 0, st>>>(f->ptr, f->idx, f->val, f->n_seg, gvec, f->part, done_flag); break;
-    case 4: k_csr_rowwise<4, BINARY><<<grid, 256, 0, st>>>(f->ptr, f->idx, f->val, f->n_seg, gvec, f->part, done_flag); break;
-    case 8: k_csr_rowwise<8, BINARY><<<grid, 256, 0, st>>>(f->ptr, f->idx, f->val, f->n_seg, gvec, f->part, done_flag); break;
-    case 16: k_csr_rowwise<16, BINARY><<<grid, 256, 0, st>>>(f->ptr, f->idx, f->val, f->n_seg, gvec, f->part, done_flag); break;
-    default: k_csr_rowwise<32, BINARY><<<grid, 256, 0, st>>>(f->ptr, f->idx, f->val, f->n_seg, gvec, f->part, done_flag); break;
+    case 2: e = bb_launch(ctx, true, k_csr_rowwise<2, BINARY>, dim3(grid), dim3(256), 0, f->ptr, f->idx, f->val, f->n_seg, gvec, f->part, done_flag); break;
+    case 4: e = bb_launch(ctx, true, k_csr_rowwise<4, BINARY>, dim3(grid), dim3(256), 0, f->ptr, f->idx, f->val, f->n_seg, gvec, f->part, done_flag); break;
+    case 8: e = bb_launch(ctx, true, k_csr_rowwise<8, BINARY>, dim3(grid), dim3(256), 0, f->ptr, f->idx, f->val, f->n_seg, gvec, f->part, done_flag); break;
+    case 16: e = bb_launch(ctx, true, k_csr_rowwise<16, BINARY>, dim3(grid), dim3(256), 0, f->ptr, f->idx, f->val, f->n_seg, gvec, f->part, done_flag); break;
+    default: e = bb_launch(ctx, true, k_csr_rowwise<32, BINARY>, dim3(grid), dim3(256), 0, f->ptr, f->idx, f->val, f->n_seg, gvec, f->part, done_flag); break;
     }
+    return e;
 }
 
 // launch the SpMV + fix-up for one format; gvec has f->n_gather entries
@@ -831,8 +840,8 @@ int bb_launch_spmv(bb_mat* m, SlabFmt* f, const double* gvec, const int* done_fl
     if (f->variant == 1) return bb_sell_launch(ctx, f, gvec, done_flag, skip_overflow_add);
     if (f->variant == 2) {
         if (f->n_seg == 0) return BB_OK;
-        if (f->val == nullptr) launch_rowwise<true>(f, gvec, done_flag, ctx->stream);
-        else launch_rowwise<false>(f, gvec, done_flag, ctx->stream);
+        if (f->val == nullptr) BB_CUDA(launch_rowwise<true>(ctx, f, gvec, done_flag));
+        else BB_CUDA(launch_rowwise<false>(ctx, f, gvec, done_flag));
         BB_LAUNCHED(ctx);
         return BB_OK;
     }
@@ -880,19 +889,31 @@ int bb_op_prepare_flag(bb_mat* m, const double* vP, const double* scale, const i
 }
 int bb_op_prepare(bb_mat* m, const double* vP, const double* scale) { return bb_op_prepare_flag(m, vP, scale, nullptr); }
 
+// the small kernels between the SpMV launches ask for the same shared-memory carve-out as the SpMV (opt_uniform_carveout)
+static int iteration_kernel_attrs(bb_ctx* ctx) {
+    static BBDeviceOnce once = {{0, 0, 0, 0}};
+    if (!once.first(ctx->device)) return BB_OK;
+    BB_CUDA(bb_prefer_max_smem(ctx, k_dot_finish<0>));
+    BB_CUDA(bb_prefer_max_smem(ctx, k_dot_finish<1>));
+    BB_CUDA(bb_prefer_max_smem(ctx, k_tdot_collect));
+    BB_CUDA(bb_prefer_max_smem(ctx, k_prepare));
+    return BB_OK;
+}
+
 int bb_op_dot_flag(bb_mat* m, int mode, const int* done_flag) {
     bb_ctx* ctx = m->ctx;
     if (!m->is_sparse) return bb_dense_dot(m, mode, done_flag);
+    BB_TRY(iteration_kernel_attrs(ctx));
     BB_TRY(bb_launch_spmv(m, &m->fdot, m->sv + m->add_intercept, done_flag));
     const double* red_shift = m->red + RED_SHIFT * RED_MAX;
     int nshift = P_grid(m->P);
     if (mode == 0) {
-        k_dot_finish<0><<<N_grid(m->n), 256, 0, ctx->stream>>>(m->fdot.part, m->fdot.nslab, m->n, red_shift, nshift,
-                                                             nullptr, nullptr, m->u_n, nullptr, nullptr, done_flag);
+        BB_CUDA(bb_launch(ctx, true, k_dot_finish<0>, dim3(N_grid(m->n)), dim3(256), 0, m->fdot.part, m->fdot.nslab, m->n,
+                          red_shift, nshift, nullptr, nullptr, m->u_n, nullptr, nullptr, done_flag));
     } else {
-        k_dot_finish<1><<<N_grid(m->n), 256, 0, ctx->stream>>>(m->fdot.part, m->fdot.nslab, m->n, red_shift, nshift,
-                                                             m->use_omega_scalar ? nullptr : m->omega, m->omega_scalar_dev, m->w_n, nullptr,
-                                                             m->red + RED_W * RED_MAX, done_flag);
+        BB_CUDA(bb_launch(ctx, true, k_dot_finish<1>, dim3(N_grid(m->n)), dim3(256), 0, m->fdot.part, m->fdot.nslab, m->n,
+                          red_shift, nshift, m->use_omega_scalar ? nullptr : m->omega, m->omega_scalar_dev, m->w_n, nullptr,
+                          m->red + RED_W * RED_MAX, done_flag));
         m->nred_w = N_grid(m->n);
     }
     BB_LAUNCHED(ctx);
@@ -951,9 +972,9 @@ int bb_op_tdot_local(bb_mat* m, const double* w, const int* done_flag) {
 // traw = [sum of the w partials; column sums of the slab / row-block partials]
 int bb_op_collect_local(bb_mat* m, const int* done_flag) {
     bb_ctx* ctx = m->ctx;
-    k_tdot_collect<<<grid_for(m->p, 32, 4096), 256, 0, ctx->stream>>>(
-        m->is_sparse ? m->ftdot.part : m->dense_part, m->is_sparse ? m->ftdot.nslab : m->dense_nblk, m->p,
-        m->red + RED_W * RED_MAX, m->nred_w, m->traw, done_flag, nullptr);
+    BB_CUDA(bb_launch(ctx, true, k_tdot_collect, dim3(grid_for(m->p, 32, 4096)), dim3(256), 0,
+                      m->is_sparse ? m->ftdot.part : m->dense_part, m->is_sparse ? m->ftdot.nslab : m->dense_nblk, m->p,
+                      m->red + RED_W * RED_MAX, m->nred_w, m->traw, done_flag, nullptr));
     BB_LAUNCHED(ctx);
     return BB_OK;
 }

@@ -106,11 +106,26 @@ def generate_dense_rows(blocks, n, p, seed=0, logit=False):
     return np.ascontiguousarray(np.vstack(Xs)), np.concatenate(ys)
 
 
+def _block_job(job):
+    b, n, p, density = job
+    return generate_block(b, n, p, column_frequencies(p, density))
+
+
 def generate_rows(blocks, n, p, density, logit_dense=False):
     if density >= 1.0:
         return generate_dense_rows(blocks, n, p, logit=logit_dense)
     freq = column_frequencies(p, density)
-    parts = [generate_block(b, n, p, freq) for b in blocks]
+    blocks = list(blocks)
+    # the row blocks are independent (seeded per block): generate them on several host cores (forked numpy-only workers;
+    # callers generate BEFORE the CUDA context exists).  The result does not depend on the number of workers.
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    workers = min(len(blocks), max(1, (os.cpu_count() or 1) // max(world, 1)), 16)
+    if workers > 1 and n * p * density > 2e6 and os.environ.get('BENCH_GEN_WORKERS', '') != '1':
+        import multiprocessing as mp
+        with mp.get_context('fork').Pool(workers) as pool:
+            parts = pool.map(_block_job, [(b, n, p, density) for b in blocks], chunksize=1)
+    else:
+        parts = [generate_block(b, n, p, freq) for b in blocks]
     X = sp.vstack([q[0] for q in parts], format='csr')
     X.indices = X.indices.astype(np.int32)
     X.indptr = X.indptr.astype(np.int32)
@@ -186,7 +201,7 @@ def import_reference():
     return bayesbridge
 
 
-def reference_run(workload, steps, warmup, sample_blocks=None, init_state=None, data=None, sampler='cg'):
+def reference_run(workload, steps, warmup, sample_blocks=None, init_state=None, data=None, sampler='cg', budget_s=None):
     """The reference's own numpy/scipy/Cython sampler (oracle/_ref, the unmodified package built by
     oracle/build_ref.sh) through ITS public API, on the host cores of this box.
 
@@ -198,12 +213,15 @@ def reference_run(workload, steps, warmup, sample_blocks=None, init_state=None, 
     reference from the state the GPU chain has reached so that its CG iteration counts are comparable.
     Returns (iterations/s, description dict)."""
     n, p, density = WORKLOADS[workload]
+    t_start = time.time()
     ref = import_reference()
     blocks = range(N_BLOCKS) if sample_blocks is None else range(sample_blocks)
     t_gen = time.time()
     X, y = data if data is not None else generate_rows(blocks, n, p, density, logit_dense=workload in N_CHAINS)
     t_gen = time.time() - t_gen
     frac = X.shape[0] / n
+    budget_note = ''
+    steps_run, warmup_run = steps, warmup
     if ref is not None:
         kind = 'reference'
         model = ref.RegressionModel(y, X, family='linear' if (is_dense(workload) and workload not in N_CHAINS) else 'logit')
@@ -214,23 +232,47 @@ def reference_run(workload, steps, warmup, sample_blocks=None, init_state=None, 
             # the reference's initialize_obs_precision takes len() of a given obs_prec (bayesbridge.py:355-360), which a
             # linear model's scalar precision does not have: let it recompute the precision from the coefficients
             kw['init'] = {k: v for k, v in init_state.items() if not (linear and k == 'obs_prec')}
+
+        def advance(info, k):
+            # k more Gibbs iterations of the same chain.  The reference's gibbs_resume fails for the linear model (same
+            # len() of a scalar): restart from the reached state instead, which skips the mode search (bayesbridge.py:279-353)
+            if linear:
+                st = info['_markov_chain_state']
+                return bridge.gibbs(n_iter=k, **dict(kw, init={q: st[q] for q in ('coef', 'local_scale', 'global_scale')}))[1]
+            return bridge.gibbs_resume(info, k)[1]
+
         t0 = time.time()
         if warmup > 0:
-            _, info = bridge.gibbs(n_iter=warmup, **kw)
+            # Wall-clock guard (budget_s; the driver's per-run limit is a few hundred seconds and a full-size C4 iteration
+            # of the reference takes ~20 s): the first warm-up iteration carries the chain initialisation, the second one
+            # is timed on its own; if W + K iterations at that pace would overrun the budget, FEWER full-size iterations
+            # are run -- reported as such ('steps' / 'warmup' of the line are the counts actually executed).  Nothing is
+            # ever extrapolated or run on a sub-sample.
+            _, info = bridge.gibbs(n_iter=1, **kw)
+            done_w = 1
+            if warmup >= 2:
+                t1 = time.time()
+                info = advance(info, 1)
+                t_iter = time.time() - t1
+                done_w = 2
+                if budget_s is not None:
+                    left = budget_s - (time.time() - t_start) - 5.0
+                    fit = int(max(left, 0.0) / max(t_iter, 1e-9))
+                    if fit < (warmup - done_w) + steps:
+                        steps_run = max(min(steps, 2), min(steps, int(0.8 * fit)))
+                        warmup_run = done_w + max(0, min(warmup - done_w, fit - steps_run))
+                        budget_note = ('; wall-clock budget %.0f s: %d + %d of the requested %d + %d iterations run (%.1f s each)'
+                                       % (budget_s, warmup_run, steps_run, warmup, steps, t_iter))
+            if warmup_run > done_w:
+                info = advance(info, warmup_run - done_w)
             t1 = time.time()
-            if linear:
-                # ... and for the same reason its gibbs_resume fails for the linear model: restart from the reached state
-                st = info['_markov_chain_state']
-                kw2 = dict(kw, init={k: st[k] for k in ('coef', 'local_scale', 'global_scale')})
-                _, info2 = bridge.gibbs(n_iter=steps, **kw2)
-            else:
-                _, info2 = bridge.gibbs_resume(info, steps)
+            info2 = advance(info, steps_run)
             dt = time.time() - t1
         else:
             _, info2 = bridge.gibbs(n_iter=steps, **kw)
             dt = info2['runtime']               # includes the (skipped or trivial) chain initialisation
         n_cg = (float(np.mean(info2['_reg_coef_sampling_info']['n_cg_iter']))
-                if steps > 0 and sampler == 'cg' else float('nan'))
+                if steps_run > 0 and sampler == 'cg' else float('nan'))
     else:
         # the oracle port (numpy restatement) when the reference could not be built
         kind = 'port'
@@ -244,7 +286,7 @@ def reference_run(workload, steps, warmup, sample_blocks=None, init_state=None, 
                                              TiltedStablePort, True)
         dt = (time.time() - t0) * steps / max(warmup + steps, 1)
         n_cg = float(n_cg_arr.mean())
-    its = steps / dt
+    its = steps_run / dt
     nnz_x = int(X.nnz) if sp.issparse(X) else int(X.size)
     what = ('the full %s matrix (%d x %d, nnz %d)' % (workload, X.shape[0], p, nnz_x) if sample_blocks is None else
             'rows 0..%d of %s (%d of %d row blocks, %.0f%% of the rows; NOT scaled to the full problem)'
@@ -253,11 +295,12 @@ def reference_run(workload, steps, warmup, sample_blocks=None, init_state=None, 
         'kind': kind, 'cores': (os.cpu_count() if is_dense(workload) else 1),
         'sample': '%s; %d timed Gibbs iterations after %d warm-up%s; %s and the Cython PG / tilted-stable '
                   'samplers are single-threaded (host has %d cores)'
-                  % (what, steps, warmup, '' if init_state is None else ', chain started from the state the GPU chain reached',
+                  % (what, steps_run, warmup_run, ('' if init_state is None else ', chain started from the state the GPU chain reached') + budget_note,
                      'numpy BLAS gemv uses all cores; the rest of the sampler' if is_dense(workload) else 'scipy SpMV',
                      os.cpu_count()),
         'full_size': sample_blocks is None, 'mean_n_cg_iter': (None if n_cg != n_cg else n_cg), 'sample_nnz': nnz_x,
-        'seconds_per_iteration': dt / steps, 'generate_seconds': t_gen,
+        'seconds_per_iteration': dt / steps_run, 'generate_seconds': t_gen,
+        'steps_run': steps_run, 'warmup_run': warmup_run, 'steps_requested': steps, 'warmup_requested': warmup,
     }
     return its, desc
 
@@ -283,6 +326,9 @@ def main():
                     help="coef_sampler_type; 'cholesky' is the comparator of BASELINE config 2 (dense workloads)")
     ap.add_argument('--ref-blocks', type=int, default=0,
                     help='time the CPU reference on the first K of the 50 row blocks only (0 = the full workload, the default)')
+    ap.add_argument('--ref-budget-s', type=float, default=float(os.environ.get('BENCH_REF_BUDGET_S', '700')),
+                    help='--impl reference: wall-clock budget of the whole run; when W + K full-size iterations would overrun it, '
+                         'fewer (still full-size) iterations are run and reported (0 = no limit)')
     ap.add_argument('--cpu-baseline-steps', type=int, default=2, help='full-size reference iterations of the cpu_baseline leg')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--clocks', default=os.environ.get('BENCH_CLOCKS', 'nvml'), choices=['nvml', 'none'])
@@ -305,15 +351,24 @@ def main():
     if args.impl == 'reference':
         if rank != 0:
             return
-        value, desc = reference_run(args.workload, args.steps, max(args.warmup, 1), args.ref_blocks or None, sampler=args.sampler)
+        value, desc = reference_run(args.workload, args.steps, max(args.warmup, 1), args.ref_blocks or None, sampler=args.sampler,
+                                    budget_s=(args.ref_budget_s if args.ref_budget_s > 0 else None))
         print(json.dumps({
             'impl': 'reference', 'metric': 'gibbs_iters_per_sec', 'value': value, 'unit': 'iter/s',
-            'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1000.0 / value,
+            'n_gpus': args.gpus, 'steps': desc['steps_run'], 'warmup': desc['warmup_run'] if args.warmup > 0 else 0,
+            'ms_per_step': 1000.0 / value,
             'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': config, 'cpu_baseline': dict(desc, value=value, unit='iter/s'),
+            # the same config object as the GPU arm prints (nnz of the whole matrix included)
+            'config': dict(config, nnz=int(desc['sample_nnz'])) if not args.ref_blocks else dict(config, ref_blocks=args.ref_blocks),
+            'cpu_baseline': dict(desc, value=value, unit='iter/s'),
             'e2e': {'value': value, 'unit': 'iter/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         }))
         return
+
+    # this rank's row blocks (generated first: the generator forks numpy-only workers, which must not inherit a CUDA context)
+    blocks = range(N_BLOCKS * rank // world, N_BLOCKS * (rank + 1) // world)
+    X, y = generate_rows(blocks, n, p, density, logit_dense=n_chains > 1)
+    row_offset = n * blocks[0] // N_BLOCKS
 
     import torch
     import torch.distributed as dist
@@ -325,11 +380,6 @@ def main():
     ctx = _lib.Context(local_rank)
     if world > 1:
         ctx.init_comm_from_torch()
-
-    # this rank's row blocks
-    blocks = range(N_BLOCKS * rank // world, N_BLOCKS * (rank + 1) // world)
-    X, y = generate_rows(blocks, n, p, density, logit_dense=n_chains > 1)
-    row_offset = n * blocks[0] // N_BLOCKS
     t_build = time.perf_counter()
     nnz_local = 0 if dense else int(X.nnz)
     from bayesbridge_b200.design_matrix import GpuSparseDesignMatrix, GpuDenseDesignMatrix
@@ -536,6 +586,7 @@ def main():
         'roofline': roofline if roofline is not None else {
             'bound': 'hbm', 'kernel': kernel_name, 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
             'frac': ach / peak, 'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peak_src,
+            'frac_of_8000GBs_spec': ach / 8000.0,          # the north star's nominal figure (SURVEY section 8d asks for both)
             'algorithmic_bytes_per_launch': int(alg[dom]),
             'ms_per_launch': roof[dom], 'timing': 'CUDA events on the library stream, L2 flushed before every launch (cold)',
             'other': dict([(k + '_ms', v) for k, v in roof.items()] + [(k + '_GBs', alg[k] / (v * 1e-3) / 1e9) for k, v in roof.items()]
