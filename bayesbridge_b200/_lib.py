@@ -82,6 +82,7 @@ SIGNATURES = {
     'bb_cg_sample_resident': (c_int, [c_void_p, P_dbl, c_dbl, c_dbl, c_dbl, c_int, c_u64, c_u64, P_dbl, P_int, P_int, P_dbl]),
     'bb_local_scale_resident': (c_int, [c_void_p, c_dbl, c_dbl, c_u64, c_u64, P_int, P_dbl]),
     'bb_time_kernel': (c_int, [c_void_p, c_char_p, c_int, c_int, P_dbl]),
+    'bb_spmv_timeline': (c_int, [c_void_p, c_int, c_int, c_void_p, ctypes.c_int64, ctypes.POINTER(c_int)]),
 }
 
 BB_NOISE_INJECT, BB_NOISE_PHILOX = 0, 1

@@ -101,6 +101,8 @@ static i64* option_slot(bb_ctx* c, const char* name) {
     if (!strcmp(name, "pside_fold_ovf")) return &c->opt_pside_fold_ovf;
     if (!strcmp(name, "pside_collect_max")) return &c->opt_pside_collect_max;
     if (!strcmp(name, "dense_stream")) return &c->opt_dense_stream;
+    if (!strcmp(name, "sell_slice_cost")) return &c->opt_sell_slice_cost;
+    if (!strcmp(name, "sell_partition")) return &c->opt_sell_partition;
     if (!strcmp(name, "pdl")) return &c->opt_pdl;
     if (!strcmp(name, "uniform_carveout")) return &c->opt_uniform_carveout;
     if (!strcmp(name, "allreduce_p2p")) return &c->opt_allreduce_p2p;

@@ -96,6 +96,9 @@ struct bb_ctx {
     i64 opt_pside_fold_ovf;     // overflow fragments folded inside the fused kernel: -1 automatic (few of them), 0 never, 1 always
     i64 opt_pside_collect_max;  // slab partials per column the fused kernel sums itself (0 = default 8); above: k_tdot_collect
     i64 opt_dense_stream;  // 1 (default): dense products through the one-pass TMA streaming kernel when a row pair fits in shared memory
+    i64 opt_sell_slice_cost;   // sliced format, work partition: per-slice overhead in row equivalents (0 = default 3)
+    i64 opt_sell_partition;    // 0 (default): slab-aligned CTA ranges when that shortens the estimated critical path; 1: always
+                               // equal-cost ranges (a CTA may stage two windows); 2: always slab-aligned
     i64 opt_pdl;           // 1 (default): the kernels of a fused CG iteration are launched with programmatic dependent launch
                            // (their launch and data-independent prologue overlap the tail of the previous kernel)
     i64 opt_uniform_carveout;  // 1 (default 0: measured, no gain): every kernel of the CG iteration asks for the maximum shared-memory carve-out, so
@@ -220,6 +223,7 @@ struct SlabFmt {
     double*   sl_vals;        // [64 * sl_off[nslices]] values in the same order, or NULL (pattern-only)
     int*  sl_slab_slice0;     // [nslab+1] first slice of each slab
     int*  sl_cta_slice0;      // [sl_ncta+1] first slice of each CTA's contiguous range (balanced by cost)
+    int   sl_partition;       // 1: equal-cost CTA ranges (a CTA may stage two windows), 2: slab-aligned ranges (bb_sell.cu)
     int   sl_ncta, sl_nsec;   // sl_cta_slice0 packs [cta_sec0 (sl_ncta+1) | sec_slab (sl_nsec) | sec_wstart (sl_nsec*33)]
     int   n_ovf_pieces;       // virtual segments longer than SELL_LMAX (their extra fragments land in overflow slots)
     int*  ovf_piece;          // [n_ovf_pieces] virtual segment id

@@ -43,6 +43,8 @@ constexpr int SELL_WARPS = SELL_THREADS / 32;
 constexpr int SELL_RING_BIN = 8;        // rows in flight per warp, pattern-only
 constexpr int SELL_RING_VAL = 2;        // rows in flight per warp, valued
 constexpr int SELL_SLICE_COST = 3;      // per-slice overhead in row equivalents (partitioning)
+constexpr int SELL_RESTAGE_COST = 400;  // a second window staged by the same CTA, in row equivalents of the CTA's cost: measured
+                                        // 2.5-3.8 us against ~0.31 us per 32 rows (one row per warp), profiles/r02_spmv_timeline.md
 
 i64 bb_sell_max_width(bb_ctx* ctx) {
     i64 w = ((i64)ctx->smem_optin - 64) / 8 - 2;
@@ -375,13 +377,23 @@ __device__ __forceinline__ void sell_batch(SellRow<BINARY> (&cur)[R], SellRow<BI
     }
 }
 
-template <bool BINARY, int R>
+__device__ __forceinline__ unsigned long long sell_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+constexpr int SELL_DBG_WORDS = 8 + SELL_WARPS;      // per CTA: entry, after wait, window staged, end, #sections, spare; per-warp end
+
+// DBG = true is a separate instantiation used only by bb_spmv_timeline (per-CTA / per-warp %globaltimer stamps into `dbg`);
+// the production instantiation carries none of that code.
+template <bool BINARY, int R, bool DBG = false>
 __global__ void __launch_bounds__(SELL_THREADS, 1)
 k_sell_spmv(const uint2* __restrict__ rows, const double* __restrict__ vals,
             const int* __restrict__ cta_sec0, const int* __restrict__ sec_slab, const int* __restrict__ sec_wstart,
             const double* __restrict__ gvec, int W, i64 n_gather, int use_bulk,
-            double* __restrict__ part, const int* __restrict__ done_flag)
+            double* __restrict__ part, const int* __restrict__ done_flag, unsigned long long* __restrict__ dbg = nullptr)
 {
+    if constexpr (DBG) { if (threadIdx.x == 0) { dbg[blockIdx.x * SELL_DBG_WORDS + 0] = sell_now(); dbg[blockIdx.x * SELL_DBG_WORDS + 4] = 0ull; } }
     // PDL (bb_internal.cuh): everything up to pdl_wait() reads only the matrix format and writes only shared memory
     pdl_trigger();
     extern __shared__ __align__(128) double sell_smem[];
@@ -422,6 +434,7 @@ k_sell_spmv(const uint2* __restrict__ rows, const double* __restrict__ vals,
         if (sec == sec_lo) {
             pdl_wait();                           // the gathered vector and the done flag come from the previous kernel
             if (done_flag != nullptr && *done_flag) return;
+            if constexpr (DBG) { if (tid == 0) dbg[blockIdx.x * SELL_DBG_WORDS + 1] = sell_now(); }
         }
         __syncthreads();                          // readers of the previous window are done; mbarrier init is visible
         if (use_bulk) {
@@ -457,6 +470,7 @@ k_sell_spmv(const uint2* __restrict__ rows, const double* __restrict__ vals,
         } else {
             __syncthreads();
         }
+        if constexpr (DBG) { if (tid == 0) { if (sec == sec_lo) dbg[blockIdx.x * SELL_DBG_WORDS + 2] = sell_now(); dbg[blockIdx.x * SELL_DBG_WORDS + 4] += 1ull; } }
         while (r < r_end) {
             sell_batch<BINARY, R>(bufA, bufB, rp, vp, r, r_end, sbase, part, w);
             r += R; rp += R * 32; if constexpr (!BINARY) vp += R * 64;
@@ -464,6 +478,11 @@ k_sell_spmv(const uint2* __restrict__ rows, const double* __restrict__ vals,
             sell_batch<BINARY, R>(bufB, bufA, rp, vp, r, r_end, sbase, part, w);
             r += R; rp += R * 32; if constexpr (!BINARY) vp += R * 64;
         }
+        if constexpr (DBG) { if (lane == 0) dbg[blockIdx.x * SELL_DBG_WORDS + 8 + warp] = sell_now(); }
+    }
+    if constexpr (DBG) {
+        __syncthreads();
+        if (tid == 0) dbg[blockIdx.x * SELL_DBG_WORDS + 3] = sell_now();
     }
 }
 
@@ -544,6 +563,7 @@ int bb_sell_build(bb_ctx* ctx, SlabFmt* f) {
     const int TB = 256;
     DevBuf tmp;
     f->variant = 1;
+    f->sl_partition = 1;
     f->nslices = 0; f->n_ovf = 0; f->n_ovf_pieces = 0;
     if (W > 65504) { bb_set_error("sliced format: slab width %d exceeds the 16-bit index range", W); return BB_ERR_ARG; }
     int *nfr = nullptr, *novf = nullptr, *frag_base = nullptr, *ovf_base = nullptr;
@@ -679,16 +699,80 @@ int bb_sell_build(bb_ctx* ctx, SlabFmt* f) {
 
     // work partition: CTA ranges of equal cost, cut at slab boundaries into sections, every section into 32 warp strips
     const int ncta = std::max(1, std::min(ctx->sm_count, nslices));
-    auto cost = [&](i64 s) { return (i64)off[(size_t)s] + (i64)(SELL_SLICE_COST - 1) * s; };   // off counts the header rows
+    const i64 slice_cost = (ctx->opt_sell_slice_cost > 0) ? ctx->opt_sell_slice_cost : SELL_SLICE_COST;
+    auto cost = [&](i64 s) { return (i64)off[(size_t)s] + (slice_cost - 1) * s; };   // off counts the header rows
     auto cut = [&](i64 lo, i64 hi, i64 target) {      // first s in [lo, hi] with cost(s) >= target
         while (lo < hi) { i64 mid = (lo + hi) >> 1; if (cost(mid) < target) lo = mid + 1; else hi = mid; }
         return lo;
     };
     std::vector<int> cta_sec0((size_t)ncta + 1, 0), sec_slab, sec_wstart;
     const i64 total_cost = cost(nslices);
+    // CTA b owns slices [cta_lo[b], cta_lo[b + 1]).  Two ways to draw the ranges:
+    //  A  equal cost, wherever the cuts fall: a CTA whose range straddles a slab boundary stages two windows one after the
+    //     other.  Measured (profiles/r02_spmv_timeline.md): +3.8 us on the N = 8 shard (15.3 us against 11.5 us for the
+    //     one-section CTAs), +2.5 us on C4 -- about SELL_RESTAGE_COST rows of streaming, and it sits on the critical path.
+    //  B  slab-aligned: slab s gets k_s CTAs in proportion to its cost (largest remainders, k_s >= 1) and is cut into k_s
+    //     equal parts; nobody stages twice, but the parts of different slabs differ by the rounding of k_s.
+    // The one with the smaller estimated critical path is taken (B needs at least as many CTAs as non-empty slabs).
+    std::vector<i64> cta_lo((size_t)ncta + 1, 0);
+    for (int b = 0; b <= ncta; ++b) cta_lo[(size_t)b] = (b == ncta) ? nslices : cut(0, nslices, total_cost * b / ncta);
+    {
+        bool straddles = false;
+        int sl = 0;
+        for (int b = 0; b < ncta && !straddles; ++b) {
+            if (cta_lo[(size_t)b] >= cta_lo[(size_t)b + 1]) continue;
+            while (slab_slice0[(size_t)sl + 1] <= cta_lo[(size_t)b]) ++sl;
+            straddles = cta_lo[(size_t)b + 1] > slab_slice0[(size_t)sl + 1];
+        }
+        int n_nonempty = 0;
+        for (int s2 = 0; s2 < nslab; ++s2) n_nonempty += (slab_slice0[(size_t)s2 + 1] > slab_slice0[(size_t)s2]) ? 1 : 0;
+        const bool try_aligned = (ctx->opt_sell_partition == 0) ? (straddles && n_nonempty <= ncta) : (ctx->opt_sell_partition == 2 && n_nonempty <= ncta);
+        if (try_aligned && total_cost > 0) {
+            std::vector<int> k((size_t)nslab, 0);
+            std::vector<std::pair<double, int>> rem;
+            int used = 0;
+            for (int s2 = 0; s2 < nslab; ++s2) {
+                const i64 cs = cost(slab_slice0[(size_t)s2 + 1]) - cost(slab_slice0[(size_t)s2]);
+                if (slab_slice0[(size_t)s2 + 1] == slab_slice0[(size_t)s2]) continue;
+                const double share = (double)cs * ncta / (double)total_cost;
+                k[(size_t)s2] = std::max(1, (int)share);
+                used += k[(size_t)s2];
+                rem.push_back({share - (double)k[(size_t)s2], s2});
+            }
+            std::sort(rem.begin(), rem.end(), [](const std::pair<double, int>& a, const std::pair<double, int>& b2) {
+                return a.first > b2.first || (a.first == b2.first && a.second < b2.second); });
+            for (size_t q = 0; used < ncta && !rem.empty(); q = (q + 1) % rem.size()) { k[(size_t)rem[q].second] += 1; ++used; }
+            while (used > ncta) {              // the floor of 1 CTA per slab overshot: take from the slab with the lightest parts
+                int best = -1; double lightest = 0.0;
+                for (int s2 = 0; s2 < nslab; ++s2) {
+                    if (k[(size_t)s2] < 2) continue;
+                    const double per = (double)(cost(slab_slice0[(size_t)s2 + 1]) - cost(slab_slice0[(size_t)s2])) / k[(size_t)s2];
+                    if (best < 0 || per < lightest) { best = s2; lightest = per; }
+                }
+                if (best < 0) break;
+                k[(size_t)best] -= 1; --used;
+            }
+            i64 worst_aligned = 0;
+            for (int s2 = 0; s2 < nslab; ++s2)
+                if (k[(size_t)s2] > 0)
+                    worst_aligned = std::max(worst_aligned, (cost(slab_slice0[(size_t)s2 + 1]) - cost(slab_slice0[(size_t)s2]) + k[(size_t)s2] - 1) / k[(size_t)s2]);
+            const i64 worst_equal = (total_cost + ncta - 1) / ncta + (i64)SELL_RESTAGE_COST;
+            if (used == ncta && (ctx->opt_sell_partition == 2 || worst_aligned < worst_equal)) {
+                int b = 0;
+                for (int s2 = 0; s2 < nslab; ++s2) {
+                    const i64 s_lo = slab_slice0[(size_t)s2], s_hi = slab_slice0[(size_t)s2 + 1];
+                    const i64 c_lo = cost(s_lo), c_hi = cost(s_hi);
+                    for (int j = 0; j < k[(size_t)s2]; ++j, ++b)
+                        cta_lo[(size_t)b] = (j == 0) ? s_lo : cut(s_lo, s_hi, c_lo + (c_hi - c_lo) * j / k[(size_t)s2]);
+                }
+                cta_lo[(size_t)ncta] = nslices;
+                f->sl_partition = 2;
+            }
+        }
+    }
     int slab = 0;
     for (int b = 0; b < ncta; ++b) {
-        const i64 c0 = cut(0, nslices, total_cost * b / ncta), c1 = (b == ncta - 1) ? nslices : cut(0, nslices, total_cost * (b + 1) / ncta);
+        const i64 c0 = cta_lo[(size_t)b], c1 = cta_lo[(size_t)b + 1];
         cta_sec0[(size_t)b] = (int)sec_slab.size();
         i64 cur = c0;
         while (cur < c1) {
@@ -741,15 +825,55 @@ int bb_sell_launch(bb_ctx* ctx, SlabFmt* f, const double* gvec, const int* done_
     const uint2* rows = reinterpret_cast<const uint2*>(f->sl_pairs);
     if (f->sl_vals == nullptr)
         BB_CUDA(bb_launch(ctx, true, k_sell_spmv<true, SELL_RING_BIN>, dim3(f->sl_ncta), dim3(SELL_THREADS), smem,
-                          rows, nullptr, cta_sec0, sec_slab, sec_wstart, gvec, f->W, f->n_gather, use_bulk, f->part, done_flag));
+                          rows, nullptr, cta_sec0, sec_slab, sec_wstart, gvec, f->W, f->n_gather, use_bulk, f->part, done_flag, nullptr));
     else
         BB_CUDA(bb_launch(ctx, true, k_sell_spmv<false, SELL_RING_VAL>, dim3(f->sl_ncta), dim3(SELL_THREADS), smem,
-                          rows, f->sl_vals, cta_sec0, sec_slab, sec_wstart, gvec, f->W, f->n_gather, use_bulk, f->part, done_flag));
+                          rows, f->sl_vals, cta_sec0, sec_slab, sec_wstart, gvec, f->W, f->n_gather, use_bulk, f->part, done_flag, nullptr));
     BB_LAUNCHED(ctx);
     if (f->n_ovf_pieces > 0 && !skip_overflow_add) {
         BB_CUDA(bb_launch(ctx, true, k_sell_ovf_add, dim3((unsigned)(((i64)f->n_ovf_pieces * 32 + 255) / 256)), dim3(256), 0,
                           f->ovf_piece, f->ovf_first, f->n_ovf_pieces, (i64)f->nslab * f->n_seg, f->part, done_flag));
         BB_LAUNCHED(ctx);
     }
+    return BB_OK;
+}
+
+// ---- profiling aid: per-CTA time line of one SpMV launch (debug instantiation of the kernel) ------------------------
+// out[cta * (8 + 32) + k]: k = 0 kernel entry, 1 after the dependency wait, 2 first window staged, 3 CTA end, 4 number of
+// sections, 8.. = end of each warp's last strip; all in ns of %globaltimer.  which: 0 = dot format, 1 = Tdot format.
+extern "C" int bb_spmv_timeline(bb_mat* m, int which, int flush_l2, uint64_t* out, int64_t capacity, int* ncta_out) {
+    BB_ARG(m && out && ncta_out, "mat/out/ncta_out");
+    BB_ARG(m->is_sparse, "sparse matrix needed");
+    bb_ctx* ctx = m->ctx;
+    BB_CUDA(cudaSetDevice(ctx->device));
+    SlabFmt* f = which ? &m->ftdot : &m->fdot;
+    BB_ARG(f->variant == 1 && f->nslices > 0 && f->sl_vals == nullptr, "pattern-only sliced format needed");
+    const int ncta = f->sl_ncta;
+    BB_ARG(capacity >= (int64_t)ncta * SELL_DBG_WORDS, "capacity");
+    const size_t smem = sell_smem_bytes(f);
+    static BBDeviceOnce attr_set = {{0, 0, 0, 0}};
+    if (attr_set.first(ctx->device))
+        BB_CUDA(cudaFuncSetAttribute(k_sell_spmv<true, SELL_RING_BIN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
+    unsigned long long* dbg = nullptr;
+    BB_TRY(bb_ctx_scratch(ctx, 3, (size_t)ncta * SELL_DBG_WORDS * sizeof(unsigned long long), (void**)&dbg));
+    const double* gvec = which ? m->eps_n : (m->sv + m->add_intercept);
+    const int use_bulk = (ctx->opt_spmv_bulk != 0 && (reinterpret_cast<uintptr_t>(gvec) & 15u) == 0 && (f->W & 1) == 0) ? 1 : 0;
+    const int* cta_sec0 = f->sl_cta_slice0;
+    const int* sec_slab = cta_sec0 + (f->sl_ncta + 1);
+    const int* sec_wstart = sec_slab + f->sl_nsec;
+    for (int rep = 0; rep < 3; ++rep) {       // the last repetition is the one reported
+        if (flush_l2) {
+            if (!ctx->flush_buf) { BB_CUDA(cudaMalloc(&ctx->flush_buf, (size_t)512 << 20)); ctx->flush_bytes = (size_t)512 << 20; }
+            BB_CUDA(cudaMemsetAsync(ctx->flush_buf, rep, ctx->flush_bytes, ctx->stream));
+        }
+        BB_CUDA(cudaMemsetAsync(dbg, 0, (size_t)ncta * SELL_DBG_WORDS * sizeof(unsigned long long), ctx->stream));
+        k_sell_spmv<true, SELL_RING_BIN, true><<<ncta, SELL_THREADS, smem, ctx->stream>>>(
+            reinterpret_cast<const uint2*>(f->sl_pairs), nullptr, cta_sec0, sec_slab, sec_wstart, gvec, f->W, f->n_gather, use_bulk,
+            f->part, nullptr, dbg);
+        BB_LAUNCHED(ctx);
+    }
+    BB_CUDA(cudaMemcpyAsync(out, dbg, (size_t)ncta * SELL_DBG_WORDS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    BB_CUDA(cudaStreamSynchronize(ctx->stream));
+    *ncta_out = ncta;
     return BB_OK;
 }

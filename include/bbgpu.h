@@ -218,6 +218,11 @@ int  bb_mode_search(bb_mat* mat, const double* coef0, const double* scale, const
  * what = "dot" | "tdot" | "op" (one application of X' Omega X v, two products) | "spmv_dot" | "spmv_tdot" (the sparse
  * kernel alone) | "fused_op" (dense: the one-pass operator) | "exchange" (the all-reduce of a (p+1)-vector) */
 int  bb_time_kernel(bb_mat* mat, const char* what, int reps, int flush_l2, double* ms_out);
+/* profiling aid: per-CTA time line (ns of %globaltimer) of ONE launch of the sliced SpMV kernel, taken with a debug
+ * instantiation of the kernel.  which = 0: the dot format, 1: the Tdot format.  out[cta * 40 + k]: k = 0 kernel entry,
+ * 1 dependency wait passed, 2 first gather window staged, 3 CTA end, 4 number of sections, 8..39 end of each warp's strip.
+ * capacity = words available in `out` (>= 40 * number of SMs).  (introspection, SURVEY section 8b "bb_get_timers") */
+int  bb_spmv_timeline(bb_mat* mat, int which, int flush_l2, uint64_t* out, int64_t capacity, int* ncta_out);
 /* measured fp64 tensor-core throughput (mma.sync m8n8k4 f64 issued back to back from registers), TFLOP/s: the roofline
  * denominator of the X'WX kernel (MEASURED_PEAKS.json carries no fp64 figure) */
 int  bb_measure_fp64_mma(bb_ctx* ctx, double* tflops);

@@ -113,6 +113,34 @@ def test_bank_aware_order_changes_rounding_only(ctx):
     assert np.array_equal(out[1][2][4], C.indices) and np.array_equal(out[1][2][5], C.data)
 
 
+@pytest.mark.parametrize('slab', [0, 256, 2048])
+def test_work_partition_does_not_change_a_bit(ctx, slab):
+    """The sliced kernel's work partition (option sell_partition: 1 = equal-cost CTA ranges that may straddle slabs,
+    2 = slab-aligned ranges, 0 = whichever has the shorter estimated critical path) and its cost model (sell_slice_cost)
+    only decide WHO sums a fragment: every product must come out bit-identical, and equal to the oracle's."""
+    Sparse, _ = _designs()
+    X = random_sparse(50000, 3000, 0.004, 5, binary=True)
+    O = co.DesignOracle(X, True, True)
+    rng = np.random.default_rng(9)
+    v, w = rng.standard_normal(3001), rng.standard_normal(50000)
+    ctx.set_option('slab_width', slab)
+    out = {}
+    try:
+        for part, sc in ((1, 0), (2, 0), (0, 0), (0, 9)):
+            ctx.set_option('sell_partition', part)
+            ctx.set_option('sell_slice_cost', sc)
+            D = Sparse(X, center_predictor=True, add_intercept=True, ctx=ctx)
+            out[(part, sc)] = (D.dot(v), D.Tdot(w))
+    finally:
+        ctx.set_option('sell_partition', 0)
+        ctx.set_option('sell_slice_cost', 0)
+        ctx.set_option('slab_width', 0)
+    base = out[(1, 0)]
+    assert relerr(base[0], O.dot(v)) < 1e-13 and relerr(base[1], O.Tdot(w)) < 1e-13
+    for key, (d, t) in out.items():
+        assert np.array_equal(d, base[0]) and np.array_equal(t, base[1]), key
+
+
 @pytest.mark.parametrize('n,p,stream', [(200, 30, 1), (5000, 1300, 1), (1001, 2049, 1), (3, 5, 1), (777, 4097, 1), (301, 9001, 1),
                                         (200, 30, 0), (5000, 1300, 0)])
 def test_dense_products_vs_oracle(ctx, n, p, stream):
