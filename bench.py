@@ -296,21 +296,27 @@ def reference_run(workload, steps, warmup, sample_blocks=None, init_state=None, 
         'sample': '%s; %d timed Gibbs iterations after %d warm-up%s; %s and the Cython PG / tilted-stable '
                   'samplers are single-threaded (host has %d cores)'
                   % (what, steps_run, warmup_run, ('' if init_state is None else ', chain started from the state the GPU chain reached') + budget_note,
-                     'numpy BLAS gemv uses all cores; the rest of the sampler' if is_dense(workload) else 'scipy SpMV',
+                     'numpy BLAS gemv uses all cores; the rest of the sampler' if is_dense(workload)
+                     else 'thread counts left at their defaults (numpy BLAS level-1 may spin up all cores; it does not help: C3 measured at '
+                          '2.66 s/iteration with 1 thread, 2.83 s with 8); scipy SpMV',
                      os.cpu_count()),
         'full_size': sample_blocks is None, 'mean_n_cg_iter': (None if n_cg != n_cg else n_cg), 'sample_nnz': nnz_x,
         'seconds_per_iteration': dt / steps_run, 'generate_seconds': t_gen,
-        'steps_run': steps_run, 'warmup_run': warmup_run, 'steps_requested': steps, 'warmup_requested': warmup,
+        'host_cores': os.cpu_count(), 'steps_run': steps_run, 'warmup_run': warmup_run, 'steps_requested': steps, 'warmup_requested': warmup,
     }
     return its, desc
 
 
 # ---- main ---------------------------------------------------------------------------------------
-def kernel_version():
-    """Identifies the source of the roofline kernels (a DRAM-traffic capture is only quoted for the version it was taken on)."""
+KERNEL_SOURCES = {'spmv_dot': ('bb_sell.cu',), 'spmv_tdot': ('bb_sell.cu',), 'fused_op': ('bb_dense.cu',), 'op': ('bb_dense.cu',),
+                  'batch_op': ('bb_batch.cu',)}
+
+
+def kernel_version(files=('bb_sell.cu', 'bb_dense.cu', 'bb_batch.cu')):
+    """Identifies the source of a roofline kernel (a DRAM-traffic capture is only quoted for the version it was taken on)."""
     import hashlib
     h = hashlib.sha1()
-    for f in ('bb_sell.cu', 'bb_dense.cu', 'bb_batch.cu'):
+    for f in files:
         h.update(open(os.path.join(ROOT, 'bayesbridge_b200', 'csrc', f), 'rb').read())
     return h.hexdigest()[:12]
 
@@ -535,7 +541,7 @@ def main():
     try:
         tr = json.load(open(os.path.join(ROOT, 'profiles', 'r02_traffic.json')))
         ent = tr.get('%s/%s/n%d' % (args.workload, dom, world))
-        if ent and ent.get('kernel_version') == kernel_version():
+        if ent and ent.get('kernel_version') == kernel_version(tuple(ent.get('kernel_sources', ('bb_sell.cu', 'bb_dense.cu', 'bb_batch.cu')))):
             traffic, traffic_src = float(ent['dram_bytes']), ent['source']
     except Exception:
         traffic, traffic_src = None, None

@@ -42,7 +42,9 @@ if '--traffic-key' in sys.argv:
     tr = json.load(open(path)) if os.path.exists(path) else {}
     for key, r in zip(keys, body):
         tr[key] = {'dram_bytes': get(r, 'dram__bytes_read.sum') + get(r, 'dram__bytes_write.sum'),
-                   'time_us_under_ncu': get(r, 'gpu__time_duration.sum'), 'kernel_version': bench.kernel_version(),
+                   'time_us_under_ncu': get(r, 'gpu__time_duration.sum'),
+                   'kernel_sources': list(bench.KERNEL_SOURCES[key.split('/')[1]]),
+                   'kernel_version': bench.kernel_version(bench.KERNEL_SOURCES[key.split('/')[1]]),
                    'source': '%s (ncu --set full --clock-control none, launch of %s)' % (os.path.basename(sys.argv[1]).replace('.csv', '.ncu-rep'), r[kname].split('(')[0])}
     json.dump(tr, open(path, 'w'), indent=1)
     print('traffic entries written to', path)
