@@ -50,6 +50,7 @@ extern "C" int bb_init(int device, bb_ctx** out) {
     c->opt_pside_fold_ovf = -1;
     c->opt_dense_stream = 1;
     c->opt_pdl = 1;
+    c->opt_sell_lpt = 1;
     c->opt_uniform_carveout = 0;   // measured (profiles/r02_pdl_ab.md): no gain at the N = 8 shard size, the dot SpMV loses 1-5 % (less L1 for its stores)
     c->opt_allreduce_p2p = 1;
     c->opt_p2p_variant = 3;      // one system fence + relaxed flag stores, parallel flag polls (fastest measured at N=8)
@@ -103,6 +104,7 @@ static i64* option_slot(bb_ctx* c, const char* name) {
     if (!strcmp(name, "dense_stream")) return &c->opt_dense_stream;
     if (!strcmp(name, "sell_slice_cost")) return &c->opt_sell_slice_cost;
     if (!strcmp(name, "sell_partition")) return &c->opt_sell_partition;
+    if (!strcmp(name, "sell_lpt")) return &c->opt_sell_lpt;
     if (!strcmp(name, "pdl")) return &c->opt_pdl;
     if (!strcmp(name, "uniform_carveout")) return &c->opt_uniform_carveout;
     if (!strcmp(name, "allreduce_p2p")) return &c->opt_allreduce_p2p;

@@ -97,6 +97,8 @@ struct bb_ctx {
     i64 opt_pside_collect_max;  // slab partials per column the fused kernel sums itself (0 = default 8); above: k_tdot_collect
     i64 opt_dense_stream;  // 1 (default): dense products through the one-pass TMA streaming kernel when a row pair fits in shared memory
     i64 opt_sell_slice_cost;   // sliced format, work partition: per-slice overhead in row equivalents (0 = default 3)
+    i64 opt_sell_lpt;          // 1 (default): the warp strips of a section are filled longest-slice-first (balanced to within one short
+                               // slice) and the slices laid out strip by strip; 0: contiguous cuts of the sorted slice order
     i64 opt_sell_partition;    // 0 (default): slab-aligned CTA ranges when that shortens the estimated critical path; 1: always
                                // equal-cost ranges (a CTA may stage two windows); 2: always slab-aligned
     i64 opt_pdl;           // 1 (default): the kernels of a fused CG iteration are launched with programmatic dependent launch
@@ -217,7 +219,7 @@ struct SlabFmt {
                               // 2: sub-warp-per-segment kernel on the canonical arrays (k_csr_rowwise)
     int   nslices;            // slices of 32 fragments
     int   sl_lmax;            // fragment length cap chosen at build time (<= 256)
-    unsigned* sl_off;         // [nslices+1] offset of a slice in index PAIRS per lane (slice length L = 2*(off[s+1]-off[s]))
+    unsigned* sl_off;         // [nslices+1] first row of every slice (sorted slice order) in the row stream; build-time only
     unsigned* sl_slot;        // [nslices*32] output slot of every lane's fragment (index into part)
     unsigned* sl_pairs;       // [32 * sl_off[nslices]] two 16-bit in-slab gather indices per word, blocked per lane
     double*   sl_vals;        // [64 * sl_off[nslices]] values in the same order, or NULL (pattern-only)

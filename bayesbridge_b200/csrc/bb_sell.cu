@@ -35,6 +35,8 @@
 #include <cub/cub.cuh>
 #include <vector>
 #include <algorithm>
+#include <queue>
+#include <functional>
 
 constexpr int SELL_LMAX = 256;          // max nnz per fragment (multiple of 4)
 constexpr int SELL_WINDOW_BITS = 17;    // fragments are length-sorted inside windows of 2^17 segments (write locality)
@@ -176,7 +178,7 @@ __global__ void __launch_bounds__(SELL_FILL_WARPS * 32)
 k_sell_fill(const int* __restrict__ slab_slice0, const int* __restrict__ slab_frag0, int nslab, int nslices,
             const int* __restrict__ sorted_id, const int* __restrict__ frag_src, const int* __restrict__ frag_len,
             const unsigned* __restrict__ frag_slot, const int* __restrict__ idx, const double* __restrict__ val, int W,
-            const unsigned* __restrict__ sl_off, unsigned trash_slot, int permute,
+            const unsigned* __restrict__ sl_off, const int* __restrict__ sl_nrows, unsigned trash_slot, int permute,
             unsigned* __restrict__ words, double* __restrict__ vals) {
     extern __shared__ __align__(16) unsigned char fill_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -204,8 +206,8 @@ k_sell_fill(const int* __restrict__ slab_slice0, const int* __restrict__ slab_fr
         for (int b = 0; b < 16; ++b) if (S.bptr[lane][b] < S.bend[lane][b]) mask |= 1u << b;
     }
     __syncwarp();
-    const unsigned r0 = sl_off[slice] + 1u;                 // first data row (the header row precedes it)
-    const int nrows = (int)(sl_off[slice + 1] - r0);
+    const unsigned r0 = sl_off[slice] + 1u;                 // first data row (the header row precedes it); sl_off = the slice's
+    const int nrows = sl_nrows[slice] - 1;                  // place in the row stream, which the work partition decides
     {   // header row: {output slot, data rows of the slice}
         const size_t o32 = ((size_t)(r0 - 1u) * 32 + lane) * 2;
         words[o32] = slot;
@@ -667,35 +669,30 @@ int bb_sell_build(bb_ctx* ctx, SlabFmt* f) {
     BB_CUDA(cudaMalloc((void**)&f->sl_slab_slice0, ((size_t)nslab + 1) * sizeof(int)));
     BB_CUDA(cudaMemcpyAsync(f->sl_slab_slice0, slab_slice0.data(), ((size_t)nslab + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
 
-    // rows per slice -> offsets
+    // rows per slice (device) -> host; `off` = prefix sums in the sorted slice order (the cost scale of the partition below)
     int* nrows = nullptr;
     BB_CUDA(tmp.alloc(&nrows, (size_t)nslices + 1));
     BB_CUDA(cudaMemsetAsync(nrows, 0, ((size_t)nslices + 1) * sizeof(int), st));
     BB_CUDA(cudaMalloc((void**)&f->sl_off, ((size_t)nslices + 1) * sizeof(unsigned)));
     BB_CUDA(cudaMemsetAsync(f->sl_off, 0, ((size_t)nslices + 1) * sizeof(unsigned), st));
+    std::vector<int> nr((size_t)nslices + 1, 0);
     std::vector<unsigned> off((size_t)nslices + 1, 0u);
     if (nslices > 0) {
         k_sell_slice_rows<<<(int)(((i64)nslices * 32 + TB - 1) / TB), TB, 0, st>>>(f->sl_slab_slice0, d_slab_frag0, nslab, nslices,
                                                                                   sorted_id, frag_len, nrows);
         ctx->launches += 1;
-        BB_TRY(sell_exclusive_scan(ctx, nrows, reinterpret_cast<int*>(f->sl_off), (i64)nslices + 1));
-        BB_CUDA(cudaMemcpyAsync(off.data(), f->sl_off, ((size_t)nslices + 1) * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+        BB_CUDA(cudaMemcpyAsync(nr.data(), nrows, (size_t)nslices * sizeof(int), cudaMemcpyDeviceToHost, st));
         BB_CUDA(cudaStreamSynchronize(st));
     }
+    {
+        unsigned long long run = 0;
+        for (int s2 = 0; s2 < nslices; ++s2) { off[(size_t)s2] = (unsigned)run; run += (unsigned long long)nr[(size_t)s2]; }
+        if (run >= (1ull << 31)) { bb_set_error("sliced format: too many rows"); return BB_ERR_ARG; }
+        off[(size_t)nslices] = (unsigned)run;
+    }
     const size_t total_rows = off[(size_t)nslices];
-    if (total_rows >= ((size_t)1 << 31)) { bb_set_error("sliced format: too many rows"); return BB_ERR_ARG; }
     BB_CUDA(cudaMalloc((void**)&f->sl_pairs, (total_rows * 64 + 4) * sizeof(unsigned)));
     if (f->val) BB_CUDA(cudaMalloc((void**)&f->sl_vals, (total_rows * 128 + 4) * sizeof(double)));
-    if (nslices > 0) {
-        static BBDeviceOnce fill_attr = {{0, 0, 0, 0}};
-        const size_t fill_smem = sizeof(SellFillSmem) * SELL_FILL_WARPS;
-        if (fill_attr.first(ctx->device))
-            BB_CUDA(cudaFuncSetAttribute(k_sell_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fill_smem));
-        k_sell_fill<<<(nslices + SELL_FILL_WARPS - 1) / SELL_FILL_WARPS, SELL_FILL_WARPS * 32, fill_smem, st>>>(
-            f->sl_slab_slice0, d_slab_frag0, nslab, nslices, sorted_id, frag_src, frag_len, frag_slot, f->idx, f->val, W,
-            f->sl_off, trash_slot, (int)ctx->opt_bank_permute, f->sl_pairs, f->sl_vals);
-        ctx->launches += 1;
-    }
 
     // work partition: CTA ranges of equal cost, cut at slab boundaries into sections, every section into 32 warp strips
     const int ncta = std::max(1, std::min(ctx->sm_count, nslices));
@@ -771,6 +768,9 @@ int bb_sell_build(bb_ctx* ctx, SlabFmt* f) {
         }
     }
     int slab = 0;
+    std::vector<unsigned> dst((size_t)nslices + 1, 0u);       // first row of every slice in the row stream
+    std::vector<int> order, wlist[SELL_WARPS];
+    unsigned next_row = 0;
     for (int b = 0; b < ncta; ++b) {
         const i64 c0 = cta_lo[(size_t)b], c1 = cta_lo[(size_t)b + 1];
         cta_sec0[(size_t)b] = (int)sec_slab.size();
@@ -779,15 +779,56 @@ int bb_sell_build(bb_ctx* ctx, SlabFmt* f) {
             while (slab + 1 <= nslab && slab_slice0[(size_t)slab + 1] <= cur) ++slab;      // slab containing slice `cur`
             const i64 e = std::min<i64>(c1, slab_slice0[(size_t)slab + 1]);
             sec_slab.push_back(slab);
-            const i64 ca = cost(cur), cb = cost(e);
-            for (int w = 0; w <= SELL_WARPS; ++w) {
-                i64 sw = (w == 0) ? cur : (w == SELL_WARPS) ? e : cut(cur, e, ca + (cb - ca) * w / SELL_WARPS);
-                sec_wstart.push_back((int)off[(size_t)sw]);       // strips are stored as ROW offsets
+            if (ctx->opt_sell_lpt != 0) {
+                // The 32 warp strips of a section: longest-processing-time-first assignment of its slices (the longest
+                // slice is up to 65 rows, a strip ~25 rows on the N = 8 shard and ~180 on C4: contiguous cuts at slice
+                // granularity left the slowest warp of a CTA 3-9 us behind the median, profiles/r02_spmv_timeline.md).
+                // The slices are then LAID OUT strip by strip, so that a warp still streams one contiguous byte range.
+                const int cnt = (int)(e - cur);
+                order.resize((size_t)cnt);
+                for (int q = 0; q < cnt; ++q) order[(size_t)q] = (int)cur + q;
+                std::stable_sort(order.begin(), order.end(), [&](int a2, int b2) { return nr[(size_t)a2] > nr[(size_t)b2]; });
+                for (int w = 0; w < SELL_WARPS; ++w) wlist[w].clear();
+                // min-heap over (load, warp): deterministic
+                std::priority_queue<std::pair<i64, int>, std::vector<std::pair<i64, int>>, std::greater<std::pair<i64, int>>> heap;
+                for (int w = 0; w < SELL_WARPS; ++w) heap.push({0, w});
+                for (int q = 0; q < cnt; ++q) {
+                    const std::pair<i64, int> top = heap.top(); heap.pop();
+                    const int sl2 = order[(size_t)q];
+                    wlist[top.second].push_back(sl2);
+                    heap.push({top.first + nr[(size_t)sl2] + (slice_cost - 1), top.second});
+                }
+                for (int w = 0; w < SELL_WARPS; ++w) {
+                    sec_wstart.push_back((int)next_row);
+                    for (int sl2 : wlist[w]) { dst[(size_t)sl2] = next_row; next_row += (unsigned)nr[(size_t)sl2]; }
+                }
+                sec_wstart.push_back((int)next_row);
+            } else {
+                const i64 ca = cost(cur), cb = cost(e);
+                for (int w = 0; w <= SELL_WARPS; ++w) {
+                    i64 sw = (w == 0) ? cur : (w == SELL_WARPS) ? e : cut(cur, e, ca + (cb - ca) * w / SELL_WARPS);
+                    sec_wstart.push_back((int)off[(size_t)sw]);       // strips are stored as ROW offsets
+                }
+                for (i64 q = cur; q < e; ++q) dst[(size_t)q] = off[(size_t)q];
+                next_row = off[(size_t)e];
             }
             cur = e;
         }
     }
     cta_sec0[(size_t)ncta] = (int)sec_slab.size();
+    if ((size_t)next_row != total_rows) { bb_set_error("sliced format: layout covers %u of %zu rows", next_row, total_rows); return BB_ERR_STATE; }
+    dst[(size_t)nslices] = (unsigned)total_rows;
+    BB_CUDA(cudaMemcpyAsync(f->sl_off, dst.data(), ((size_t)nslices + 1) * sizeof(unsigned), cudaMemcpyHostToDevice, st));
+    if (nslices > 0) {
+        static BBDeviceOnce fill_attr = {{0, 0, 0, 0}};
+        const size_t fill_smem = sizeof(SellFillSmem) * SELL_FILL_WARPS;
+        if (fill_attr.first(ctx->device))
+            BB_CUDA(cudaFuncSetAttribute(k_sell_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fill_smem));
+        k_sell_fill<<<(nslices + SELL_FILL_WARPS - 1) / SELL_FILL_WARPS, SELL_FILL_WARPS * 32, fill_smem, st>>>(
+            f->sl_slab_slice0, d_slab_frag0, nslab, nslices, sorted_id, frag_src, frag_len, frag_slot, f->idx, f->val, W,
+            f->sl_off, nrows, trash_slot, (int)ctx->opt_bank_permute, f->sl_pairs, f->sl_vals);
+        ctx->launches += 1;
+    }
     f->sl_ncta = ncta;
     const size_t nsec = sec_slab.size();
     // one allocation: [cta_sec0 (ncta+1) | sec_slab (nsec) | sec_wstart (nsec*33)]

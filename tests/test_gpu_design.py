@@ -116,8 +116,9 @@ def test_bank_aware_order_changes_rounding_only(ctx):
 @pytest.mark.parametrize('slab', [0, 256, 2048])
 def test_work_partition_does_not_change_a_bit(ctx, slab):
     """The sliced kernel's work partition (option sell_partition: 1 = equal-cost CTA ranges that may straddle slabs,
-    2 = slab-aligned ranges, 0 = whichever has the shorter estimated critical path) and its cost model (sell_slice_cost)
-    only decide WHO sums a fragment: every product must come out bit-identical, and equal to the oracle's."""
+    2 = slab-aligned ranges, 0 = whichever has the shorter estimated critical path), its cost model (sell_slice_cost) and
+    the way a section is split into warp strips (sell_lpt: longest slice first + strip-major layout, or contiguous cuts)
+    only decide WHO sums a fragment and WHERE its indices are stored: every product must come out bit-identical, and equal to the oracle's."""
     Sparse, _ = _designs()
     X = random_sparse(50000, 3000, 0.004, 5, binary=True)
     O = co.DesignOracle(X, True, True)
@@ -126,16 +127,18 @@ def test_work_partition_does_not_change_a_bit(ctx, slab):
     ctx.set_option('slab_width', slab)
     out = {}
     try:
-        for part, sc in ((1, 0), (2, 0), (0, 0), (0, 9)):
+        for part, sc, lpt in ((1, 0, 0), (2, 0, 0), (0, 0, 0), (0, 9, 0), (1, 0, 1), (2, 0, 1), (0, 0, 1), (0, 9, 1)):
             ctx.set_option('sell_partition', part)
             ctx.set_option('sell_slice_cost', sc)
+            ctx.set_option('sell_lpt', lpt)
             D = Sparse(X, center_predictor=True, add_intercept=True, ctx=ctx)
-            out[(part, sc)] = (D.dot(v), D.Tdot(w))
+            out[(part, sc, lpt)] = (D.dot(v), D.Tdot(w))
     finally:
         ctx.set_option('sell_partition', 0)
         ctx.set_option('sell_slice_cost', 0)
+        ctx.set_option('sell_lpt', 1)
         ctx.set_option('slab_width', 0)
-    base = out[(1, 0)]
+    base = out[(1, 0, 0)]
     assert relerr(base[0], O.dot(v)) < 1e-13 and relerr(base[1], O.Tdot(w)) < 1e-13
     for key, (d, t) in out.items():
         assert np.array_equal(d, base[0]) and np.array_equal(t, base[1]), key
