@@ -47,6 +47,8 @@ extern "C" int bb_init(int device, bb_ctx** out) {
     c->opt_use_graph = 1;
     c->opt_cg_fused = 1;
     c->opt_pside_ctas = 0;
+    c->opt_pside_barrier = 1;
+    c->opt_pside_ll = 1;
     c->opt_pside_fold_ovf = -1;
     c->opt_dense_stream = 1;
     c->opt_pdl = 1;
@@ -99,6 +101,8 @@ static i64* option_slot(bb_ctx* c, const char* name) {
     if (!strcmp(name, "use_graph")) return &c->opt_use_graph;
     if (!strcmp(name, "cg_fused")) return &c->opt_cg_fused;
     if (!strcmp(name, "pside_ctas")) return &c->opt_pside_ctas;
+    if (!strcmp(name, "pside_barrier")) return &c->opt_pside_barrier;
+    if (!strcmp(name, "pside_ll")) return &c->opt_pside_ll;
     if (!strcmp(name, "pside_fold_ovf")) return &c->opt_pside_fold_ovf;
     if (!strcmp(name, "pside_collect_max")) return &c->opt_pside_collect_max;
     if (!strcmp(name, "dense_stream")) return &c->opt_dense_stream;

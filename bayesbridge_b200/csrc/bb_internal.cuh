@@ -93,6 +93,9 @@ struct bb_ctx {
     i64 opt_use_graph;     // capture the CG iteration chunk into a CUDA graph
     i64 opt_cg_fused;      // 1 (default): the P-side of a CG iteration (+ its all-reduce) is one kernel (bb_pside.cu)
     i64 opt_pside_ctas;    // grid of that kernel (0 = automatic)
+    i64 opt_pside_ll;      // 1 (default): the exchange inside that kernel sends flag-in-data lines (no flag round trips, no grid barriers
+                           // around them) when the exchange buffer has room for 2 (p + 1) doubles per region; 0: data + flags
+    i64 opt_pside_barrier; // 1 (default): its grid barriers arrive with a release reduction and poll at once; 0: fence + atomicAdd + fence
     i64 opt_pside_fold_ovf;     // overflow fragments folded inside the fused kernel: -1 automatic (few of them), 0 never, 1 always
     i64 opt_pside_collect_max;  // slab partials per column the fused kernel sums itself (0 = default 8); above: k_tdot_collect
     i64 opt_dense_stream;  // 1 (default): dense products through the one-pass TMA streaming kernel when a row pair fits in shared memory

@@ -39,6 +39,8 @@ struct PsideArgs {
     double* red_pq; double* red_rr; double* red_shift; int nshift;
     unsigned long long* bar;
     const P2PView* view;                                             // nullptr: no exchange
+    int lean_barrier;                                                // option pside_barrier
+    int ll;                                                          // exchange with flag-in-data lines (option pside_ll)
 };
 
 __device__ __forceinline__ unsigned long long ps_ld_acquire_gpu(const unsigned long long* p) {
@@ -47,14 +49,23 @@ __device__ __forceinline__ unsigned long long ps_ld_acquire_gpu(const unsigned l
     return v;
 }
 
-// all CTAs of the grid are co-resident (grid <= PS_MAX_CTAS <= number of SMs, one stream): a counting barrier
-__device__ __forceinline__ void ps_grid_barrier(unsigned long long* ctr, unsigned long long target) {
+// all CTAs of the grid are co-resident (grid <= PS_MAX_CTAS <= number of SMs, one stream): a counting barrier.
+// Arrival is a release reduction WITHOUT a return value (the CTA's writes, ordered before it by the block barrier, are
+// visible to whoever observes the count), so the poll starts at once instead of after the atomic's round trip; the poll is
+// an acquire load.  (Round-2 measurement: the fused kernel is four to five of these per CG iteration, each followed by a
+// fixed-order sum of the partials -- at the N = 8 shard size it is the largest single kernel, profiles/r02_launches.md.)
+__device__ __forceinline__ void ps_grid_barrier(unsigned long long* ctr, unsigned long long target, int lean = 1) {
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(ctr, 1ull);
-        while (ps_ld_acquire_gpu(ctr) < target) { }
-        __threadfence();
+        if (lean) {
+            asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(ctr) : "memory");
+            while (ps_ld_acquire_gpu(ctr) < target) { }
+        } else {                                  // the first form (option pside_barrier = 0), kept for the A/B
+            __threadfence();
+            atomicAdd(ctr, 1ull);
+            while (ps_ld_acquire_gpu(ctr) < target) { }
+            __threadfence();
+        }
     }
     __syncthreads();
 }
@@ -77,6 +88,29 @@ __device__ __forceinline__ void ps_wait_flags(const unsigned long long* flags, i
         }
     }
     __syncthreads();
+}
+
+// ---- flag-in-data ("LL") lines: the exchange without flag round trips -------------------------------------------------
+// An exchanged double travels as one 16-byte line {lo32, tag, hi32, tag}, tag = low 32 bits of the exchange number, written
+// with ONE 16-byte store.  8-byte halves of such a store are never torn, so a reader that sees `tag` in both halves has the
+// whole value: the data announce themselves, and neither a grid barrier + system fence + flag store on the sending side nor a
+// flag wait on the receiving side is needed.  (The technique of NCCL's LL protocol, here with fp64 payloads.)  Twice the
+// bytes over NVLink (3.2 MB per rank and exchange at p = 1e5) for two flag round trips and two grid barriers less.
+__device__ __forceinline__ void ll_store(double* line, double v, unsigned tag) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};"
+                 ::"l"(line), "r"((unsigned)b), "r"(tag), "r"((unsigned)(b >> 32)), "r"(tag) : "memory");
+}
+// spins until the line carries `tag`; a lost peer raises the error flag (and yields 0) instead of hanging the GPU
+__device__ __forceinline__ double ll_load_wait(const double* line, unsigned tag, P2PState* st) {
+    unsigned x, f0, y, f1;
+    unsigned long long spins = 0;
+    for (;;) {
+        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x), "=r"(f0), "=r"(y), "=r"(f1) : "l"(line) : "memory");
+        if (f0 == tag && f1 == tag) break;
+        if (++spins > (1ull << 24)) { st->error = 1u; return 0.0; }
+    }
+    return __longlong_as_double((long long)(((unsigned long long)y << 32) | (unsigned long long)x));
 }
 
 __global__ void __launch_bounds__(PS_THREADS)
@@ -124,16 +158,20 @@ k_cg_pside(const PsideArgs a) {
             if (lane == 0) a.part[a.ovf_piece[i]] += t;
         }
         target += (unsigned long long)G;
-        ps_grid_barrier(a.bar, target);
+        ps_grid_barrier(a.bar, target, a.lean_barrier);
     }
 
     // ---- phase A1: local [sum w; X'w]; with an exchange, pushed chunk by chunk into the owners' inboxes ----
+    const bool ll = (N > 1) && (a.ll != 0);
+    const unsigned tag = (unsigned)want;
     if (a.precollected) {
         // many slabs (few ranks): a separate, much wider launch has already summed them into traw
         if (N > 1) {
             for (i64 j = gtid; j < L; j += gthreads) {
                 const i64 owner = j / Cw;
-                peer[owner][inbox_off + (i64)me * Cw + (j - owner * Cw)] = a.traw[j];
+                const i64 e = (i64)me * Cw + (j - owner * Cw);
+                if (ll) ll_store(peer[owner] + inbox_off + 2 * e, a.traw[j], tag);
+                else peer[owner][inbox_off + e] = a.traw[j];
             }
         }
     } else {
@@ -141,6 +179,7 @@ k_cg_pside(const PsideArgs a) {
             const double sw = warp_sum_partials(a.red_w, a.nred_w);
             if (lane == 0) {
                 if (N == 1) a.traw[0] = sw;
+                else if (ll) ll_store(peer[0] + inbox_off + 2 * ((i64)me * Cw), sw, tag);
                 else peer[0][inbox_off + (i64)me * Cw] = sw;
             }
         }
@@ -158,17 +197,30 @@ k_cg_pside(const PsideArgs a) {
                 a.traw[j] = t;
             } else {
                 const i64 owner = j / Cw;
-                peer[owner][inbox_off + (i64)me * Cw + (j - owner * Cw)] = t;
+                const i64 e = (i64)me * Cw + (j - owner * Cw);
+                if (ll) ll_store(peer[owner] + inbox_off + 2 * e, t, tag);
+                else peer[owner][inbox_off + e] = t;
             }
         }
     }
-    if (!(a.precollected && N == 1)) {
+    if (!(a.precollected && N == 1) && !ll) {
         target += (unsigned long long)G;
-        ps_grid_barrier(a.bar, target);
+        ps_grid_barrier(a.bar, target, a.lean_barrier);
     }
 
     const double* tvec = a.traw;
-    if (N > 1) {
+    if (ll) {
+        // ---- phase B: reduce the own chunk in rank order as its lines arrive, push the sums to every rank ----
+        double* own = peer[me];
+        const i64 lo = (i64)me * Cw;
+        i64 cnt = L - lo; if (cnt > Cw) cnt = Cw; if (cnt < 0) cnt = 0;
+        for (i64 jj = gtid; jj < cnt; jj += gthreads) {
+            double acc = 0.0;
+            for (int sdr = 0; sdr < N; ++sdr) acc += ll_load_wait(own + inbox_off + 2 * ((i64)sdr * Cw + jj), tag, pst);
+            for (int qq = 0; qq < N; ++qq) ll_store(peer[qq] + result_off + 2 * (lo + jj), acc, tag);
+        }
+        tvec = own + result_off;          // lines: entry j of the reduced vector is at tvec + 2 j, read with ll_load_wait
+    } else if (N > 1) {
         double* own = peer[me];
         unsigned long long* own_flags = reinterpret_cast<unsigned long long*>(own);
         if (lead) {
@@ -186,7 +238,7 @@ k_cg_pside(const PsideArgs a) {
             for (int qq = 0; qq < N; ++qq) peer[qq][result_off + lo + jj] = acc;
         }
         target += (unsigned long long)G;
-        ps_grid_barrier(a.bar, target);
+        ps_grid_barrier(a.bar, target, a.lean_barrier);
         if (lead) {
             __threadfence_system();
             for (int qq = 0; qq < N; ++qq)
@@ -198,11 +250,12 @@ k_cg_pside(const PsideArgs a) {
     }
 
     // ---- q = D.p + s.t ; p.q ----
-    const double sw = __ldcv(tvec);
+    const double sw = ll ? ll_load_wait(tvec, tag, pst) : __ldcv(tvec);
     double acc = 0.0;
     for (i64 j = gtid; j < a.P; j += gthreads) {
         // sparse_matrix.py:126-128   result = X.T.dot(v); result -= sum(v) * column_offset
-        const double t = (j < a.icpt) ? sw : __dsub_rn(__ldcv(tvec + 1 + (j - a.icpt)), __dmul_rn(sw, a.c[j - a.icpt]));
+        const double tj = (j < a.icpt) ? sw : (ll ? ll_load_wait(tvec + 2 * (1 + (j - a.icpt)), tag, pst) : __ldcv(tvec + 1 + (j - a.icpt)));
+        const double t = (j < a.icpt) ? sw : __dsub_rn(tj, __dmul_rn(sw, a.c[j - a.icpt]));
         const double pj = a.pvec[j];
         const double qj = __dadd_rn(__dmul_rn(a.D[j], pj), __dmul_rn(a.s[j], t));
         a.q[j] = qj;
@@ -211,7 +264,7 @@ k_cg_pside(const PsideArgs a) {
     acc = block_sum(acc, sm);
     if (tid == 0) a.red_pq[blockIdx.x] = acc;
     target += (unsigned long long)G;
-    ps_grid_barrier(a.bar, target);
+    ps_grid_barrier(a.bar, target, a.lean_barrier);
     const double pq = ps_sum_partials(a.red_pq, G);
 
     // ---- alpha = rho/(p.q) ; x += alpha p ; r -= alpha q ; r.r ----
@@ -226,7 +279,7 @@ k_cg_pside(const PsideArgs a) {
     acc = block_sum(acc, sm);
     if (tid == 0) a.red_rr[blockIdx.x] = acc;
     target += (unsigned long long)G;
-    ps_grid_barrier(a.bar, target);
+    ps_grid_barrier(a.bar, target, a.lean_barrier);
     const double rho = ps_sum_partials(a.red_rr, G);
 
     // ---- stop test of the next iteration, search direction, scaled gather vector of the next product ----
@@ -342,10 +395,15 @@ int bb_pside_enqueue(bb_mat* m) {
     i64 gP = (m->P + 1023) / 1024; if (gP < 1) gP = 1; if (gP > RED_MAX) gP = RED_MAX;
     a.nshift = (int)gP;
     a.bar = m->ps_bar;
+    a.lean_barrier = (ctx->opt_pside_barrier != 0) ? 1 : 0;
     a.view = nullptr;
+    a.ll = 0;
     if (ctx->nranks > 1) {
         if (m->p2p_view_valid == 0) { bb_set_error("fused CG iteration: bb_pside_prepare first"); return BB_ERR_STATE; }
         a.view = m->p2p_view_dev;
+        // flag-in-data lines need twice the room: nranks chunks of Cw lines in the inbox, p + 1 lines in the result region
+        const i64 Lx = m->p + 1, Nr = ctx->nranks, Cwx = (((Lx + Nr - 1) / Nr) + 1) & ~(i64)1;
+        a.ll = (ctx->opt_pside_ll != 0 && 2 * Nr * Cwx <= bb_p2p_capacity(ctx) && 2 * Lx <= bb_p2p_capacity(ctx)) ? 1 : 0;
     }
     static BBDeviceOnce attr_set = {{0, 0, 0, 0}};
     if (attr_set.first(ctx->device)) BB_CUDA(bb_prefer_max_smem(ctx, k_cg_pside));
