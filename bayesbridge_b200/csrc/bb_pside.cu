@@ -18,6 +18,15 @@
 // stopping decision in lock-step.  Buffers are reused by consecutive exchanges without a further handshake: a rank
 // can only push into a peer's inbox for exchange k+1 after it has passed phase C of exchange k, which needs the
 // peer's phase-B flag, which the peer raised after reading its inbox; the same argument covers the result buffer.
+//
+// Default form of the same data flow: flag-in-data lines (ll_store / ll_load_wait below, option pside_ll).  A value is
+// announced by the tag inside its own 16-byte line, so phases A-C have no flags, fences or grid barriers; a reader spins on
+// exactly the lines it needs.  Buffer reuse without a handshake, line by line: (inbox) rank a stores lines of exchange k+1
+// only after its p.q grid barrier of iteration k, i.e. after ALL its threads have read their result lines of exchange k;
+// result line j of exchange k exists only after owner c has read the N inbox lines of element j -- so every inbox line of
+// exchange k has been consumed by then.  (result region) owner c stores result line j of exchange k+1 after reading the
+// inbox line of j sent by rank q for k+1, which q sent after its p.q barrier of iteration k, i.e. after reading result line
+// j of exchange k.  Tags are exchange numbers, so a stale line never matches.
 #include "bb_internal.cuh"
 
 constexpr int PS_THREADS = 512;
