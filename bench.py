@@ -259,7 +259,10 @@ def reference_run(workload, steps, warmup, sample_blocks=None, init_state=None, 
                     left = budget_s - (time.time() - t_start) - 5.0
                     fit = int(max(left, 0.0) / max(t_iter, 1e-9))
                     if fit < (warmup - done_w) + steps:
-                        steps_run = max(min(steps, 2), min(steps, int(0.8 * fit)))
+                        # keep the warm-up and cut timed iterations first; below half the requested steps cut both
+                        steps_run = fit - (warmup - done_w)
+                        if steps_run < max(2, steps // 2):
+                            steps_run = max(min(steps, 2), min(steps, int(0.8 * fit)))
                         warmup_run = done_w + max(0, min(warmup - done_w, fit - steps_run))
                         budget_note = ('; wall-clock budget %.0f s: %d + %d of the requested %d + %d iterations run (%.1f s each)'
                                        % (budget_s, warmup_run, steps_run, warmup, steps, t_iter))
@@ -332,7 +335,7 @@ def main():
                     help="coef_sampler_type; 'cholesky' is the comparator of BASELINE config 2 (dense workloads)")
     ap.add_argument('--ref-blocks', type=int, default=0,
                     help='time the CPU reference on the first K of the 50 row blocks only (0 = the full workload, the default)')
-    ap.add_argument('--ref-budget-s', type=float, default=float(os.environ.get('BENCH_REF_BUDGET_S', '700')),
+    ap.add_argument('--ref-budget-s', type=float, default=float(os.environ.get('BENCH_REF_BUDGET_S', '790')),
                     help='--impl reference: wall-clock budget of the whole run; when W + K full-size iterations would overrun it, '
                          'fewer (still full-size) iterations are run and reported (0 = no limit)')
     ap.add_argument('--cpu-baseline-steps', type=int, default=2, help='full-size reference iterations of the cpu_baseline leg')
