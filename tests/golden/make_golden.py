@@ -282,9 +282,14 @@ def golden_posterior():
     y = rs.binomial(1, 1 / (1 + np.exp(-(X @ beta - 0.5))))
     br = ref.BayesBridge(ref.RegressionModel(y, X, family='logit'), ref.RegressionCoefPrior(bridge_exponent=.5))
     s, info = br.gibbs(n_iter=2500, n_burnin=500, coef_sampler_type='cg', seed=0)
+    # thinned marginals (every 20th of the 2000 kept draws) of the intercept, the ten signal coefficients, five null ones,
+    # log tau and the log-posterior: the two-sample KS tests of test_device_rng_chain_matches_reference_posterior
+    thin_idx = np.array(list(range(0, 11)) + [20, 50, 100, 200, 300])
     np.savez(os.path.join(HERE, 'posterior_ref.npz'), y=y, coef_mean=s['coef'].mean(1), coef_sd=s['coef'].std(1),
              log_gscale_mean=np.log(s['global_scale']).mean(), logp_mean=s['logp'].mean(),
-             n_cg_mean=info['_reg_coef_sampling_info']['n_cg_iter'].mean())
+             n_cg_mean=info['_reg_coef_sampling_info']['n_cg_iter'].mean(),
+             thin_idx=thin_idx, thin_coef=s['coef'][thin_idx][:, ::20], thin_log_gscale=np.log(s['global_scale'][::20]),
+             thin_logp=s['logp'][::20])
 
 
 if __name__ == '__main__':
