@@ -133,11 +133,17 @@ def test_device_rng_chain_matches_reference_posterior(ctx):
     se = np.sqrt(sd ** 2 + ref_sd ** 2) / np.sqrt(100)
     assert np.all(np.abs(mean - ref_mean) < 6 * se + 1e-3)
     big = np.abs(ref_mean) > 0.5
-    assert big.sum() >= 8 and np.allclose(mean[big], ref_mean[big], rtol=0.15)
-    assert np.log(samples['global_scale']).mean() == pytest.approx(float(g['log_gscale_mean']), abs=0.25)
-    assert samples['logp'].mean() == pytest.approx(float(g['logp_mean']), rel=0.02)
+    assert big.sum() >= 8 and np.allclose(mean[big], ref_mean[big], rtol=0.08)        # achieved on B200: 0.027
+    assert np.log(samples['global_scale']).mean() == pytest.approx(float(g['log_gscale_mean']), abs=0.15)   # achieved: 0.025
+    assert samples['logp'].mean() == pytest.approx(float(g['logp_mean']), rel=0.01)                        # achieved: 0.0036
     n_cg = info['_reg_coef_sampling_info']['n_cg_iter']
-    assert n_cg.mean() == pytest.approx(float(g['n_cg_mean']), rel=0.25)
+    assert n_cg.mean() == pytest.approx(float(g['n_cg_mean']), rel=0.06)                                   # achieved: 0.015
+    from conftest import record_achieved as _rec
+    _rec('device_rng_chain', 'max |mean - ref| / se over 301 coefficients', float(np.max(np.abs(mean - ref_mean) / (se + 1e-3 / 6))), 6.0)
+    _rec('device_rng_chain', 'max rel diff of the big coefficients', float(np.max(np.abs(mean[big] / ref_mean[big] - 1))), 0.08)
+    _rec('device_rng_chain', '|mean log tau - ref|', abs(float(np.log(samples['global_scale']).mean()) - float(g['log_gscale_mean'])), 0.15)
+    _rec('device_rng_chain', 'rel diff of mean logp', abs(float(samples['logp'].mean()) / float(g['logp_mean']) - 1), 0.01)
+    _rec('device_rng_chain', 'rel diff of mean n_cg_iter', abs(float(n_cg.mean()) / float(g['n_cg_mean']) - 1), 0.06)
     # Two-sample Kolmogorov-Smirnov on thinned marginals: 100 thinned draws of the reference chain
     # (every 20th of 2000) against 100 of this chain (every 10th of 1000) for the intercept, the ten signal coefficients,
     # five null coefficients, log tau and the log-posterior.  For n = m = 100 the critical distance is 0.276 at alpha = 1e-3
