@@ -201,6 +201,20 @@ def import_reference():
     return bayesbridge
 
 
+def plan_reference_iterations(fit, warmup, steps, done_w):
+    """How many warm-up and timed iterations the reference arm still runs when only `fit` more iterations fit into its
+    wall-clock budget (`done_w` warm-up iterations are already done).  Everything fits: as requested.  Otherwise the warm-up
+    is kept and timed iterations are cut first; below half the requested steps both are cut (never fewer than 2 timed).
+    Returns (warmup_run, steps_run), warmup_run counting the iterations already done."""
+    if fit >= (warmup - done_w) + steps:
+        return warmup, steps
+    steps_run = fit - (warmup - done_w)
+    if steps_run < max(2, steps // 2):
+        steps_run = max(min(steps, 2), min(steps, int(0.8 * fit)))
+    warmup_run = done_w + max(0, min(warmup - done_w, fit - steps_run))
+    return warmup_run, steps_run
+
+
 def reference_run(workload, steps, warmup, sample_blocks=None, init_state=None, data=None, sampler='cg', budget_s=None):
     """The reference's own numpy/scipy/Cython sampler (oracle/_ref, the unmodified package built by
     oracle/build_ref.sh) through ITS public API, on the host cores of this box.
@@ -258,12 +272,8 @@ def reference_run(workload, steps, warmup, sample_blocks=None, init_state=None, 
                 if budget_s is not None:
                     left = budget_s - (time.time() - t_start) - 5.0
                     fit = int(max(left, 0.0) / max(t_iter, 1e-9))
-                    if fit < (warmup - done_w) + steps:
-                        # keep the warm-up and cut timed iterations first; below half the requested steps cut both
-                        steps_run = fit - (warmup - done_w)
-                        if steps_run < max(2, steps // 2):
-                            steps_run = max(min(steps, 2), min(steps, int(0.8 * fit)))
-                        warmup_run = done_w + max(0, min(warmup - done_w, fit - steps_run))
+                    warmup_run, steps_run = plan_reference_iterations(fit, warmup, steps, done_w)
+                    if (warmup_run, steps_run) != (warmup, steps):
                         budget_note = ('; wall-clock budget %.0f s: %d + %d of the requested %d + %d iterations run (%.1f s each)'
                                        % (budget_s, warmup_run, steps_run, warmup, steps, t_iter))
             if warmup_run > done_w:

@@ -246,3 +246,23 @@ def test_reference_arm_line_has_the_contract_keys():
                 'cpu_baseline', 'e2e'):
         assert key in d
     assert d['cpu_baseline']['kind'] in ('reference', 'port') and d['e2e']['h2d_bytes_per_step'] == 0
+
+
+def test_reference_arm_budget_plan():
+    """bench.plan_reference_iterations: what the reference arm still runs when its wall-clock budget is short.  It never
+    extrapolates and never runs a sub-sample: it runs FEWER full-size iterations and reports the counts it executed."""
+    sys.path.insert(0, ROOT)
+    import bench
+    plan = bench.plan_reference_iterations
+    assert plan(23, 5, 20, 2) == (5, 20)            # everything fits (W = 5 of which 2 are done, K = 20)
+    assert plan(100, 5, 20, 2) == (5, 20)
+    assert plan(22, 5, 20, 2) == (5, 19)            # one short: the warm-up is kept, one timed iteration goes
+    assert plan(13, 5, 20, 2) == (5, 10)            # down to half the requested steps the warm-up is still kept
+    w, k = plan(10, 5, 20, 2)                       # below that both are cut ...
+    assert k == 8 and w == 4 and (w - 2) + k <= 10
+    w, k = plan(1, 5, 20, 2)                        # ... but never fewer than two timed iterations
+    assert k == 2 and w == 2
+    for fit in range(0, 40):
+        w, k = plan(fit, 5, 20, 2)
+        assert 2 <= k <= 20 and 2 <= w <= 5
+        assert (w - 2) + k <= max(fit, 2)           # never plans more than fits (beyond the two-iteration floor)
